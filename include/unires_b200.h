@@ -1,0 +1,231 @@
+/* unires_b200.h -- C ABI of the B200-native UniRes ADMM/CG hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer named
+ * d_* / documented "device" is a CUDA device pointer; volumes are float32,
+ * C-contiguous (X, Y, Z) with Z fastest, exactly the layout UniRes keeps
+ * (unires/_update.py:29 allocates (C,3,X,Y,Z); unires/_project.py:78 adds
+ * the two leading singleton dims).  All calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*) unless stated otherwise.  Return value:
+ * UR_OK or an error code; ur_last_error() gives the message.
+ *
+ * "Reference" citations are relative to the upstream repo brudfors/UniRes
+ * (file:line); "nitorch" is its pinned third-party dependency
+ * (setup.py:11), whose functions these entry points replace at the call
+ * sites listed.
+ */
+#ifndef UNIRES_B200_H
+#define UNIRES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UR_MAX_TAPS 32     /* max length of one separable slice-profile factor */
+#define UR_MAX_OBS 8       /* max observations (repeats) of one channel        */
+#define UR_MAX_CHANNELS 16 /* max channels in one JTV-prox launch              */
+#define UR_CG_MAX_ITER 256 /* capacity of the on-device CG objective trace     */
+
+typedef void *ur_stream;
+
+enum {
+  UR_OK = 0,
+  UR_ERR_ARG = 1,         /* bad argument (the reference raises ValueError)   */
+  UR_ERR_CUDA = 2,        /* CUDA runtime failure                             */
+  UR_ERR_UNSUPPORTED = 3  /* valid in nitorch, not implemented here           */
+};
+
+enum { UR_SUPERRES = 0, UR_DENOISE = 1 };        /* unires/_project.py:125 */
+enum { UR_OP_A = 0, UR_OP_AT = 1, UR_OP_ATA = 2 }; /* unires/_project.py:123 */
+/* nitorch cg `stop` (Appendix A.7 / Q1 of SURVEY.md): NONE = tolerance 0,
+ * RESIDUAL = sqrt(r.z) ('e'), ENERGY = 0.5 x'Ax - b'x (what 'max_gain' selects) */
+enum { UR_STOP_NONE = 0, UR_STOP_RESIDUAL = 1, UR_STOP_ENERGY = 2 };
+
+const char *ur_last_error(void);
+int ur_version(void);
+/* device in use: SM count and compute capability */
+int ur_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- finite
+ * differences: nitorch.spatial.im_gradient / im_divergence, 'forward',
+ * bound 'zero' (unires/_project.py:314-315; unires/_update.py:132,168,176,
+ * 188,419).  grad/vec are (3, X, Y, Z).                                    */
+int ur_im_gradient(const float *d_dat, float *d_grad, const int32_t dim[3],
+                   const float vx[3], ur_stream stream);
+int ur_im_divergence(const float *d_vec, float *d_div, const int32_t dim[3],
+                     const float vx[3], ur_stream stream);
+/* _DtD (unires/_project.py:300-317): out = div(grad(dat)) in one pass */
+int ur_dtd(const float *d_dat, float *d_out, const int32_t dim[3],
+           const float vx[3], ur_stream stream);
+
+/* ---------------------------------------------------------------- resampling:
+ * nitorch.spatial.grid_pull / grid_push, bound 'zero' (unires/_project.py:
+ * 164,172,174,179,183,185,187,188).  order 0|1; extrapolate 0 = the
+ * reference's setting.  `grid` is the dense (ox,oy,oz,3) voxel-coordinate
+ * field of nitorch.affine_grid; the *_affine variants evaluate the same
+ * coordinates in-kernel from the 3x4 matrix (row major) and never touch a
+ * dense grid (replaces unires/_project.py:159).  push ACCUMULATES
+ * scale*value into d_out (zero it first for a plain push).                 */
+int ur_grid_pull(const float *d_src, const int32_t sdim[3], const float *d_grid,
+                 float *d_out, const int32_t odim[3], int order, int extrapolate,
+                 ur_stream stream);
+int ur_grid_push(const float *d_in, const int32_t idim[3], const float *d_grid,
+                 float *d_out, const int32_t sdim[3], int order, int extrapolate,
+                 float scale, ur_stream stream);
+int ur_affine_pull(const float *d_src, const int32_t sdim[3], const float mat[12],
+                   float *d_out, const int32_t odim[3], int order, int extrapolate,
+                   ur_stream stream);
+int ur_affine_push(const float *d_in, const int32_t idim[3], const float mat[12],
+                   float *d_out, const int32_t sdim[3], int order, int extrapolate,
+                   float scale, ur_stream stream);
+/* nitorch.spatial.affine_grid materialised (only for callers that index the
+ * grid, unires/run.py:169-174): d_grid is (ox,oy,oz,3).                    */
+int ur_affine_grid(const float mat[12], float *d_grid, const int32_t odim[3],
+                   ur_stream stream);
+
+/* ---------------------------------------------------------------- slice profile:
+ * F.conv3d / F.conv_transpose3d with a 1->1 channel separable kernel and
+ * stride = ratio (unires/_project.py:153-154); valid padding.  One axis per
+ * call: odim[axis] = (idim[axis]-K)/stride+1 (conv) or (idim[axis]-1)*stride+K
+ * (transpose); the other two extents are unchanged.                        */
+int ur_conv_axis(const float *d_in, const int32_t idim[3], float *d_out, int axis,
+                 const float *ker, int K, int stride, int transpose,
+                 ur_stream stream);
+/* _apply_scaling (unires/_project.py:9-24): out = exp(+-scl) * in, sign
+ * alternating along `axis` (even slices +).                                */
+int ur_apply_scaling(const float *d_in, float *d_out, const int32_t dim[3],
+                     float scl, int axis, ur_stream stream);
+
+/* ---------------------------------------------------------------- projection
+ * operator.  Plain-data image of unires.struct._proj_op (unires/struct.py:
+ * 36-54) after _proj_info (unires/_project.py:193-297), with smo_ker split
+ * into its three 1-D factors (it is an outer product, _project.py:277) and
+ * `mat` = mat_y^-1 . rigid . mat_yx (super-resolution) or mat_y^-1 . rigid .
+ * mat_x (denoising) solved ONCE in float64 and cast to float32 exactly as
+ * unires/_project.py:147,150,159 does on every call.                       */
+typedef struct ur_proj {
+  int32_t method; /* UR_SUPERRES | UR_DENOISE */
+  int32_t dim_y[3];
+  int32_t dim_x[3];
+  int32_t dim_yx[3];
+  int32_t ratio[3];
+  int32_t ksize[3];
+  float ker[3][UR_MAX_TAPS];
+  float mat[12];
+  float scl;         /* even/odd log-scaling, 0 = off (po.scl)   */
+  int32_t dim_thick; /* axis the scaling alternates along        */
+} ur_proj;
+
+/* 1 if the operator is "lattice aligned" (mat = identity + integer shift):
+ * pull/push degenerate to crop/zero-pad and the fused kernels apply.       */
+int ur_proj_is_lattice(const ur_proj *po);
+size_t ur_proj_workspace_bytes(const ur_proj *po);
+/* _proj_apply (unires/_project.py:99-190): op in {A, At, AtA}.
+ * A: in = y-space, out = x-space; At: reverse; AtA: y -> y.  out = result
+ * (overwritten).                                                           */
+int ur_proj_apply(int op, const ur_proj *po, const float *d_in, float *d_out,
+                  void *d_ws, size_t ws_bytes, ur_stream stream);
+/* out += scale * op(in) for op in {At, AtA}: the accumulation of
+ * unires/_update.py:125-128 (tmp += tau * At x) without a temporary.      */
+int ur_proj_accumulate(int op, const ur_proj *po, const float *d_in, float *d_out,
+                       float scale, void *d_ws, size_t ws_bytes, ur_stream stream);
+
+/* ---------------------------------------------------------------- CG left-hand
+ * side of one channel: v -> sum_n tau_n An'An v + rho lam^2 D'D v
+ * (unires/_project.py:73-87 with operator 'AtA'; do_proj = 0 is the
+ * operator 'none' branch, :76-77, A = identity).                          */
+typedef struct ur_lhs {
+  int32_t dim_y[3];
+  float vx[3];
+  float rho_lam2; /* rho * lam^2, formed in float32 by the host as the reference does */
+  int32_t do_proj;
+  int32_t n_obs;
+  float tau[UR_MAX_OBS];
+  ur_proj obs[UR_MAX_OBS];
+} ur_lhs;
+
+size_t ur_lhs_workspace_bytes(const ur_lhs *lhs);
+/* out = lhs(v).  If d_dot != NULL also writes sum(v*out) (float64). */
+int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, double *d_dot,
+                 void *d_ws, size_t ws_bytes, ur_stream stream);
+
+/* ---------------------------------------------------------------- CG solve:
+ * nitorch.core.optim.cg as called at unires/_update.py:142-148 (in place on
+ * x, identity preconditioner, float64 dot products), run entirely on the
+ * device: no host synchronisation between iterations; the stop test
+ * |gain| < tolerance is evaluated on the device and later launches of the
+ * same solve early-out.                                                    */
+typedef struct ur_cg_opts {
+  int32_t max_iter;  /* sett.cgs_max_iter (unires/struct.py:65), <= UR_CG_MAX_ITER */
+  int32_t stop_rule; /* UR_STOP_* */
+  double tolerance;  /* sett.cgs_tol (unires/struct.py:66) */
+  int32_t variant;   /* kernel selection: 0 = auto (for A/B measurements) */
+} ur_cg_opts;
+
+size_t ur_cg_workspace_bytes(const ur_lhs *lhs);
+int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_ws,
+                size_t ws_bytes, const ur_cg_opts *opts, ur_stream stream);
+/* Synchronises `stream`, then returns the iterate count and the objective
+ * trace obj[0..n_iter] (as many as fit in n_obj).                          */
+int ur_cg_fetch(const void *d_ws, int32_t *n_iter, double *obj, int32_t n_obj,
+                ur_stream stream);
+
+/* building blocks for cg() with an arbitrary host callable as A */
+int ur_dot(const float *d_a, const float *d_b, size_t n, double *d_out,
+           ur_stream stream);
+/* x += alpha p ; r -= alpha Ap ; *d_rr = sum(r*r).  alpha read from device */
+int ur_cg_update_xr(float *d_x, float *d_r, const float *d_p, const float *d_Ap,
+                    size_t n, const double *d_alpha, double *d_rr,
+                    ur_stream stream);
+/* p = beta p + r, beta read from device */
+int ur_cg_update_p(float *d_p, const float *d_r, size_t n, const double *d_beta,
+                   ur_stream stream);
+
+/* ---------------------------------------------------------------- ADMM pieces
+ * (unires/_update.py:105-195).                                             */
+/* RHS of the y-update (:124-133): b = acc - lam * div(w_c - rho z_c), where
+ * acc = sum_n tau_n An' x_n has already been accumulated into d_b by the
+ * caller (ur_proj_apply + ur_axpy) or is taken as tau*x when do_proj = 0.  */
+int ur_admm_rhs(float *d_b, const float *d_w, const float *d_z,
+                const int32_t dim[3], const float vx[3], float lam, float rho,
+                ur_stream stream);
+/* y += a * x (float32) */
+int ur_axpy(float *d_y, const float *d_x, float a, size_t n, ur_stream stream);
+
+/* z- and w-update in ONE pass over all channels (:160-193):
+ *   g_c = lam_c grad(y_c)  [alpha != 1: g_c = alpha g_c + (1-alpha) z_c_old]
+ *   u_c = w_c/rho + g_c; s = sqrt(sum_c |u_c|^2);
+ *   f = max(s - 1/rho, 0)/(s + 1e-7); z_c = f u_c; w_c += rho (g_c - z_c)
+ * d_y: array of C device pointers (host array), d_z,d_w: (C,3,X,Y,Z),
+ * d_jtv: (X,Y,Z) receives f.                                               */
+int ur_jtv_prox(const float *const *d_y, float *d_z, float *d_w, float *d_jtv,
+                int n_channels, const float *lam, const int32_t dim[3],
+                const float vx[3], float rho, float alpha, ur_stream stream);
+/* channel-sharded variant (multi-GPU): (1) accumulate this rank's
+ * sum_c |u_c|^2 into d_nrm2; (all-reduce d_nrm2 across ranks); (2) apply. */
+int ur_jtv_norm2(const float *const *d_y, const float *d_z, const float *d_w,
+                 float *d_nrm2, int n_channels, const float *lam,
+                 const int32_t dim[3], const float vx[3], float rho, float alpha,
+                 int accumulate, ur_stream stream);
+int ur_jtv_apply(const float *const *d_y, float *d_z, float *d_w,
+                 const float *d_nrm2, float *d_jtv, int n_channels,
+                 const float *lam, const int32_t dim[3], const float vx[3],
+                 float rho, float alpha, ur_stream stream);
+
+/* objective (_compute_nll, unires/_update.py:396-427), float64 sums.
+ * data term of one observation: *d_out (+)= 0.5 tau sum_{x!=0} (x - Ay)^2,
+ * d_Ay already projected.  prior: accumulate sum_c sum_d (lam_c grad y_c)_d^2
+ * into d_e (X,Y,Z), then ur_sqrt_sum.                                      */
+int ur_nll_data(const float *d_x, const float *d_Ay, size_t n, float tau,
+                double *d_out, int accumulate, ur_stream stream);
+int ur_nll_prior_energy(const float *const *d_y, float *d_e, int n_channels,
+                        const float *lam, const int32_t dim[3], const float vx[3],
+                        int accumulate, ur_stream stream);
+int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIRES_B200_H */

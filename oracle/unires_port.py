@@ -1,0 +1,258 @@
+"""Independent CPU restatement of UniRes' ADMM/CG hot path (the travelling oracle).
+
+TEST INFRASTRUCTURE, PARITY UNPINNED (see oracle/__init__.py).  The GPU box
+has no /root/reference, so the parity tests there compare the CUDA path with
+THIS port; in the build container the port itself is checked against the
+reference's unmodified files run on the same shim primitives
+(tests/test_oracle_vs_reference.py) and against tests/golden/.
+
+Reference lines restated (relative to /root/reference):
+  ProjGeometry / proj_info   unires/_project.py:193-297
+  apply_scaling              unires/_project.py:9-24
+  proj_apply                 unires/_project.py:99-190
+  proj                       unires/_project.py:54-96
+  dtd                        unires/_project.py:300-317
+  admm_aux / step_size       unires/_update.py:17-64
+  compute_nll                unires/_update.py:396-427
+  update_admm                unires/_update.py:105-195
+"""
+import math
+import types
+
+import torch
+from torch.nn import functional as F
+
+from oracle.nitorch_shim import spatial as S
+from oracle.nitorch_shim.core import kernels as K
+from oracle.nitorch_shim.core import optim as O
+
+F64 = torch.float64
+
+
+# ----------------------------------------------------------------------------
+# containers (same field names as unires/struct.py so that one scenario can be
+# handed to the reference files, to this port and to the CUDA product)
+# ----------------------------------------------------------------------------
+def Observation(dat, mat, tau, po=None, mu=1.0, sd=1.0, ct=False):
+    return types.SimpleNamespace(dat=dat, dim=tuple(dat.shape), mat=mat, tau=tau,
+                                 po=po, mu=mu, sd=sd, ct=ct, rigid_q=None,
+                                 label=None)
+
+
+def Recon(dat, mat, lam):
+    return types.SimpleNamespace(dat=dat, dim=tuple(dat.shape), mat=mat, lam=lam,
+                                 lam0=lam, label=None)
+
+
+def Settings(**kw):
+    s = types.SimpleNamespace(alpha=1.0, bound='zero', cgs_max_iter=20,
+                              cgs_tol=1e-3, cgs_verbose=False, device='cpu',
+                              diff='forward', do_proj=True, do_print=0,
+                              interpolation='linear',
+                              method='super-resolution', rho=None, rho_scl=1.0,
+                              tolerance=1e-4, profile_ip=2, profile_tp=0,
+                              gap=0.0)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+# ----------------------------------------------------------------------------
+# operator geometry  (unires/_project.py:193-297)
+# ----------------------------------------------------------------------------
+def proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0,
+              gap=0.0, scl=0.0):
+    po = types.SimpleNamespace()
+    mat_y = mat_y.to(F64)
+    mat_x = mat_x.to(F64)
+    nd = len(dim_y)
+    po.dim_y = tuple(int(d) for d in dim_y)
+    po.dim_x = tuple(int(d) for d in dim_x)
+    po.mat_y, po.mat_x = mat_y, mat_x
+    po.vx_y, po.vx_x = S.voxel_size(mat_y), S.voxel_size(mat_x)
+    po.rigid = torch.eye(nd + 1, dtype=F64) if rigid is None else rigid.to(F64)
+    # thick-slice axis: first maximum of the input voxel size (:241)
+    thick = int(torch.max(po.vx_x, dim=0)[1])
+    po.dim_thick = thick
+    profile = [prof_ip] * nd
+    profile[thick] = prof_tp
+    gaps = [0.0] * nd
+    gaps[thick] = gap
+    # integer decimation factor per axis (:266-268)
+    y2x = torch.linalg.solve(mat_y, mat_x)[:nd, :nd]
+    ratio = (y2x ** 2).sum(0).sqrt().ceil().clamp(1)
+    po.ratio = tuple(int(r) for r in ratio.tolist())
+    # intermediate grid: x orientation, voxel size vx_x / ratio (:269-271)
+    shrink = torch.diag(torch.cat([1 / ratio, torch.ones(1, dtype=F64)]))
+    mat_yx = mat_x @ shrink
+    dim_yx = [(dx - 1) * r + 1 for dx, r in zip(po.dim_x, po.ratio)]
+    # slice profile; ratio 1 -> dirac (:273-277)
+    fwhm = [(1.0 - g) * r for g, r in zip(gaps, po.ratio)]
+    profile = [-1 if r == 1 else p for p, r in zip(profile, po.ratio)]
+    po.smo_ker = K.smooth(profile, fwhm, sep=False, dtype=torch.float32)
+    # pad the intermediate grid so the valid strided conv lands on dim_x (:280-285)
+    off = [-((k - 1) // 2) for k in po.smo_ker.shape[-nd:]]
+    shift = torch.eye(nd + 1, dtype=F64)
+    shift[:nd, -1] = torch.tensor(off, dtype=F64)
+    po.mat_yx = mat_yx @ shift
+    po.dim_yx = tuple(d + 2 * abs(o) for d, o in zip(dim_yx, off))
+    po.scl = scl if isinstance(scl, torch.Tensor) else torch.tensor(scl, dtype=torch.float32)
+    return po
+
+
+def apply_scaling(dat, scl, dim):
+    """exp(+scl) on even, exp(-scl) on odd slices along spatial axis dim (:9-24)."""
+    n = dat.shape[dat.dim() - 3 + dim]
+    sign = torch.ones(n, dtype=dat.dtype)
+    sign[1::2] = -1
+    shape = [1] * dat.dim()
+    shape[dat.dim() - 3 + dim] = n
+    return dat * torch.exp(scl * sign).reshape(shape)
+
+
+def proj_apply(operator, dat, po, method='super-resolution', bound='zero',
+               interpolation='linear'):
+    """dat is (1,1,X,Y,Z).  A = S.C.P ; At = P'.C'.S ; AtA = P'C' S^2 C P  (:99-190)."""
+    if operator not in ('A', 'At', 'AtA', 'none'):
+        raise ValueError('Undefined operator')
+    if method not in ('denoising', 'super-resolution'):
+        raise ValueError('Undefined method')
+    if operator == 'none':
+        return dat
+    sr = method == 'super-resolution'
+    src_mat, src_dim = (po.mat_yx, po.dim_yx) if sr else (po.mat_x, po.dim_x)
+    vox = torch.linalg.solve(po.mat_y, po.rigid @ src_mat)  # :147,150
+    grid = S.affine_grid(vox.to(dat.dtype), src_dim)[None]
+    kw = dict(bound=bound, extrapolate=False, interpolation=interpolation)
+    scl, thick = po.scl, int(po.dim_thick)
+    ker, stride = po.smo_ker.to(dat.dtype), po.ratio
+
+    def down(v):
+        return F.conv3d(v, ker, stride=stride) if sr else v
+
+    def up(v):
+        return F.conv_transpose3d(v, ker, stride=stride) if sr else v
+
+    def scale(v, s):
+        return apply_scaling(v, s, thick) if (sr and scl != 0) else v
+
+    if operator == 'A':
+        return scale(down(S.grid_pull(dat, grid, **kw)), scl)
+    if operator == 'At':
+        return S.grid_push(up(scale(dat, scl)), grid, shape=po.dim_y, **kw)
+    mid = scale(down(S.grid_pull(dat, grid, **kw)), 2 * scl)
+    return S.grid_push(up(mid), grid, shape=po.dim_y, **kw)
+
+
+def dtd(dat, vx_y, bound='zero', diff='forward'):
+    return S.im_divergence(S.im_gradient(dat, vx=vx_y, bound=bound, which=diff),
+                           vx=vx_y, bound=bound, which=diff)
+
+
+def proj(operator, dat, x, y, method='super-resolution', do=True, rho=1, n=0,
+         vx_y=None, interpolation='linear', bound='zero', diff='forward'):
+    """x: list of observations of ONE channel, y: that channel's recon (:54-96)."""
+    op = operator if do else 'none'
+    kw = dict(method=method, bound=bound, interpolation=interpolation)
+    if operator != 'AtA':
+        return proj_apply(op, dat[None, None], x[n].po, **kw)[0, 0]
+    out = None
+    for obs in x:
+        term = obs.tau * proj_apply(op, dat[None, None], obs.po, **kw)
+        out = term if out is None else out + term
+    out = out[0, 0]
+    return out + rho * y.lam ** 2 * dtd(dat, vx_y, bound=bound, diff=diff)
+
+
+# ----------------------------------------------------------------------------
+# solver  (unires/_update.py)
+# ----------------------------------------------------------------------------
+def admm_aux(y):
+    shape = (len(y), 3) + tuple(y[0].dim)
+    return torch.zeros(shape), torch.zeros(shape)
+
+
+def step_size(x, y, sett):
+    """rho = rho_scl * sqrt(mean tau) / mean lam unless fixed (:35-64)."""
+    rho = sett.rho
+    if any(obs.ct for xc in x for obs in xc):
+        rho = 1.0
+    if rho is not None:
+        return torch.tensor(rho, dtype=torch.float32)
+    lam = torch.tensor([float(yc.lam) for yc in y], dtype=torch.float32)
+    tau = torch.tensor([float(o.tau) for xc in x for o in xc], dtype=torch.float32)
+    return sett.rho_scl * torch.sqrt(tau.mean()) / lam.mean()
+
+
+def compute_nll(x, y, sett, rho=None):
+    """(nll, nll_xy, nll_y) in float64 (:396-427)."""
+    vx_y = S.voxel_size(y[0].mat).float()
+    nll_xy = torch.zeros((), dtype=F64)
+    prior = None
+    for xc, yc in zip(x, y):
+        for n, obs in enumerate(xc):
+            fit = proj('A', yc.dat, xc, yc, n=n, method=sett.method, do=sett.do_proj,
+                       bound=sett.bound, interpolation=sett.interpolation)
+            msk = obs.dat != 0
+            nll_xy = nll_xy + 0.5 * obs.tau * torch.sum((obs.dat[msk] - fit[msk]) ** 2, dtype=F64)
+        g = yc.lam * S.im_gradient(yc.dat, vx=vx_y, bound=sett.bound, which=sett.diff)
+        e = torch.sum(g ** 2, dim=0)
+        prior = e if prior is None else prior + e
+    nll_y = torch.sum(torch.sqrt(prior), dtype=F64)
+    return nll_xy + nll_y, nll_xy, nll_y
+
+
+def update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett, cg_stop='max_gain',
+                cg_record=None):
+    """One ADMM iteration: y by CG per channel, objective, JTV prox z, dual w (:105-195).
+
+    Returns (y, z, w, jtv, obj, cg_iters)."""
+    vx_y = S.voxel_size(y[0].mat).float()
+    alpha = float(sett.alpha)
+    C = len(x)
+    kw = dict(method=sett.method, do=sett.do_proj, bound=sett.bound,
+              interpolation=sett.interpolation)
+    cg_iters = []
+    # ---- y ----
+    for c in range(C):
+        rhs = torch.zeros_like(tmp)
+        for n, obs in enumerate(x[c]):
+            rhs += obs.tau * proj('At', obs.dat, x[c], y[c], n=n, **kw)
+        rhs -= y[c].lam * S.im_divergence(w[c] - rho * z[c], vx=vx_y,
+                                          bound=sett.bound, which=sett.diff)
+
+        def lhs(v, c=c):
+            return proj('AtA', v, x[c], y[c], rho=rho, vx_y=vx_y, diff=sett.diff, **kw)
+
+        rec = (lambda it, xi, c=c: cg_record(c, it, xi)) if cg_record else None
+        O.cg(A=lhs, b=rhs, x=y[c].dat, verbose=sett.cgs_verbose,
+             max_iter=sett.cgs_max_iter, stop=cg_stop, inplace=True,
+             precond=lambda v: v, tolerance=sett.cgs_tol, record=rec)
+        cg_iters.append(O.cg.last_n_iter)
+    # ---- objective ----
+    if sett.tolerance > 0:
+        obj[n_iter, 0], obj[n_iter, 1], obj[n_iter, 2] = compute_nll(x, y, sett, rho)
+    # ---- z (JTV prox) ----
+    z_old = z.clone() if alpha != 1 else None
+
+    def scaled_grad(c):
+        g = y[c].lam * S.im_gradient(y[c].dat, vx=vx_y, bound=sett.bound, which=sett.diff)
+        if alpha != 1:
+            g = alpha * g + (1 - alpha) * z_old[c]
+        return g
+
+    nrm = torch.zeros_like(tmp)
+    for c in range(C):
+        nrm += torch.sum((w[c] / rho + scaled_grad(c)) ** 2, dim=0)
+    nrm.sqrt_()
+    one = torch.tensor(1, dtype=torch.float32)
+    tiny = torch.tensor(1e-7, dtype=torch.float32)
+    jtv = (nrm - one / rho).clamp_min(0) / (nrm + tiny)
+    for c in range(C):
+        g = scaled_grad(c)
+        for d in range(3):
+            z[c, d] = jtv * (w[c, d] / rho + g[d])
+    # ---- w ----
+    for c in range(C):
+        w[c] += rho * (scaled_grad(c) - z[c])
+    return y, z, w, jtv, obj, cg_iters

@@ -1,0 +1,274 @@
+"""Projection operators of the hot path -- same names, arguments and error
+behaviour as unires/_project.py, executed by the sm_100a kernels.
+
+    _proj_info      unires/_project.py:193-297   operator construction
+    _proj_apply     unires/_project.py:99-190    A, At, AtA of one observation
+    _proj           unires/_project.py:54-96     dispatcher incl. the CG lhs
+    _DtD            unires/_project.py:300-317
+    _apply_scaling  unires/_project.py:9-24
+    _check_adjoint  unires/_project.py:27-51
+
+Differences in *how* (not what): the 4x4 solve of :147 is done once per
+operator (cached) instead of on every application, no dense coordinate grid is
+built (:159), pull + slice-profile + push run as CUDA kernels of this package,
+and the CG left-hand side is available as a fused operator object
+(:class:`LhsOperator`) that `optim.cg` solves without host synchronisation.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, i3, f3, stream, require_cuda_f32
+from .kernels import smooth, separable_factors
+from .spatial import voxel_size
+from .struct import _proj_op
+
+_F64 = torch.float64
+
+
+# ---------------------------------------------------------------------------
+# operator construction
+# ---------------------------------------------------------------------------
+def _proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0, gap=0.0,
+               device='cpu', scl=0.0, samp=0):
+    """Describe the projection  y (dim_y, mat_y)  ->  x (dim_x, mat_x).
+
+    Returns a `_proj_op` with the reference's fields.  The geometry is tiny
+    float64 host arithmetic; tensors are placed on `device` like upstream."""
+    if samp:
+        raise NotImplementedError('samp > 0 (sub-sampling for the rigid update, '
+                                  'unires/_project.py:245-264) is out of scope')
+    po = _proj_op()
+    nd = len(dim_y)
+    cpu = lambda t: torch.as_tensor(t).detach().to('cpu', _F64)
+    m_y, m_x = cpu(mat_y), cpu(mat_x)
+    d_x = [int(v) for v in cpu(dim_x).tolist()]
+    d_y = [int(v) for v in cpu(dim_y).tolist()]
+    vx_x, vx_y = voxel_size(m_x), voxel_size(m_y)
+    # thick-slice axis = first arg-max of the observed voxel size
+    thick = int(torch.max(vx_x, dim=0)[1])
+    profile = [prof_ip] * nd
+    profile[thick] = prof_tp
+    slice_gap = [0.0] * nd
+    slice_gap[thick] = float(gap)
+    # per-axis integer decimation  ceil(|cols of mat_y^-1 mat_x|) >= 1
+    cols = torch.linalg.solve(m_y, m_x)[:nd, :nd]
+    ratio = [max(1, int(math.ceil(float(v)))) for v in cols.pow(2).sum(0).sqrt()]
+    # intermediate grid in x's orientation with voxels vx_x / ratio, padded by
+    # the kernel half-width so that the *valid* strided correlation lands on dim_x
+    kinds = [-1 if r == 1 else p for p, r in zip(profile, ratio)]
+    fwhm = [(1.0 - g) * r for g, r in zip(slice_gap, ratio)]
+    ker = smooth(kinds, fwhm, sep=False, dtype=torch.float32)
+    half = [(k - 1) // 2 for k in ker.shape[-nd:]]
+    scale = torch.diag(torch.tensor([1.0 / r for r in ratio] + [1.0], dtype=_F64))
+    shift = torch.eye(nd + 1, dtype=_F64)
+    shift[:nd, -1] = torch.tensor([-float(h) for h in half], dtype=_F64)
+    m_yx = m_x @ scale @ shift
+    d_yx = [(dx - 1) * r + 1 + 2 * h for dx, r, h in zip(d_x, ratio, half)]
+
+    dev = torch.device(device)
+    po.dim_y, po.dim_x, po.dim_yx = tuple(d_y), tuple(d_x), tuple(d_yx)
+    po.ratio = tuple(ratio)
+    po.mat_y, po.mat_x, po.mat_yx = m_y.to(dev), m_x.to(dev), m_yx.to(dev)
+    po.vx_y, po.vx_x = vx_y.to(dev), vx_x.to(dev)
+    po.rigid = (torch.eye(nd + 1, dtype=_F64) if rigid is None else cpu(rigid)).to(dev)
+    po.smo_ker = ker.to(dev)
+    po.dim_thick = torch.tensor(thick, device=dev)
+    po.scl = scl if isinstance(scl, torch.Tensor) else torch.tensor(scl, dtype=torch.float32,
+                                                                    device=dev)
+    return po
+
+
+def _version_key(*tensors):
+    return tuple((id(t), t._version) if isinstance(t, torch.Tensor) else t for t in tensors)
+
+
+def proj_struct(po, method):
+    """ctypes image (ur_proj) of a `_proj_op`; cached on the object."""
+    if method not in _lib.METHODS:
+        raise ValueError('Undefined method')
+    src_mat = po.mat_yx if method == 'super-resolution' else po.mat_x
+    key = (method,) + _version_key(po.mat_y, src_mat, po.rigid, po.smo_ker, po.scl,
+                                   po.dim_thick)
+    cache = po.__dict__.setdefault('_c_cache', {})
+    hit = cache.get(method)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    cpu = lambda t: torch.as_tensor(t).detach().to('cpu', _F64)
+    # mat_y \ (rigid . mat_src) in float64, then float32 -- as :147/:150/:159
+    vox = torch.linalg.solve(cpu(po.mat_y), cpu(po.rigid) @ cpu(src_mat)).to(torch.float32)
+    s = _lib.ur_proj()
+    s.method = _lib.METHODS[method]
+    s.dim_y = i3(po.dim_y)
+    s.dim_x = i3(po.dim_x)
+    s.dim_yx = i3(po.dim_yx if po.dim_yx is not None else po.dim_x)
+    s.ratio = i3(po.ratio if po.ratio is not None else (1, 1, 1))
+    factors = separable_factors(po.smo_ker) if po.smo_ker is not None else [[1.0]] * 3
+    for a, f in enumerate(factors):
+        if len(f) > _lib.UR_MAX_TAPS:
+            raise NotImplementedError('slice profile longer than %d taps' % _lib.UR_MAX_TAPS)
+        s.ksize[a] = len(f)
+        for t, v in enumerate(f):
+            s.ker[a][t] = v
+    for k, v in enumerate(vox[:3, :].reshape(-1).tolist()):
+        s.mat[k] = v
+    s.scl = float(po.scl) if po.scl is not None else 0.0
+    s.dim_thick = int(po.dim_thick) if po.dim_thick is not None else 0
+    cache[method] = (key, s)
+    return s
+
+
+# ---------------------------------------------------------------------------
+# single-observation operator
+# ---------------------------------------------------------------------------
+def _proj_apply(operator, dat, po, method='super-resolution', bound='zero',
+                interpolation='linear'):
+    """Apply A, At or AtA of one observation to `dat` (1, 1, X, Y, Z)."""
+    if operator not in ('A', 'At', 'AtA', 'none'):
+        raise ValueError('Undefined operator')
+    if method not in ('denoising', 'super-resolution'):
+        raise ValueError('Undefined method')
+    if operator == 'none':
+        return dat
+    if bound not in ('zero', 'zeros'):
+        raise NotImplementedError('bound %r' % (bound,))
+    if interpolation not in ('linear', 1):
+        raise NotImplementedError('interpolation %r' % (interpolation,))
+    d = require_cuda_f32(dat, 'dat')
+    s = proj_struct(po, method)
+    src = tuple(po.dim_y) if operator != 'At' else tuple(po.dim_x)
+    dst = tuple(po.dim_x) if operator == 'A' else tuple(po.dim_y)
+    if tuple(d.shape[-3:]) != src or d.numel() != src[0] * src[1] * src[2]:
+        raise ValueError('_proj_apply(%s): data shape %s does not match %s'
+                         % (operator, tuple(d.shape), src))
+    out = torch.empty((1, 1) + dst, dtype=torch.float32, device=d.device)
+    nbytes = lib.ur_proj_workspace_bytes(C.byref(s))
+    ws = _lib.workspace(nbytes, d.device, 'proj')
+    check(lib.ur_proj_apply(_lib.OPS[operator], C.byref(s), ptr(d), ptr(out), ptr(ws),
+                            ws.numel(), stream()))
+    return out
+
+
+def _apply_scaling(dat, scl, dim):
+    """Even/odd slice scaling exp(+-scl) along spatial axis `dim`."""
+    d = require_cuda_f32(dat, 'dat')
+    out = torch.empty_like(d)
+    shape = tuple(d.shape[-3:])
+    lead = d.numel() // (shape[0] * shape[1] * shape[2])
+    dv, ov = d.reshape((lead,) + shape), out.reshape((lead,) + shape)
+    for k in range(lead):
+        check(lib.ur_apply_scaling(ptr(dv[k]), ptr(ov[k]), i3(shape), float(scl), int(dim),
+                                   stream()))
+    return out
+
+
+def _DtD(dat, vx_y, bound='zero', diff='forward'):
+    """div(grad(dat)): forward differences, zero bound, one fused pass."""
+    if bound not in ('zero', 'zeros') or diff != 'forward':
+        raise NotImplementedError('only bound="zero", diff="forward"')
+    d = require_cuda_f32(dat, 'dat')
+    out = torch.empty_like(d)
+    check(lib.ur_dtd(ptr(d), ptr(out), i3(d.shape), f3(_floats(vx_y, 3)), stream()))
+    return out
+
+
+def _floats(v, n=None):
+    if isinstance(v, torch.Tensor):
+        v = v.detach().to('cpu', torch.float32).flatten().tolist()
+    elif isinstance(v, (int, float)):
+        v = [float(v)]
+    else:
+        v = [float(a) for a in v]
+    if n is not None and len(v) == 1:
+        v = v * n
+    return v
+
+
+def _f32(v):
+    """Python/torch scalar -> numpy float32 (value as the reference holds it)."""
+    return np.float32(float(v))
+
+
+# ---------------------------------------------------------------------------
+# CG left-hand side
+# ---------------------------------------------------------------------------
+class LhsOperator:
+    """dat -> sum_n tau_n An'An dat + rho lam^2 D'D dat  for one channel.
+
+    Built from the same arguments the reference's `lhs` closure captures
+    (unires/_update.py:140-141).  Callable like that closure; `optim.cg`
+    recognises it and runs the whole solve on the device."""
+
+    def __init__(self, x, y, method='super-resolution', do=True, rho=1, vx_y=None,
+                 interpolation='linear', bound='zero', diff='forward'):
+        if method not in ('denoising', 'super-resolution'):
+            raise ValueError('Undefined method')
+        if bound not in ('zero', 'zeros') or diff != 'forward':
+            raise NotImplementedError('only bound="zero", diff="forward"')
+        if interpolation not in ('linear', 1):
+            raise NotImplementedError('interpolation %r' % (interpolation,))
+        if len(x) > _lib.UR_MAX_OBS:
+            raise NotImplementedError('more than %d observations per channel' % _lib.UR_MAX_OBS)
+        s = _lib.ur_lhs()
+        dim_y = tuple(y.dim) if y.dim is not None else tuple(y.dat.shape)
+        s.dim_y = i3(dim_y)
+        s.vx = f3(_floats(vx_y if vx_y is not None else 1.0, 3))
+        # rho * lam ** 2 evaluated in float32 like the reference's 0-dim tensors (:87)
+        s.rho_lam2 = float(_f32(rho) * (_f32(y.lam) * _f32(y.lam)))
+        s.do_proj = 1 if do else 0
+        s.n_obs = len(x)
+        for n, obs in enumerate(x):
+            s.tau[n] = float(obs.tau)
+            if do:
+                C.memmove(C.byref(s.obs[n]), C.byref(proj_struct(obs.po, method)),
+                          C.sizeof(_lib.ur_proj))
+        self.c = s
+        self.dim_y = dim_y
+        self.cg_bytes = lib.ur_cg_workspace_bytes(C.byref(s))
+        self.lhs_bytes = lib.ur_lhs_workspace_bytes(C.byref(s))
+        if self.cg_bytes == 0 or self.lhs_bytes == 0:
+            check(_lib.UR_ERR_ARG)
+
+    def __call__(self, dat, dot=None):
+        d = require_cuda_f32(dat, 'dat')
+        if tuple(d.shape) != self.dim_y:
+            raise ValueError('lhs: data shape %s != %s' % (tuple(d.shape), self.dim_y))
+        out = torch.empty_like(d)
+        ws = _lib.workspace(self.lhs_bytes, d.device, 'lhs')
+        check(lib.ur_lhs_apply(C.byref(self.c), ptr(d), ptr(out),
+                               ptr(dot) if dot is not None else None, ptr(ws), ws.numel(),
+                               stream()))
+        return out
+
+
+def _proj(operator, dat, x, y, method='super-resolution', do=True, rho=1, n=0, vx_y=None,
+          interpolation='linear', bound='zero', diff='forward'):
+    """Project by A, At (observation n) or by the CG left-hand side ('AtA')."""
+    if operator == 'AtA':
+        op = LhsOperator(x, y, method=method, do=do, rho=rho, vx_y=vx_y,
+                         interpolation=interpolation, bound=bound, diff=diff)
+        return op(dat)
+    if operator not in ('A', 'At', 'none'):
+        raise ValueError('Undefined operator')
+    if not do:
+        return dat
+    return _proj_apply(operator, dat[None, None, ...], x[n].po, method=method, bound=bound,
+                       interpolation=interpolation)[0, 0, ...]
+
+
+def _check_adjoint(po, method, bound, interpolation, dtype=torch.float32):
+    """<Ay, x> - <At x, y> for seeded uniform inputs; prints and returns it."""
+    if dtype != torch.float32:
+        raise NotImplementedError('the CUDA operators are float32')
+    device = po.smo_ker.device
+    gen = torch.Generator(device='cpu').manual_seed(0)
+    x = torch.rand((1, 1) + tuple(po.dim_x), generator=gen).to(device)
+    y = torch.rand((1, 1) + tuple(po.dim_y), generator=gen).to(device)
+    Ay = _proj_apply('A', y, po, method=method, bound=bound, interpolation=interpolation)
+    Atx = _proj_apply('At', x, po, method=method, bound=bound, interpolation=interpolation)
+    val = torch.sum(Ay * x, dtype=_F64) - torch.sum(Atx * y, dtype=_F64)
+    print('<Ay, x> - <Atx, y> = {}'.format(val))
+    return val

@@ -1,0 +1,194 @@
+"""The ADMM iteration of UniRes on the sm_100a kernels -- same function names,
+arguments, in-place behaviour and return values as unires/_update.py:
+
+    _admm_aux      unires/_update.py:17-32
+    _step_size     unires/_update.py:35-64
+    _compute_nll   unires/_update.py:396-427
+    _update_admm   unires/_update.py:105-195
+
+Per ADMM iteration the reference launches O(100) ATen kernels per channel and
+synchronises the host in every CG iteration; here the y-update is one
+device-resident CG solve per channel (`optim.cg_fused`), the objective is two
+reductions and the z/w updates are ONE pass over all channels
+(`ur_jtv_prox`).  `_update_admm_sharded` is the multi-GPU form: channels are
+sharded over ranks and only the JTV coupling field and the objective scalars
+cross NVLink.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, i3, f3, stream, require_cuda_f32
+from ._project import LhsOperator, _proj, _floats, proj_struct
+from .optim import cg, cg_fused, stop_rule
+from .spatial import voxel_size
+
+
+def _admm_aux(y, sett):
+    """z, w = zeros (C, 3, X, Y, Z) float32 on sett.device."""
+    shape = (len(y), 3) + tuple(y[0].dim)
+    z = torch.zeros(shape, dtype=torch.float32, device=sett.device)
+    w = torch.zeros(shape, dtype=torch.float32, device=sett.device)
+    return z, w
+
+
+def _has_ct(x):
+    return any(bool(obs.ct) for xc in x for obs in xc)
+
+
+def _step_size(x, y, sett, verbose=False):
+    """rho: sett.rho if given (1 with CT data), else rho_scl sqrt(mean tau) / mean lam."""
+    rho = 1.0 if _has_ct(x) else sett.rho
+    if rho is not None:
+        return torch.tensor(rho, device=sett.device, dtype=torch.float32)
+    lam = torch.tensor([float(yc.lam) for yc in y], dtype=torch.float32, device=sett.device)
+    tau = torch.tensor([float(o.tau) for xc in x for o in xc], dtype=torch.float32,
+                       device=sett.device)
+    return sett.rho_scl * torch.sqrt(torch.mean(tau)) / torch.mean(lam)
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def _geometry(y):
+    dim = tuple(y[0].dim) if y[0].dim is not None else tuple(y[0].dat.shape)
+    vx = _floats(voxel_size(y[0].mat).float(), 3)
+    return dim, vx
+
+
+def _nll_terms(x, y, sett, out, prior_field=None, accumulate_prior=False):
+    """Write nll_xy into out[1] and (unless prior_field is given) nll_y into out[2].
+
+    out: float64 CUDA tensor with >= 3 elements.  With `prior_field` the
+    per-voxel prior energy of these channels is accumulated there instead (the
+    caller all-reduces it and finishes with ur_sqrt_sum)."""
+    dim, vx = _geometry(y)
+    n_vox = dim[0] * dim[1] * dim[2]
+    out[1].zero_()
+    for c in range(len(x)):
+        for n, obs in enumerate(x[c]):
+            dat = require_cuda_f32(obs.dat, 'x.dat')
+            Ay = _proj('A', y[c].dat, x[c], y[c], n=n, method=sett.method, do=sett.do_proj,
+                       bound=sett.bound, interpolation=sett.interpolation)
+            check(lib.ur_nll_data(ptr(dat), ptr(Ay), dat.numel(), float(obs.tau),
+                                  ptr(out[1:2]), 1, stream()))
+    ys = [require_cuda_f32(yc.dat, 'y.dat') for yc in y]
+    lam = _lib.farr([float(yc.lam) for yc in y])
+    field = prior_field
+    if field is None:
+        field = _lib.workspace(4 * n_vox, ys[0].device, 'prior').view(torch.float32)[:n_vox]
+    for c0 in range(0, len(ys), _lib.UR_MAX_CHANNELS):
+        chunk = ys[c0:c0 + _lib.UR_MAX_CHANNELS]
+        acc = 1 if (c0 > 0 or accumulate_prior) else 0
+        check(lib.ur_nll_prior_energy(_ptr_array(chunk), ptr(field), len(chunk),
+                                      _lib.farr(list(lam)[c0:c0 + len(chunk)]), i3(dim), f3(vx),
+                                      acc, stream()))
+    if prior_field is None:
+        check(lib.ur_sqrt_sum(ptr(field), n_vox, ptr(out[2:3]), stream()))
+
+
+def _compute_nll(x, y, sett, rho, sum_dtype=torch.float64):
+    """(nll, nll_xy, nll_y): negative log posterior / likelihood / prior, float64."""
+    if sum_dtype != torch.float64:
+        raise NotImplementedError('sums are float64')
+    out = torch.zeros(3, dtype=torch.float64, device=y[0].dat.device)
+    _nll_terms(x, y, sett, out)
+    return out[1] + out[2], out[1], out[2]
+
+
+def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
+    """tmp = sum_n tau_n An' x_n - lam div(w_c - rho z_c)   (unires/_update.py:124-133)."""
+    tmp.zero_()
+    n_vox = tmp.numel()
+    for n, obs in enumerate(xc):
+        dat = require_cuda_f32(obs.dat, 'x.dat')
+        if not sett.do_proj:
+            check(lib.ur_axpy(ptr(tmp), ptr(dat), float(obs.tau), n_vox, stream()))
+            continue
+        s = proj_struct(obs.po, sett.method)
+        ws = _lib.workspace(lib.ur_proj_workspace_bytes(C.byref(s)), tmp.device, 'proj')
+        check(lib.ur_proj_accumulate(_lib.UR_OP_AT, C.byref(s), ptr(dat), ptr(tmp),
+                                     float(obs.tau), ptr(ws), ws.numel(), stream()))
+    check(lib.ur_admm_rhs(ptr(tmp), ptr(w_c), ptr(z_c), i3(dim), f3(vx), float(yc.lam),
+                          float(rho), stream()))
+
+
+def _solve_y(x, y, z, w, rho, tmp, sett, dim, vx):
+    """y-update: one device-resident CG per channel.  Returns the CgInfo handles."""
+    infos = []
+    stop = getattr(sett, 'cgs_stop', 'max_gain')
+    for c in range(len(x)):
+        _rhs(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx)
+        lhs = LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj, rho=rho, vx_y=vx,
+                          bound=sett.bound, interpolation=sett.interpolation, diff=sett.diff)
+        y[c].dat = require_cuda_f32(y[c].dat, 'y.dat')
+        cg(A=lhs, b=tmp, x=y[c].dat, verbose=sett.cgs_verbose, max_iter=sett.cgs_max_iter,
+           stop=stop, inplace=True, precond=None, tolerance=sett.cgs_tol)
+        infos.append(cg.last)
+    return infos
+
+
+def _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett):
+    """One ADMM iteration (y by CG, objective, JTV prox z, dual w).
+
+    In place on y[c].dat, z, w and obj[n_iter]; returns (y, z, w, jtv, obj) where
+    jtv is the shrink-factor image the reference returns in `tmp`."""
+    dim, vx = _geometry(y)
+    z = require_cuda_f32(z, 'z')
+    w = require_cuda_f32(w, 'w')
+    tmp = require_cuda_f32(tmp, 'tmp')
+    rho_f = float(rho)
+    _update_admm.last_cg = _solve_y(x, y, z, w, rho_f, tmp, sett, dim, vx)
+    if sett.tolerance > 0:
+        row = torch.zeros(3, dtype=torch.float64, device=tmp.device)
+        _nll_terms(x, y, sett, row)
+        row[0] = row[1] + row[2]
+        obj[n_iter, :] = row.to(obj.device, obj.dtype)
+    # z and w in one pass; the shrink factor lands in tmp (returned, as upstream)
+    ys = [yc.dat for yc in y]
+    if len(ys) > _lib.UR_MAX_CHANNELS:
+        raise NotImplementedError('more than %d channels' % _lib.UR_MAX_CHANNELS)
+    check(lib.ur_jtv_prox(_ptr_array(ys), ptr(z), ptr(w), ptr(tmp), len(ys),
+                          _lib.farr([float(yc.lam) for yc in y]), i3(dim), f3(vx), rho_f,
+                          float(sett.alpha), stream()))
+    return y, z, w, tmp, obj
+
+
+_update_admm.last_cg = None
+
+
+def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
+    """Channel-sharded ADMM iteration: this rank holds a subset of the channels
+    (x, y, z, w are the LOCAL lists / tensors).  Communication per iteration:
+    one SUM all-reduce of the (X,Y,Z) JTV coupling field, one of the prior
+    energy field and one of the scalar data term (only if sett.tolerance > 0).
+    With a single rank it reduces to `_update_admm`."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett)
+    dim, vx = _geometry(y)
+    n_vox = dim[0] * dim[1] * dim[2]
+    rho_f = float(rho)
+    _update_admm.last_cg = _solve_y(x, y, z, w, rho_f, tmp, sett, dim, vx)
+    ys = [yc.dat for yc in y]
+    lam = _lib.farr([float(yc.lam) for yc in y])
+    field = torch.empty(dim, dtype=torch.float32, device=tmp.device)
+    if sett.tolerance > 0:
+        row = torch.zeros(3, dtype=torch.float64, device=tmp.device)
+        _nll_terms(x, y, sett, row, prior_field=field)
+        dist.all_reduce(field, group=group)
+        dist.all_reduce(row[1:2], group=group)
+        check(lib.ur_sqrt_sum(ptr(field), n_vox, ptr(row[2:3]), stream()))
+        row[0] = row[1] + row[2]
+        obj[n_iter, :] = row.to(obj.device, obj.dtype)
+    check(lib.ur_jtv_norm2(_ptr_array(ys), ptr(z), ptr(w), ptr(field), len(ys), lam, i3(dim),
+                           f3(vx), rho_f, float(sett.alpha), 0, stream()))
+    dist.all_reduce(field, group=group)
+    check(lib.ur_jtv_apply(_ptr_array(ys), ptr(z), ptr(w), ptr(field), ptr(tmp), len(ys), lam,
+                           i3(dim), f3(vx), rho_f, float(sett.alpha), stream()))
+    return y, z, w, tmp, obj

@@ -1,0 +1,105 @@
+// Shared helpers for the unires_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/unires_b200.h"
+
+namespace ur {
+
+void set_error(const char *fmt, ...);
+int sm_count();
+
+#define UR_CUDA_CHECK(expr)                                                         \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      ur::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                    cudaGetErrorString(e_));                                        \
+      return UR_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+#define UR_LAUNCH_CHECK() UR_CUDA_CHECK(cudaGetLastError())
+#define UR_REQUIRE(cond, ...)                                                       \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      ur::set_error(__VA_ARGS__);                                                   \
+      return UR_ERR_ARG;                                                            \
+    }                                                                               \
+  } while (0)
+
+struct Dim3i {
+  int x, y, z;
+  __host__ __device__ size_t numel() const { return (size_t)x * y * z; }
+};
+inline Dim3i make_dim(const int32_t d[3]) { return Dim3i{d[0], d[1], d[2]}; }
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// deterministic float64 reductions
+// ---------------------------------------------------------------------------
+constexpr int kMaxWarps = 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in thread 0.  `sh` holds >= kMaxWarps doubles.
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthr = blockDim.x * blockDim.y * blockDim.z;
+  const int lane = tid & 31, wid = tid >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect sh from a previous use
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = (nthr + 31) >> 5;
+  if (wid == 0) {
+    v = lane < nw ? sh[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// Two-stage grid reduction with a fixed summation order: every block writes
+// its partial to partials[block]; the last block to arrive (atomic ticket)
+// re-reads all partials in index order and returns the total in thread 0
+// (is_last = true for every thread of that block).  The ticket counter is
+// reset by the last block, so the same buffers serve the next launch.
+struct GridReduce {
+  double *partials;       // >= number of blocks
+  unsigned int *counter;  // zero-initialised once
+};
+
+__device__ __forceinline__ bool grid_sum(double v, const GridReduce &gr, double *sh,
+                                         double *total) {
+  __shared__ bool s_last;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nthr = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
+  double s = block_sum(v, sh);
+  if (tid == 0) {
+    gr.partials[bid] = s;
+    __threadfence();
+    unsigned t = atomicAdd(gr.counter, 1u);
+    s_last = (t == nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned i = tid; i < nblk; i += nthr) acc += __ldcg(gr.partials + i);
+  acc = block_sum(acc, sh);
+  if (tid == 0) {
+    *total = acc;
+    *gr.counter = 0u;
+  }
+  return true;
+}
+
+}  // namespace ur

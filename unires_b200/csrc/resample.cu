@@ -1,0 +1,199 @@
+// Trilinear / nearest resampling with zero bound: nitorch grid_pull and its
+// exact transpose grid_push.  Coordinates come
+// either from a dense (ox,oy,oz,3) grid or are evaluated in-kernel from a 3x4
+// affine matrix in float32, the same arithmetic type the reference uses when
+// it materialises affine_grid (unires/_project.py:159).
+#include "common.cuh"
+
+namespace ur {
+
+constexpr float kFovTol = 5e-2f;  // nitorch's in-FOV tolerance when extrapolate=False
+
+struct Affine {
+  float m[12];
+};
+
+struct CoordDense {
+  const float *grid;
+  __device__ __forceinline__ void get(int i, int j, int k, size_t lin, float &cx, float &cy,
+                                      float &cz) const {
+    cx = grid[3 * lin + 0];
+    cy = grid[3 * lin + 1];
+    cz = grid[3 * lin + 2];
+  }
+};
+
+struct CoordAffine {
+  Affine a;
+  __device__ __forceinline__ void get(int i, int j, int k, size_t lin, float &cx, float &cy,
+                                      float &cz) const {
+    const float fi = (float)i, fj = (float)j, fk = (float)k;
+    cx = fmaf(a.m[2], fk, fmaf(a.m[1], fj, a.m[0] * fi)) + a.m[3];
+    cy = fmaf(a.m[6], fk, fmaf(a.m[5], fj, a.m[4] * fi)) + a.m[7];
+    cz = fmaf(a.m[10], fk, fmaf(a.m[9], fj, a.m[8] * fi)) + a.m[11];
+  }
+};
+
+__device__ __forceinline__ bool in_fov(float cx, float cy, float cz, const Dim3i &s) {
+  return cx > -kFovTol && cx < (float)(s.x - 1) + kFovTol && cy > -kFovTol &&
+         cy < (float)(s.y - 1) + kFovTol && cz > -kFovTol && cz < (float)(s.z - 1) + kFovTol;
+}
+
+// PUSH = false: out[o] = sum_corners w * src[corner]
+// PUSH = true : dst[corner] += scale * w * in[o]        (atomic)
+template <class Coord, bool PUSH>
+__global__ void resample_kernel(const float *__restrict__ in, float *__restrict__ out, Dim3i s,
+                                Dim3i o, Coord coord, int order, int extrapolate, float scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= o.z || j >= o.y) return;
+  const size_t lin = ((size_t)i * o.y + j) * o.z + k;
+  float cx, cy, cz;
+  coord.get(i, j, k, lin, cx, cy, cz);
+  const bool ok = extrapolate || in_fov(cx, cy, cz, s);
+  float val = 0.f;
+  if (PUSH) val = scale * in[lin];
+  if (!ok || (PUSH && val == 0.f)) {
+    if (!PUSH) out[lin] = 0.f;
+    return;
+  }
+  const size_t sy = s.z, sx = (size_t)s.y * s.z;
+  if (order == 0) {
+    const int ix = (int)floorf(cx + 0.5f), iy = (int)floorf(cy + 0.5f),
+              iz = (int)floorf(cz + 0.5f);
+    const bool inside = ix >= 0 && ix < s.x && iy >= 0 && iy < s.y && iz >= 0 && iz < s.z;
+    if (PUSH) {
+      if (inside) atomicAdd(out + ix * sx + iy * sy + iz, val);
+    } else {
+      out[lin] = inside ? __ldg(in + ix * sx + iy * sy + iz) : 0.f;
+    }
+    return;
+  }
+  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const float wx1 = cx - fx, wy1 = cy - fy, wz1 = cz - fz;
+  const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int bx = (c >> 2) & 1, by = (c >> 1) & 1, bz = c & 1;
+    const int px = ix + bx, py = iy + by, pz = iz + bz;
+    if (px < 0 || px >= s.x || py < 0 || py >= s.y || pz < 0 || pz >= s.z) continue;
+    // same association as the oracle: (wx * wy) * wz
+    const float wgt = ((bx ? wx1 : wx0) * (by ? wy1 : wy0)) * (bz ? wz1 : wz0);
+    const size_t q = px * sx + py * sy + pz;
+    if (PUSH)
+      atomicAdd(out + q, val * wgt);
+    else
+      acc += __ldg(in + q) * wgt;
+  }
+  if (!PUSH) out[lin] = acc;
+}
+
+__global__ void affine_grid_kernel(float *__restrict__ grid, Dim3i o, CoordAffine coord) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= o.z || j >= o.y) return;
+  const size_t lin = ((size_t)i * o.y + j) * o.z + k;
+  float cx, cy, cz;
+  coord.get(i, j, k, lin, cx, cy, cz);
+  grid[3 * lin + 0] = cx;
+  grid[3 * lin + 1] = cy;
+  grid[3 * lin + 2] = cz;
+}
+
+static inline void shape_for(const Dim3i &o, dim3 &grid, dim3 &block) {
+  block = dim3(64, 4, 1);
+  grid = dim3(div_up(o.z, 64), div_up(o.y, 4), o.x);
+}
+
+static inline CoordAffine make_affine(const float mat[12]) {
+  CoordAffine c;
+  for (int i = 0; i < 12; ++i) c.a.m[i] = mat[i];
+  return c;
+}
+
+int affine_pull(const float *src, Dim3i s, const float mat[12], float *out, Dim3i o, int order,
+                int extrapolate, cudaStream_t st) {
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  resample_kernel<CoordAffine, false>
+      <<<grid, block, 0, st>>>(src, out, s, o, make_affine(mat), order, extrapolate, 1.f);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+int affine_push(const float *in, Dim3i o, const float mat[12], float *out, Dim3i s, int order,
+                int extrapolate, float scale, cudaStream_t st) {
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  resample_kernel<CoordAffine, true>
+      <<<grid, block, 0, st>>>(in, out, s, o, make_affine(mat), order, extrapolate, scale);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+static bool dims_ok(const int32_t d[3]) { return d && d[0] > 0 && d[1] > 0 && d[2] > 0; }
+
+extern "C" int ur_grid_pull(const float *d_src, const int32_t sdim[3], const float *d_grid,
+                            float *d_out, const int32_t odim[3], int order, int extrapolate,
+                            ur_stream stream) {
+  UR_REQUIRE(d_src && d_grid && d_out && dims_ok(sdim) && dims_ok(odim), "ur_grid_pull: bad args");
+  UR_REQUIRE(order == 0 || order == 1, "ur_grid_pull: interpolation order must be 0 or 1");
+  Dim3i s = make_dim(sdim), o = make_dim(odim);
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  resample_kernel<CoordDense, false><<<grid, block, 0, (cudaStream_t)stream>>>(
+      d_src, d_out, s, o, CoordDense{d_grid}, order, extrapolate, 1.f);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_grid_push(const float *d_in, const int32_t idim[3], const float *d_grid,
+                            float *d_out, const int32_t sdim[3], int order, int extrapolate,
+                            float scale, ur_stream stream) {
+  UR_REQUIRE(d_in && d_grid && d_out && dims_ok(sdim) && dims_ok(idim), "ur_grid_push: bad args");
+  UR_REQUIRE(order == 0 || order == 1, "ur_grid_push: interpolation order must be 0 or 1");
+  Dim3i s = make_dim(sdim), o = make_dim(idim);
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  resample_kernel<CoordDense, true><<<grid, block, 0, (cudaStream_t)stream>>>(
+      d_in, d_out, s, o, CoordDense{d_grid}, order, extrapolate, scale);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_affine_pull(const float *d_src, const int32_t sdim[3], const float mat[12],
+                              float *d_out, const int32_t odim[3], int order, int extrapolate,
+                              ur_stream stream) {
+  UR_REQUIRE(d_src && mat && d_out && dims_ok(sdim) && dims_ok(odim), "ur_affine_pull: bad args");
+  UR_REQUIRE(order == 0 || order == 1, "ur_affine_pull: interpolation order must be 0 or 1");
+  return affine_pull(d_src, make_dim(sdim), mat, d_out, make_dim(odim), order, extrapolate,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int ur_affine_push(const float *d_in, const int32_t idim[3], const float mat[12],
+                              float *d_out, const int32_t sdim[3], int order, int extrapolate,
+                              float scale, ur_stream stream) {
+  UR_REQUIRE(d_in && mat && d_out && dims_ok(sdim) && dims_ok(idim), "ur_affine_push: bad args");
+  UR_REQUIRE(order == 0 || order == 1, "ur_affine_push: interpolation order must be 0 or 1");
+  return affine_push(d_in, make_dim(idim), mat, d_out, make_dim(sdim), order, extrapolate, scale,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int ur_affine_grid(const float mat[12], float *d_grid, const int32_t odim[3],
+                              ur_stream stream) {
+  UR_REQUIRE(mat && d_grid && dims_ok(odim), "ur_affine_grid: bad args");
+  Dim3i o = make_dim(odim);
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  affine_grid_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_grid, o, make_affine(mat));
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}

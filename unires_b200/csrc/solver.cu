@@ -1,0 +1,598 @@
+// CG left-hand side  v -> sum_n tau_n An'An v + rho lam^2 D'D v  and the
+// device-resident CG solve (nitorch cg as called at unires/_update.py:142-148).
+//
+// lhs_direct_kernel: one thread per voxel, 7-point D'D stencil plus every
+// "lattice" observation (identity rotation, integer shift: pull/push are a
+// crop / zero-pad, the slice profile is a strided 1-D correlation along at most
+// one axis) fused in the same pass, with the CG dot product / residual /
+// energy epilogue and a deterministic two-stage float64 grid reduction whose
+// last block does the scalar CG arithmetic on the device.  Observations under a
+// general rigid transform (or with more than one decimated axis) are
+// pre-accumulated by the general path (proj.cu) into `acc`.
+#include <math.h>
+#include <string.h>
+
+#include "solver.cuh"
+
+namespace ur {
+
+int validate_proj(const ur_proj *po);
+size_t proj_workspace_bytes(const ur_proj *po);
+int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_out, float scale,
+                       void *d_ws, size_t ws_bytes, cudaStream_t st);
+int scratch_reduce(GridReduce *gr);  // vecops.cu
+
+constexpr int kMaxFused = 4;
+
+struct LatticeTerm {
+  float tau;
+  int axis;  // correlation axis, -1 = pure crop
+  int r, K, off, nj;
+  int lo[3], hi[3];
+  int scl_axis;  // -1 = no even/odd scaling
+  int scl_off;
+  float s_even, s_odd;
+  float ker[UR_MAX_TAPS];
+};
+
+enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2 };
+
+struct LhsArgs {
+  int nx, ny, nz;
+  float ivx, ivy, ivz;
+  float rl2;      // rho * lam^2
+  float w_ident;  // sum of tau over identity observations (do_proj = 0)
+  const float *acc;
+  int nterm;
+  LatticeTerm term[kMaxFused];
+  const float *v;
+  float *out;      // PLAIN: A v
+  const float *b;  // RESID / ENERGY
+  float *r;        // RESID: r = b - A v ; ENERGY (p update): read
+  float *p;        // RESID: p = r       ; ENERGY (p update): p = beta p + r
+  int update_p;    // ENERGY only
+  const int *done;
+  GridReduce gr;
+  FinalizeArgs fin;
+};
+
+__device__ __forceinline__ float eval_term(const LatticeTerm &T, const float *__restrict__ v,
+                                           const int (&i)[3], size_t lin, const int (&n)[3],
+                                           const size_t (&st)[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    if (a != T.axis && (i[a] < T.lo[a] || i[a] >= T.hi[a])) return 0.f;
+  float thin = 1.f;
+  if (T.scl_axis >= 0 && T.scl_axis != T.axis)
+    thin = ((i[T.scl_axis] - T.scl_off) & 1) ? T.s_odd : T.s_even;
+  if (T.axis < 0) return T.tau * (thin * __ldg(v + lin));
+  const int ax = T.axis;
+  const int u = i[ax] - T.off;
+  if (u < 0) return 0.f;
+  int j_hi = u / T.r;
+  if (j_hi > T.nj - 1) j_hi = T.nj - 1;
+  const int a0 = u - T.K + 1;
+  const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+  const float *base = v + (lin - (size_t)i[ax] * st[ax]);
+  float acc = 0.f;
+  for (int j = j_lo; j <= j_hi; ++j) {
+    const int s0 = j * T.r + T.off;
+    float lr = 0.f;
+    for (int t = 0; t < T.K; ++t) {
+      const int q = s0 + t;
+      if (q >= 0 && q < n[ax]) lr = fmaf(T.ker[t], __ldg(base + (size_t)q * st[ax]), lr);
+    }
+    if (T.scl_axis == ax) lr *= (j & 1) ? T.s_odd : T.s_even;
+    acc = fmaf(T.ker[u - j * T.r], lr, acc);
+  }
+  return T.tau * (thin * acc);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) lhs_direct_kernel(const LhsArgs a) {
+  __shared__ LatticeTerm s_term[kMaxFused];
+  __shared__ double s_red[kMaxWarps];
+  if (a.done && *a.done) return;
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  {
+    const int nwords = a.nterm * (int)(sizeof(LatticeTerm) / 4);
+    const int *src = reinterpret_cast<const int *>(a.term);
+    int *dst = reinterpret_cast<int *>(s_term);
+    for (int w = tid; w < nwords; w += blockDim.x * blockDim.y) dst[w] = src[w];
+  }
+  __syncthreads();
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  double part = 0.0;
+  if (z < a.nz && y < a.ny) {
+    const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
+    const size_t i = x * sx + y * sy + z;
+    const float *__restrict__ v = a.v;
+    const float c = __ldg(v + i);
+    const float xm = x > 0 ? __ldg(v + i - sx) : 0.f, xp = x + 1 < a.nx ? __ldg(v + i + sx) : 0.f;
+    const float ym = y > 0 ? __ldg(v + i - sy) : 0.f, yp = y + 1 < a.ny ? __ldg(v + i + sy) : 0.f;
+    const float zm = z > 0 ? __ldg(v + i - 1) : 0.f, zp = z + 1 < a.nz ? __ldg(v + i + 1) : 0.f;
+    const float t0 = ((x > 0 ? (c - xm) * a.ivx : 0.f) - (xp - c) * a.ivx) * a.ivx;
+    const float t1 = ((y > 0 ? (c - ym) * a.ivy : 0.f) - (yp - c) * a.ivy) * a.ivy;
+    const float t2 = ((z > 0 ? (c - zm) * a.ivz : 0.f) - (zp - c) * a.ivz) * a.ivz;
+    const float dtd = (t0 + t1) + t2;
+    float data = a.w_ident * c;
+    if (a.acc) data += a.acc[i];
+    if (a.nterm) {
+      const int idx[3] = {x, y, z};
+      const int n[3] = {a.nx, a.ny, a.nz};
+      const size_t st[3] = {sx, sy, 1};
+      for (int k = 0; k < a.nterm; ++k) data += eval_term(s_term[k], v, idx, i, n, st);
+    }
+    const float val = data + a.rl2 * dtd;
+    if (MODE == LHS_PLAIN) {
+      a.out[i] = val;
+      part = (double)__fmul_rn(c, val);
+    } else if (MODE == LHS_RESID) {
+      const float rr = __fsub_rn(a.b[i], val);
+      a.r[i] = rr;
+      a.p[i] = rr;
+      part = (double)__fmul_rn(rr, rr);
+    } else {
+      const float e = __fmul_rn(__fsub_rn(val, 2.f * a.b[i]), c);
+      part = (double)e;
+      if (a.update_p) {
+        const float beta = (float)a.fin.st->beta;
+        a.p[i] = __fadd_rn(__fmul_rn(beta, a.p[i]), a.r[i]);
+      }
+    }
+  }
+  double total;
+  if (grid_sum(part, a.gr, s_red, &total) && tid == 0) finalize(a.fin, total);
+}
+
+// ---------------------------------------------------------------------------
+// CG vector kernels
+// ---------------------------------------------------------------------------
+// x += alpha p ; r -= alpha Ap ; sum r*r.  torch evaluates `alpha * p` with the
+// float64 0-dim alpha cast to float32, then a separate add (no FMA).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    cg_update_xr_kernel(float *__restrict__ x, float *__restrict__ r, const float *__restrict__ p,
+                        const float *__restrict__ Ap, size_t n, const double *alpha_ptr,
+                        const int *done, GridReduce gr, FinalizeArgs fin) {
+  __shared__ double s_red[kMaxWarps];
+  if (done && *done) return;
+  const float alpha = (float)(*alpha_ptr);
+  double part = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    const size_t n4 = n / 4;
+    float4 *x4 = reinterpret_cast<float4 *>(x), *r4 = reinterpret_cast<float4 *>(r);
+    const float4 *p4 = reinterpret_cast<const float4 *>(p),
+                 *A4 = reinterpret_cast<const float4 *>(Ap);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 xv = x4[i], rv = r4[i];
+      const float4 pv = p4[i], av = A4[i];
+      xv.x = __fadd_rn(xv.x, __fmul_rn(alpha, pv.x));
+      xv.y = __fadd_rn(xv.y, __fmul_rn(alpha, pv.y));
+      xv.z = __fadd_rn(xv.z, __fmul_rn(alpha, pv.z));
+      xv.w = __fadd_rn(xv.w, __fmul_rn(alpha, pv.w));
+      rv.x = __fsub_rn(rv.x, __fmul_rn(alpha, av.x));
+      rv.y = __fsub_rn(rv.y, __fmul_rn(alpha, av.y));
+      rv.z = __fsub_rn(rv.z, __fmul_rn(alpha, av.z));
+      rv.w = __fsub_rn(rv.w, __fmul_rn(alpha, av.w));
+      x4[i] = xv;
+      r4[i] = rv;
+      part += (double)__fmul_rn(rv.x, rv.x) + (double)__fmul_rn(rv.y, rv.y) +
+              (double)__fmul_rn(rv.z, rv.z) + (double)__fmul_rn(rv.w, rv.w);
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float xv = __fadd_rn(x[i], __fmul_rn(alpha, p[i]));
+      const float rv = __fsub_rn(r[i], __fmul_rn(alpha, Ap[i]));
+      x[i] = xv;
+      r[i] = rv;
+      part += (double)__fmul_rn(rv, rv);
+    }
+  }
+  double total;
+  if (grid_sum(part, gr, s_red, &total) && threadIdx.x == 0) finalize(fin, total);
+}
+
+// p = beta p + r   (torch: p *= beta; p += z)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    cg_update_p_kernel(float *__restrict__ p, const float *__restrict__ r, size_t n,
+                       const double *beta_ptr, const int *done) {
+  if (done && *done) return;
+  const float beta = (float)(*beta_ptr);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    const size_t n4 = n / 4;
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    const float4 *r4 = reinterpret_cast<const float4 *>(r);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 pv = p4[i];
+      const float4 rv = r4[i];
+      pv.x = __fadd_rn(__fmul_rn(beta, pv.x), rv.x);
+      pv.y = __fadd_rn(__fmul_rn(beta, pv.y), rv.y);
+      pv.z = __fadd_rn(__fmul_rn(beta, pv.z), rv.z);
+      pv.w = __fadd_rn(__fmul_rn(beta, pv.w), rv.w);
+      p4[i] = pv;
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
+      p[i] = __fadd_rn(__fmul_rn(beta, p[i]), r[i]);
+  }
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+static unsigned vec_blocks(size_t n) {
+  const size_t want = (n / 4 + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 8;
+  return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------
+struct LhsPlan {
+  LhsArgs args;             // v/out/b/... left unset
+  int n_general;            // observations routed through the general path
+  int general[UR_MAX_OBS];  // their indices
+  size_t proj_ws;           // max general-path workspace
+  dim3 grid, block;
+};
+
+static bool lattice_term(const ur_proj *po, float tau, LatticeTerm *T) {
+  if (!ur_proj_is_lattice(po)) return false;
+  memset(T, 0, sizeof(*T));
+  T->axis = -1;
+  T->scl_axis = -1;
+  T->r = 1;
+  T->K = 1;
+  T->s_even = T->s_odd = 1.f;
+  float w = tau;
+  const bool sr = po->method == UR_SUPERRES;
+  for (int a = 0; a < 3; ++a) {
+    const int shift = (int)lrintf(po->mat[4 * a + 3]);
+    const bool conv = sr && (po->ksize[a] > 1 || po->ratio[a] > 1);
+    if (conv) {
+      if (T->axis >= 0) return false;  // more than one decimated axis: general path
+      T->axis = a;
+      // trim zero end taps
+      int k0 = 0, k1 = po->ksize[a];
+      while (k1 - k0 > 1 && po->ker[a][k0] == 0.f) ++k0;
+      while (k1 - k0 > 1 && po->ker[a][k1 - 1] == 0.f) --k1;
+      T->K = k1 - k0;
+      for (int t = 0; t < T->K; ++t) T->ker[t] = po->ker[a][k0 + t];
+      T->off = shift + k0;
+      T->r = po->ratio[a];
+      T->nj = po->dim_x[a];
+      T->lo[a] = 0;
+      T->hi[a] = po->dim_y[a];
+    } else {
+      const float k = sr ? po->ker[a][0] : 1.f;
+      w *= k * k;
+      T->lo[a] = shift > 0 ? shift : 0;
+      const int hi = shift + po->dim_x[a];
+      T->hi[a] = hi < po->dim_y[a] ? hi : po->dim_y[a];
+    }
+    if (sr && po->scl != 0.f && a == po->dim_thick) {
+      T->scl_axis = a;
+      T->scl_off = shift;
+      T->s_even = expf(2.f * po->scl);
+      T->s_odd = expf(-2.f * po->scl);
+    }
+  }
+  T->tau = w;
+  return true;
+}
+
+static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
+  UR_REQUIRE(lhs, "ur_lhs is NULL");
+  UR_REQUIRE(lhs->dim_y[0] > 0 && lhs->dim_y[1] > 0 && lhs->dim_y[2] > 0, "ur_lhs: bad dim_y");
+  UR_REQUIRE(lhs->n_obs >= 1 && lhs->n_obs <= UR_MAX_OBS, "ur_lhs: n_obs %d not in [1,%d]",
+             lhs->n_obs, UR_MAX_OBS);
+  UR_REQUIRE(lhs->vx[0] > 0 && lhs->vx[1] > 0 && lhs->vx[2] > 0, "ur_lhs: bad voxel size");
+  memset(P, 0, sizeof(*P));
+  LhsArgs &A = P->args;
+  A.nx = lhs->dim_y[0];
+  A.ny = lhs->dim_y[1];
+  A.nz = lhs->dim_y[2];
+  A.ivx = 1.f / lhs->vx[0];
+  A.ivy = 1.f / lhs->vx[1];
+  A.ivz = 1.f / lhs->vx[2];
+  A.rl2 = lhs->rho_lam2;
+  for (int n = 0; n < lhs->n_obs; ++n) {
+    if (!lhs->do_proj) {
+      A.w_ident += lhs->tau[n];
+      continue;
+    }
+    const ur_proj *po = &lhs->obs[n];
+    int rc = validate_proj(po);
+    if (rc) return rc;
+    for (int a = 0; a < 3; ++a)
+      UR_REQUIRE(po->dim_y[a] == lhs->dim_y[a], "ur_lhs: observation %d dim_y mismatch", n);
+    if (A.nterm < kMaxFused && lattice_term(po, lhs->tau[n], &A.term[A.nterm])) {
+      ++A.nterm;
+    } else {
+      P->general[P->n_general++] = n;
+      const size_t w = proj_workspace_bytes(po);
+      if (w > P->proj_ws) P->proj_ws = w;
+    }
+  }
+  P->block = dim3(64, 4, 1);
+  P->grid = dim3(div_up(A.nz, 64), div_up(A.ny, 4), A.nx);
+  return UR_OK;
+}
+
+static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
+
+static size_t vol_bytes(const ur_lhs *lhs) {
+  return align_up((size_t)lhs->dim_y[0] * lhs->dim_y[1] * lhs->dim_y[2] * sizeof(float));
+}
+
+// lhs workspace: [counter 256B | partials | acc volume (general) | proj ws]
+static size_t lhs_partials_bytes(const LhsPlan &P) {
+  size_t nblk = (size_t)P.grid.x * P.grid.y * P.grid.z;
+  const size_t cap = (size_t)sm_count() * 8 + 1024;
+  if (nblk < cap) nblk = cap;  // also serves the grid-stride vector kernels
+  return align_up(nblk * sizeof(double));
+}
+
+static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
+  size_t s = 256 + lhs_partials_bytes(P);
+  if (P.n_general) s += vol_bytes(lhs) + align_up(P.proj_ws);
+  return s;
+}
+
+struct LhsWs {
+  unsigned *counter;
+  double *partials;
+  float *acc;
+  void *proj;
+  size_t proj_bytes;
+};
+
+static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
+  LhsWs w;
+  char *c = (char *)ws;
+  w.counter = (unsigned *)c;
+  c += 256;
+  w.partials = (double *)c;
+  c += lhs_partials_bytes(P);
+  w.acc = nullptr;
+  w.proj = nullptr;
+  w.proj_bytes = 0;
+  if (P.n_general) {
+    w.acc = (float *)c;
+    c += vol_bytes(lhs);
+    w.proj = c;
+    w.proj_bytes = align_up(P.proj_ws);
+  }
+  return w;
+}
+
+// Launch one lhs evaluation.  `A` carries the mode-specific pointers.
+static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs &w, LhsArgs A,
+                      int variant, cudaStream_t st) {
+  if (P.n_general) {
+    // NOTE: the general path cannot early-out on the device-side `done` flag
+    // for its memset; its kernels are cheap relative to a full iteration.
+    UR_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, vol_bytes(lhs), st));
+    for (int k = 0; k < P.n_general; ++k) {
+      const int n = P.general[k];
+      int rc = proj_apply_general(UR_OP_ATA, &lhs->obs[n], A.v, w.acc, lhs->tau[n], w.proj,
+                                  w.proj_bytes, st);
+      if (rc) return rc;
+    }
+    A.acc = w.acc;
+  }
+  A.gr = GridReduce{w.partials, w.counter};
+  (void)variant;
+  switch (mode) {
+    case LHS_PLAIN:
+      lhs_direct_kernel<LHS_PLAIN><<<P.grid, P.block, 0, st>>>(A);
+      break;
+    case LHS_RESID:
+      lhs_direct_kernel<LHS_RESID><<<P.grid, P.block, 0, st>>>(A);
+      break;
+    default:
+      lhs_direct_kernel<LHS_ENERGY><<<P.grid, P.block, 0, st>>>(A);
+      break;
+  }
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+// CG workspace: [CgState | lhs ws | r | p | Ap]
+struct CgWs {
+  CgState *st;
+  void *lhs;
+  float *r, *p, *Ap;
+};
+
+static size_t cg_state_bytes() { return align_up(sizeof(CgState)); }
+
+static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
+  CgWs w;
+  char *c = (char *)ws;
+  w.st = (CgState *)c;
+  c += cg_state_bytes();
+  w.lhs = c;
+  c += align_up(lhs_ws_bytes(lhs, P));
+  w.r = (float *)c;
+  c += vol_bytes(lhs);
+  w.p = (float *)c;
+  c += vol_bytes(lhs);
+  w.Ap = (float *)c;
+  return w;
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+extern "C" size_t ur_lhs_workspace_bytes(const ur_lhs *lhs) {
+  LhsPlan P;
+  if (make_plan(lhs, &P)) return 0;
+  return lhs_ws_bytes(lhs, P);
+}
+
+extern "C" int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, double *d_dot,
+                            void *d_ws, size_t ws_bytes, ur_stream stream) {
+  LhsPlan P;
+  int rc = make_plan(lhs, &P);
+  if (rc) return rc;
+  UR_REQUIRE(d_v && d_out && d_v != d_out, "ur_lhs_apply: bad data pointers");
+  UR_REQUIRE(d_ws && ws_bytes >= lhs_ws_bytes(lhs, P), "ur_lhs_apply: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  LhsWs w = carve_lhs_ws(lhs, P, d_ws);
+  UR_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 256, st));
+  LhsArgs A = P.args;
+  A.v = d_v;
+  A.out = d_out;
+  A.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, d_dot};
+  return launch_lhs(LHS_PLAIN, lhs, P, w, A, 0, st);
+}
+
+extern "C" size_t ur_cg_workspace_bytes(const ur_lhs *lhs) {
+  LhsPlan P;
+  if (make_plan(lhs, &P)) return 0;
+  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + 3 * vol_bytes(lhs);
+}
+
+extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_ws,
+                           size_t ws_bytes, const ur_cg_opts *opts, ur_stream stream) {
+  LhsPlan P;
+  int rc = make_plan(lhs, &P);
+  if (rc) return rc;
+  UR_REQUIRE(opts, "ur_cg_solve: opts is NULL");
+  UR_REQUIRE(opts->max_iter >= 1 && opts->max_iter <= UR_CG_MAX_ITER,
+             "ur_cg_solve: max_iter %d not in [1,%d]", opts->max_iter, UR_CG_MAX_ITER);
+  UR_REQUIRE(opts->stop_rule >= UR_STOP_NONE && opts->stop_rule <= UR_STOP_ENERGY,
+             "ur_cg_solve: unknown stop rule");
+  UR_REQUIRE(d_b && d_x && d_ws, "ur_cg_solve: null pointer");
+  UR_REQUIRE(ws_bytes >= ur_cg_workspace_bytes(lhs), "ur_cg_solve: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stop = opts->tolerance > 0 ? opts->stop_rule : UR_STOP_NONE;
+  const double tol = opts->tolerance;
+  const size_t n = (size_t)lhs->dim_y[0] * lhs->dim_y[1] * lhs->dim_y[2];
+
+  CgWs cw = carve_cg_ws(lhs, P, d_ws);
+  LhsWs lw = carve_lhs_ws(lhs, P, cw.lhs);
+  UR_CUDA_CHECK(cudaMemsetAsync(cw.st, 0, cg_state_bytes() + 256, st));  // state + ticket
+  const int *done = &cw.st->done;
+  const GridReduce gr{lw.partials, lw.counter};
+  const bool vec = (n % 4 == 0) && aligned16(d_x) && aligned16(cw.r) && aligned16(cw.p) &&
+                   aligned16(cw.Ap);
+  const unsigned vblocks = vec_blocks(n);
+
+  // r = b - A x ; p = r ; rz = r.r
+  {
+    LhsArgs A = P.args;
+    A.v = d_x;
+    A.b = d_b;
+    A.r = cw.r;
+    A.p = cw.p;
+    A.done = nullptr;
+    A.fin = FinalizeArgs{FIN_INIT_RZ, 0, stop, tol, cw.st, nullptr};
+    rc = launch_lhs(LHS_RESID, lhs, P, lw, A, opts->variant, st);
+    if (rc) return rc;
+  }
+  if (stop == UR_STOP_ENERGY) {
+    LhsArgs A = P.args;
+    A.v = d_x;
+    A.b = d_b;
+    A.update_p = 0;
+    A.done = done;
+    A.fin = FinalizeArgs{FIN_ENERGY, 0, stop, tol, cw.st, nullptr};
+    rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
+    if (rc) return rc;
+  }
+  for (int it = 1; it <= opts->max_iter; ++it) {
+    {  // Ap = A p ; alpha = rz / p.Ap
+      LhsArgs A = P.args;
+      A.v = cw.p;
+      A.out = cw.Ap;
+      A.done = done;
+      A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr};
+      rc = launch_lhs(LHS_PLAIN, lhs, P, lw, A, opts->variant, st);
+      if (rc) return rc;
+    }
+    {  // x += alpha p ; r -= alpha Ap ; beta = rz'/rz
+      FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
+      if (vec)
+        cg_update_xr_kernel<4><<<vblocks, 256, 0, st>>>(d_x, cw.r, cw.p, cw.Ap, n, &cw.st->alpha,
+                                                        done, gr, fin);
+      else
+        cg_update_xr_kernel<1><<<vblocks, 256, 0, st>>>(d_x, cw.r, cw.p, cw.Ap, n, &cw.st->alpha,
+                                                        done, gr, fin);
+      UR_LAUNCH_CHECK();
+    }
+    if (stop == UR_STOP_ENERGY) {  // obj = 0.5 (A x - 2 b).x  fused with p = beta p + r
+      LhsArgs A = P.args;
+      A.v = d_x;
+      A.b = d_b;
+      A.r = cw.r;
+      A.p = cw.p;
+      A.update_p = 1;
+      A.done = done;
+      A.fin = FinalizeArgs{FIN_ENERGY, it, stop, tol, cw.st, nullptr};
+      rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
+      if (rc) return rc;
+    } else {
+      if (vec)
+        cg_update_p_kernel<4><<<vblocks, 256, 0, st>>>(cw.p, cw.r, n, &cw.st->beta, done);
+      else
+        cg_update_p_kernel<1><<<vblocks, 256, 0, st>>>(cw.p, cw.r, n, &cw.st->beta, done);
+      UR_LAUNCH_CHECK();
+    }
+  }
+  return UR_OK;
+}
+
+extern "C" int ur_cg_fetch(const void *d_ws, int32_t *n_iter, double *obj, int32_t n_obj,
+                           ur_stream stream) {
+  UR_REQUIRE(d_ws, "ur_cg_fetch: null workspace");
+  static CgState host;  // not re-entrant across threads; guarded by the GIL in practice
+  UR_CUDA_CHECK(cudaMemcpyAsync(&host, d_ws, sizeof(CgState), cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+  UR_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (n_iter) *n_iter = host.n_iter;
+  if (obj)
+    for (int i = 0; i < n_obj && i <= host.n_iter && i <= UR_CG_MAX_ITER; ++i) obj[i] = host.obj[i];
+  return UR_OK;
+}
+
+// stand-alone building blocks for cg() over an arbitrary host callable
+extern "C" int ur_cg_update_xr(float *d_x, float *d_r, const float *d_p, const float *d_Ap,
+                               size_t n, const double *d_alpha, double *d_rr, ur_stream stream) {
+  UR_REQUIRE(d_x && d_r && d_p && d_Ap && d_alpha && d_rr && n > 0, "ur_cg_update_xr: bad args");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  FinalizeArgs fin{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, d_rr};
+  const bool vec = (n % 4 == 0) && aligned16(d_x) && aligned16(d_r) && aligned16(d_p) && aligned16(d_Ap);
+  const unsigned nb = vec_blocks(n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    cg_update_xr_kernel<4><<<nb, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_alpha, nullptr, gr, fin);
+  else
+    cg_update_xr_kernel<1><<<nb, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_alpha, nullptr, gr, fin);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_cg_update_p(float *d_p, const float *d_r, size_t n, const double *d_beta,
+                              ur_stream stream) {
+  UR_REQUIRE(d_p && d_r && d_beta && n > 0, "ur_cg_update_p: bad args");
+  const bool vec = (n % 4 == 0) && aligned16(d_p) && aligned16(d_r);
+  const unsigned nb = vec_blocks(n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    cg_update_p_kernel<4><<<nb, 256, 0, st>>>(d_p, d_r, n, d_beta, nullptr);
+  else
+    cg_update_p_kernel<1><<<nb, 256, 0, st>>>(d_p, d_r, n, d_beta, nullptr);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}

@@ -1,0 +1,81 @@
+// Device-side CG bookkeeping shared by the solver kernels.
+#pragma once
+#include "common.cuh"
+
+namespace ur {
+
+// Lives in device memory (head of the CG workspace).  Dynamic values only; the
+// loop bounds / stop rule are kernel arguments.
+struct CgState {
+  double rz, rz0, pAp, alpha, beta;
+  double obj_min, obj_max;
+  int n_iter;  // completed iterations
+  int done;    // set on the device when |gain| < tolerance
+  double obj[UR_CG_MAX_ITER + 1];
+};
+
+// What the last block of a reducing kernel does with the grid total.
+enum Finalize {
+  FIN_NONE = 0,    // *dot_out = total (stand-alone lhs / dot)
+  FIN_INIT_RZ,     // r = b - A x has been formed: rz = total, reset the state
+  FIN_ALPHA,       // total = p.Ap          -> alpha = rz / total
+  FIN_BETA,        // total = r.r (iter n)  -> beta = rz_new / rz_old, residual stop rule
+  FIN_ENERGY       // total = (Ax - 2b).x   -> obj[n] = total / 2, energy stop rule
+};
+
+struct FinalizeArgs {
+  int kind;
+  int iter;       // CG iteration this launch belongs to (0 = initialisation)
+  int stop_rule;  // UR_STOP_*
+  double tol;
+  CgState *st;
+  double *dot_out;
+};
+
+__device__ __forceinline__ void record_objective(CgState *st, int n, double o, double tol) {
+  st->obj[n] = o;
+  if (n == 0) {
+    st->obj_min = o;
+    st->obj_max = o;
+    return;
+  }
+  // nitorch get_gain(obj[:n+1], 'decreasing'): (obj[n-1] - obj[n]) / (max - min)
+  const double mn = fmin(st->obj_min, o), mx = fmax(st->obj_max, o);
+  st->obj_min = mn;
+  st->obj_max = mx;
+  const double gain = (st->obj[n - 1] - o) / (mx - mn);
+  if (fabs(gain) < tol) st->done = 1;
+}
+
+// Executed by ONE thread of the last block.
+__device__ __forceinline__ void finalize(const FinalizeArgs &f, double total) {
+  CgState *st = f.st;
+  switch (f.kind) {
+    case FIN_NONE:
+      if (f.dot_out) *f.dot_out = total;
+      break;
+    case FIN_INIT_RZ:
+      st->rz = total;
+      st->rz0 = total;
+      st->n_iter = 0;
+      st->done = 0;
+      if (f.stop_rule == UR_STOP_RESIDUAL) record_objective(st, 0, sqrt(total), f.tol);
+      break;
+    case FIN_ALPHA:
+      st->pAp = total;
+      st->alpha = st->rz / total;
+      break;
+    case FIN_BETA:
+      st->rz0 = st->rz;
+      st->rz = total;
+      st->beta = total / st->rz0;
+      st->n_iter = f.iter;
+      if (f.stop_rule == UR_STOP_RESIDUAL) record_objective(st, f.iter, sqrt(total), f.tol);
+      break;
+    case FIN_ENERGY:
+      record_objective(st, f.iter, 0.5 * total, f.tol);
+      break;
+  }
+}
+
+}  // namespace ur

@@ -1,0 +1,150 @@
+// Library plumbing (error string, device info, scratch) and the small vector /
+// reduction kernels: dot, axpy, the objective's data term and sqrt-sum
+// (_compute_nll, unires/_update.py:396-427).
+#include <stdarg.h>
+#include <string.h>
+
+#include "solver.cuh"
+
+namespace ur {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// Per-device scratch for the stand-alone reductions (ur_dot, ur_cg_update_xr,
+// ur_nll_data, ur_sqrt_sum).  Calls that share it must be stream-ordered.
+constexpr size_t kScratchPartials = 1 << 16;
+int scratch_reduce(GridReduce *gr) {
+  static void *bufs[64] = {nullptr};
+  int dev = 0;
+  UR_CUDA_CHECK(cudaGetDevice(&dev));
+  UR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (!bufs[dev]) {
+    void *p = nullptr;
+    UR_CUDA_CHECK(cudaMalloc(&p, 256 + kScratchPartials * sizeof(double)));
+    UR_CUDA_CHECK(cudaMemset(p, 0, 256));
+    bufs[dev] = p;
+  }
+  gr->counter = (unsigned *)bufs[dev];
+  gr->partials = (double *)((char *)bufs[dev] + 256);
+  return UR_OK;
+}
+
+static unsigned red_blocks(size_t n) {
+  size_t want = (n + 1023) / 1024;
+  const size_t cap = (size_t)sm_count() * 8;
+  if (want > cap) want = cap;
+  return (unsigned)(want ? want : 1);
+}
+
+// kind 0: sum a*b ; 1: 0.5*tau*sum_{a != 0} (a-b)^2 ; 2: sum sqrt(a)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    reduce_kernel(const float *__restrict__ a, const float *__restrict__ b, size_t n, float tau,
+                  int accumulate, GridReduce gr, double *out) {
+  __shared__ double s_red[kMaxWarps];
+  double part = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (KIND == 0) {
+      part += (double)__fmul_rn(a[i], b[i]);
+    } else if (KIND == 1) {
+      const float av = a[i];
+      if (av != 0.f) {
+        const float d = __fsub_rn(av, b[i]);
+        part += (double)__fmul_rn(d, d);
+      }
+    } else {
+      part += (double)sqrtf(a[i]);
+    }
+  }
+  double total;
+  if (grid_sum(part, gr, s_red, &total) && threadIdx.x == 0) {
+    if (KIND == 1) total = 0.5 * (double)tau * total;
+    *out = accumulate ? *out + total : total;
+  }
+}
+
+__global__ void axpy_kernel(float *__restrict__ y, const float *__restrict__ x, float a, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __fadd_rn(y[i], __fmul_rn(a, x[i]));
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+extern "C" const char *ur_last_error(void) { return g_err; }
+extern "C" int ur_version(void) { return 100; }
+
+extern "C" int ur_device_info(int *sm, int *major, int *minor) {
+  int dev = 0;
+  UR_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  UR_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (sm) *sm = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return UR_OK;
+}
+
+extern "C" int ur_dot(const float *d_a, const float *d_b, size_t n, double *d_out,
+                      ur_stream stream) {
+  UR_REQUIRE(d_a && d_b && d_out && n > 0, "ur_dot: bad args");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  reduce_kernel<0><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, 0.f, 0, gr, d_out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_nll_data(const float *d_x, const float *d_Ay, size_t n, float tau,
+                           double *d_out, int accumulate, ur_stream stream) {
+  UR_REQUIRE(d_x && d_Ay && d_out && n > 0, "ur_nll_data: bad args");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  reduce_kernel<1><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_x, d_Ay, n, tau, accumulate,
+                                                                    gr, d_out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream) {
+  UR_REQUIRE(d_e && d_out && n > 0, "ur_sqrt_sum: bad args");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  reduce_kernel<2><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_e, nullptr, n, 0.f, 0, gr,
+                                                                    d_out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_axpy(float *d_y, const float *d_x, float a, size_t n, ur_stream stream) {
+  UR_REQUIRE(d_y && d_x && n > 0, "ur_axpy: bad args");
+  axpy_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_y, d_x, a, n);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
