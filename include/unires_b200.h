@@ -47,6 +47,14 @@ const char *ur_last_error(void);
 int ur_version(void);
 /* device in use: SM count and compute capability */
 int ur_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of CUDA kernels this library has launched in this process */
+uint64_t ur_launch_count(void);
+/* Instrumentation for bench.py's roofline: while enabled, every CG matvec
+ * launch (the lhs kernel producing A p) is bracketed by CUDA events on its own
+ * stream.  ur_profile_matvec_read synchronises, returns the summed duration
+ * and the number of launches since the last read, and resets.            */
+int ur_profile_matvec(int enable);
+int ur_profile_matvec_read(double *total_ms, int32_t *count);
 
 /* ---------------------------------------------------------------- finite
  * differences: nitorch.spatial.im_gradient / im_divergence, 'forward',

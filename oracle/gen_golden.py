@@ -1,0 +1,136 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN control-flow files
+(/root/reference/unires/{_project,_update,struct}.py, imported by path,
+unmodified) on top of oracle/nitorch_shim.  TEST INFRASTRUCTURE.
+
+    python -m oracle.gen_golden            # only works where /root/reference exists
+
+Each fixture stores the scenario recipe (so the inputs can be regenerated from
+the seed with unires_b200.synth), sha256 digests of the regenerated inputs, and
+the reference outputs: operator applications on seeded random volumes and two
+ADMM iterations (y, z/w digests, jtv, objective, CG trip counts).
+PARITY UNPINNED at the nitorch boundary (see oracle/__init__.py); these
+fixtures pin the reference's control flow over the restated primitives.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from unires_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+SAMPLE_STRIDE = 11
+
+# name -> recipe (everything make_scenario needs)
+RECIPES = {
+    'denoise_1ch': dict(base='denoise_181', dim_y=(20, 24, 20), n_channels=1, sd=25.0,
+                        scl=0.0, rigid=None, admm_iters=2),
+    'sr3_thick_xyz': dict(base='sr3_256', dim_y=(28, 32, 24), n_channels=3, sd=25.0,
+                          scl=0.0, rigid=None, admm_iters=2),
+    'thickz2_scl': dict(base='thickz2_256', dim_y=(24, 20, 28), n_channels=2, sd=15.0,
+                        scl=0.1, rigid=None, admm_iters=2),
+    'sr2_rigid': dict(base='sr3_256', dim_y=(24, 28, 26), n_channels=2, sd=25.0, scl=0.05,
+                      rigid=[((1.3, -0.7, 0.4), (0.03, -0.02, 0.05)),
+                             ((-0.6, 0.9, 1.1), (-0.04, 0.03, 0.02))], admm_iters=2),
+    'iso2_1ch': dict(base='iso2_512', dim_y=(24, 24, 24), n_channels=1, sd=20.0, scl=0.0,
+                     rigid=None, admm_iters=2),
+}
+
+
+def digest(t):
+    a = np.ascontiguousarray(t.detach().cpu().numpy())
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def build(recipe, ops, structs, device='cpu'):
+    cfg = synth.scaled(synth.CONFIGS[recipe['base']], recipe['dim_y'], recipe['n_channels'])
+    rigid = None
+    if recipe['rigid'] is not None:
+        rigid = [synth.rigid_matrix(t, r) for t, r in recipe['rigid']]
+    return synth.make_scenario(cfg, ops, structs, device=device, seed=0, sd=recipe['sd'],
+                               scl=recipe['scl'], rigid=rigid)
+
+
+def probe_inputs(sc, c):
+    """Seeded random volumes for the operator-level golden values."""
+    g = torch.Generator().manual_seed(100 + c)
+    vy = torch.rand(tuple(sc.y[c].dim), generator=g)
+    vx = torch.rand(tuple(sc.x[c][0].dat.shape), generator=g)
+    return vy, vx
+
+
+def main():
+    from oracle.adapters import reference_namespaces
+    from oracle.load_reference import load_reference
+    from oracle.nitorch_shim.core import optim as shim_optim
+    ref = load_reference()
+    ops, structs = reference_namespaces()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, recipe in RECIPES.items():
+        torch.manual_seed(0)
+        sc = build(recipe, ops, structs)
+        out = {'recipe': json.dumps(recipe)}
+        C = len(sc.x)
+        for c in range(C):
+            out['in_x%d_sha' % c] = digest(sc.x[c][0].dat)
+            out['in_y%d_sha' % c] = digest(sc.y[c].dat)
+        # operator-level goldens
+        if sc.sett.do_proj:
+            for c in range(C):
+                vy, vx = probe_inputs(sc, c)
+                po = sc.x[c][0].po
+                kw = dict(method=sc.sett.method)
+                out['A%d' % c] = ref._project._proj_apply('A', vy[None, None], po, **kw)[0, 0].numpy()
+                out['At%d' % c] = ref._project._proj_apply('At', vx[None, None], po, **kw)[0, 0].numpy()
+                out['AtA%d' % c] = ref._project._proj_apply('AtA', vy[None, None], po, **kw)[0, 0].numpy()
+        vx_y = ref._update.voxel_size(sc.y[0].mat).float()
+        for c in range(C):
+            vy, _ = probe_inputs(sc, c)
+            out['lhs%d' % c] = ref._project._proj(
+                'AtA', vy, sc.x[c], sc.y[c], method=sc.sett.method, do=sc.sett.do_proj,
+                rho=sc.rho, vx_y=vx_y).numpy()
+        # ADMM iterations with the reference's _update_admm
+        z, w = ref._update._admm_aux(sc.y, sc.sett)
+        tmp = torch.zeros(tuple(sc.y[0].dim))
+        n_it = recipe['admm_iters']
+        obj = torch.zeros(n_it, 3, dtype=torch.float64)
+        cg_iters = []
+        # count CG trips by wrapping the shim's cg (the reference ignores its return value)
+        orig_cg = ref._update.cg
+
+        def counting_cg(*a, **k):
+            r = orig_cg(*a, **k)
+            cg_iters.append(shim_optim.cg.last_n_iter)
+            return r
+
+        ref._update.cg = counting_cg
+        try:
+            for it in range(n_it):
+                y, z, w, tmp, obj = ref._update._update_admm(sc.x, sc.y, z, w, sc.rho, tmp, obj,
+                                                             it, sc.sett)
+                for c in range(C):
+                    out['y%d_it%d' % (c, it)] = sc.y[c].dat.numpy().copy()
+                out['jtv_it%d' % it] = tmp.numpy().copy()
+                # z / w are 3C volumes each: keep their norms and a strided sample
+                for nm, t in (('z', z), ('w', w)):
+                    out['%s_norm_it%d' % (nm, it)] = np.float64(t.double().norm().item())
+                    out['%s_sample_it%d' % (nm, it)] = t.flatten()[::SAMPLE_STRIDE].numpy().copy()
+        finally:
+            ref._update.cg = orig_cg
+        out['obj'] = obj.numpy()
+        out['cg_iters'] = np.array(cg_iters, dtype=np.int32).reshape(n_it, C)
+        out['rho'] = np.float32(float(sc.rho))
+        path = os.path.join(GOLDEN_DIR, name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, 'cg_iters', out['cg_iters'].tolist(), 'obj', obj[:, 0].tolist(),
+              '%.0f KB' % (os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+    main()

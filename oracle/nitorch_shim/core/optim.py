@@ -46,6 +46,9 @@ def cg(A, b, x=None, precond=lambda y: y, max_iter=None, tolerance=1e-5,
         x = torch.zeros_like(b)
     elif not inplace:
         x = x.clone()
+    if isinstance(A, torch.Tensor):
+        A_mat = A
+        A = lambda v: A_mat.mm(v)
 
     r = b - A(x)
     z = precond(r)

@@ -1,0 +1,180 @@
+"""CUDA operators (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import pytest
+import torch
+
+from oracle.nitorch_shim import spatial as OS
+from oracle import unires_port as P
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+DIMS = [(9, 11, 13), (16, 12, 20), (5, 7, 64)]
+VX = [(1.0, 1.0, 1.0), (0.5, 0.8, 2.0)]
+
+
+def _rand(shape, seed):
+    return torch.rand(shape, generator=torch.Generator().manual_seed(seed)) - 0.3
+
+
+@pytest.mark.parametrize('dim', DIMS)
+@pytest.mark.parametrize('vx', VX)
+def test_gradient_divergence_dtd(cuda, dim, vx):
+    from unires_b200 import spatial, _project
+    u, v = _rand(dim, 1), _rand((3,) + dim, 2)
+    tvx = torch.tensor(vx)
+    g = spatial.im_gradient(u.to(cuda), vx=tvx)
+    assert U.rel_l2(g, OS.im_gradient(u, tvx)) < 1e-6
+    d = spatial.im_divergence(v.to(cuda), vx=tvx)
+    assert U.rel_l2(d, OS.im_divergence(v, tvx)) < 1e-6
+    dd = _project._DtD(u.to(cuda), tvx)
+    assert U.rel_l2(dd, P.dtd(u, tvx)) < 1e-6
+    # composed == fused
+    assert U.rel_l2(dd, spatial.im_divergence(g, vx=tvx)) < 1e-6
+
+
+def _affine(seed):
+    from unires_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.rand(3, generator=g) * 4 - 2).tolist()
+    r = (torch.rand(3, generator=g) * 0.2 - 0.1).tolist()
+    m = synth.rigid_matrix(t, r)
+    m[:3, :3] *= 0.9
+    return m.float()
+
+
+@pytest.mark.parametrize('order', [1, 0])
+@pytest.mark.parametrize('lazy', [True, False])
+def test_pull_push_vs_oracle(cuda, order, lazy):
+    from unires_b200 import spatial
+    src_dim, out_dim = (12, 10, 14), (9, 13, 11)
+    mat = _affine(3)
+    src, val = _rand((1, 1) + src_dim, 4), _rand((1, 1) + out_dim, 5)
+    ogrid = OS.affine_grid(mat, out_dim)[None]
+    grid = spatial.affine_grid(mat.to(cuda), out_dim)[None, ...]
+    if not lazy:
+        grid = grid.materialize()
+        assert U.rel_l2(grid, ogrid) < 1e-6
+    pulled = spatial.grid_pull(src.to(cuda), grid, interpolation=order, bound='zero', extrapolate=False)
+    ref = OS.grid_pull(src, ogrid, interpolation=order)
+    assert pulled.shape == ref.shape and U.rel_l2(pulled, ref) < 1e-5
+    pushed = spatial.grid_push(val.to(cuda), grid, shape=src_dim, interpolation=order)
+    ref = OS.grid_push(val, ogrid, shape=src_dim, interpolation=order)
+    assert pushed.shape == ref.shape and U.rel_l2(pushed, ref) < 1e-5
+
+
+def test_pull_integer_shift_is_exact(cuda):
+    from unires_b200 import spatial
+    src = _rand((1, 1, 6, 7, 8), 6)
+    m = torch.eye(4)
+    m[:3, 3] = torch.tensor([1.0, -2.0, 3.0])
+    out = spatial.grid_pull(src.to(cuda), spatial.affine_grid(m.to(cuda), (6, 7, 8))[None, ...])
+    ref = OS.grid_pull(src, OS.affine_grid(m, (6, 7, 8))[None])
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize('name', [n for n in U.GOLDEN_NAMES if n != 'denoise_1ch'])
+def test_proj_apply_vs_oracle_and_golden(cuda, name):
+    from oracle import gen_golden
+    from unires_b200 import _project
+    g, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    for c in range(len(x)):
+        vy, vx = gen_golden.probe_inputs(sc, c)
+        po_o, po = sc.x[c][0].po, x[c][0].po
+        for op, v in (('A', vy), ('At', vx), ('AtA', vy)):
+            out = _project._proj_apply(op, v.to(cuda)[None, None], po, method=sett.method)[0, 0]
+            ref = P.proj_apply(op, v[None, None], po_o, method=sett.method)[0, 0]
+            assert out.shape == ref.shape
+            assert U.rel_l2(out, ref) < 1e-5, (name, op, c)
+            assert U.rel_l2(out, g['%s%d' % (op, c)]) < 1e-5, (name, op, c, 'golden')
+
+
+@pytest.mark.parametrize('name', U.GOLDEN_NAMES)
+def test_lhs_vs_oracle_and_golden(cuda, name):
+    from oracle import gen_golden
+    from unires_b200 import _project
+    g, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    vx_y = torch.ones(3) * float(sc.cfg['vx_y'])
+    for c in range(len(x)):
+        vy, _ = gen_golden.probe_inputs(sc, c)
+        out = _project._proj('AtA', vy.to(cuda), x[c], y[c], method=sett.method, do=sett.do_proj,
+                             rho=sc.rho, vx_y=vx_y)
+        ref = P.proj('AtA', vy, sc.x[c], sc.y[c], method=sc.sett.method, do=sc.sett.do_proj,
+                     rho=sc.rho, vx_y=vx_y)
+        assert U.rel_l2(out, ref) < 1e-5, (name, c)
+        assert U.rel_l2(out, g['lhs%d' % c]) < 1e-5, (name, c, 'golden')
+        # fused dot-product epilogue
+        op = _project.LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj, rho=sc.rho,
+                                  vx_y=vx_y)
+        dot = torch.zeros(1, dtype=torch.float64, device=cuda)
+        out2 = op(vy.to(cuda), dot=dot)
+        want = torch.sum(vy * ref, dtype=torch.float64).item()
+        assert abs(dot.item() - want) < 1e-6 * abs(want)
+        assert torch.equal(out, out2)
+
+
+def test_lhs_two_observations_and_odd_dims(cuda):
+    """Two repeats of one channel with different thick axes, odd extents (no 16-byte rows)."""
+    from unires_b200 import _project, struct
+    dim_y = (13, 15, 17)
+    mat_y = torch.eye(4, dtype=torch.float64)
+    obs_o, obs_g = [], []
+    for axis, f in ((0, 2), (2, 3)):
+        scl = [1.0, 1.0, 1.0]
+        scl[axis] = float(f)
+        mat_x = torch.diag(torch.tensor(scl + [1.0], dtype=torch.float64))
+        dim_x = tuple(int(d // s) for d, s in zip(dim_y, scl))
+        po_o = P.proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, scl=0.07)
+        po_g = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, scl=0.07,
+                                   device=cuda)
+        tau = 0.01 * (1 + axis)
+        obs_o.append(P.Observation(torch.zeros(dim_x), mat_x, tau=tau, po=po_o))
+        obs_g.append(struct._input(dat=None, tau=tau, po=po_g))
+    rec_o = P.Recon(torch.zeros(dim_y), mat_y, lam=0.2)
+    rec_g = struct._output(dat=None, dim=dim_y, mat=mat_y, lam=0.2)
+    v = _rand(dim_y, 9)
+    vx = torch.ones(3)
+    out = _project._proj('AtA', v.to(cuda), obs_g, rec_g, rho=2.0, vx_y=vx)
+    ref = P.proj('AtA', v, obs_o, rec_o, rho=2.0, vx_y=vx)
+    assert U.rel_l2(out, ref) < 1e-5
+
+
+def test_apply_scaling_and_conv_axis(cuda):
+    import ctypes as C
+    from unires_b200 import _project, _lib
+    from torch.nn import functional as F
+    v = _rand((1, 1, 6, 9, 10), 11)
+    for dim in range(3):
+        out = _project._apply_scaling(v.to(cuda), 0.3, dim)
+        assert U.rel_l2(out, P.apply_scaling(v, torch.tensor(0.3), dim)) < 1e-6
+    ker = [0.1, 0.2, 0.4, 0.2, 0.1]
+    for axis, stride in ((0, 1), (1, 2), (2, 3)):
+        shape = [1, 1, 1, 1, 1]
+        shape[2 + axis] = 5
+        k = torch.tensor(ker).reshape(shape)
+        st = [1, 1, 1]
+        st[axis] = stride
+        ref = F.conv3d(v, k, stride=st)
+        out = torch.empty(ref.shape[2:], device=cuda)
+        _lib.check(_lib.lib.ur_conv_axis(_lib.ptr(v.to(cuda)), _lib.i3(v.shape[2:]), _lib.ptr(out),
+                                         axis, _lib.farr(ker), 5, stride, 0, _lib.stream()))
+        assert U.rel_l2(out, ref[0, 0]) < 1e-6
+        back = F.conv_transpose3d(ref, k, stride=st)
+        out2 = torch.empty(back.shape[2:], device=cuda)
+        _lib.check(_lib.lib.ur_conv_axis(_lib.ptr(out), _lib.i3(out.shape), _lib.ptr(out2), axis,
+                                         _lib.farr(ker), 5, stride, 1, _lib.stream()))
+        assert U.rel_l2(out2, back[0, 0]) < 1e-5
+
+
+def test_check_adjoint(cuda):
+    from unires_b200 import _project, synth
+    cfg = synth.scaled(synth.CONFIGS['sr3_256'], (40, 44, 36))
+    for c, rigid in ((0, None), (1, synth.rigid_matrix((1.5, -1.0, 0.5), (0.05, -0.03, 0.04)))):
+        dim_x, mat_x, dim_y, mat_y = synth.geometry(cfg, c)
+        po = _project._proj_info(dim_y, mat_y, dim_x, mat_x, rigid=rigid, prof_ip=2, prof_tp=0,
+                                 scl=0.1, device=cuda)
+        val = _project._check_adjoint(po, 'super-resolution', 'zero', 'linear')
+        assert abs(val.item()) < 1e-2  # float32 sums of O(1e4) terms (reference prints ~1e-6..1e-3)

@@ -1,0 +1,160 @@
+"""CG solve and the ADMM iteration on the GPU against the oracle and the golden fixtures:
+per-iterate relative L2 <= 1e-4 and identical CG trip counts (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gen_golden
+from oracle import unires_port as P
+from oracle.nitorch_shim.core import optim as OO
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _channel_problem(sc, c, cuda):
+    """rhs b and lhs of channel c at z = w = 0 for oracle and product."""
+    from unires_b200 import _project
+    x, y, sett = U.to_device(sc, cuda)
+    vx = torch.ones(3) * float(sc.cfg['vx_y'])
+    kw = dict(method=sc.sett.method, do=sc.sett.do_proj)
+    b = torch.zeros(sc.y[c].dim)
+    for n, obs in enumerate(sc.x[c]):
+        b += obs.tau * P.proj('At', obs.dat, sc.x[c], sc.y[c], n=n, **kw)
+    lhs_o = lambda v: P.proj('AtA', v, sc.x[c], sc.y[c], rho=sc.rho, vx_y=vx, **kw)
+    lhs_g = _project.LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj, rho=sc.rho, vx_y=vx)
+    return b, lhs_o, lhs_g, y[c].dat
+
+
+@pytest.mark.parametrize('name', U.GOLDEN_NAMES)
+@pytest.mark.parametrize('stop', ['max_gain', 'residual'])
+def test_cg_per_iterate_parity_and_trip_count(cuda, name, stop):
+    from unires_b200 import optim
+    _, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    for c in range(len(sc.x)):
+        b, lhs_o, lhs_g, x0 = _channel_problem(sc, c, cuda)
+        iterates = {}
+        xo = sc.y[c].dat.clone()
+        OO.cg(A=lhs_o, b=b, x=xo, max_iter=20, tolerance=1e-3, stop=stop,
+              record=lambda it, xi: iterates.__setitem__(it, xi.clone()))
+        n_ref, obj_ref = OO.cg.last_n_iter, OO.cg.last_obj
+        # full solve with the device-side stop test
+        xg = x0.clone()
+        optim.cg(A=lhs_g, b=b.to(cuda), x=xg, max_iter=20, tolerance=1e-3, stop=stop)
+        info = optim.cg.last
+        assert info.n_iter == n_ref, (name, c, stop)
+        assert U.rel_l2(xg, xo) < U.REL_TOL
+        assert np.allclose(info.obj, obj_ref.numpy(), rtol=1e-5, atol=1e-8 * abs(obj_ref[0].item()))
+        # per-iterate parity: fixed trip counts, no stop test
+        for k in sorted(set([1, 2, 3, n_ref])):
+            xk = x0.clone()
+            optim.cg(A=lhs_g, b=b.to(cuda), x=xk, max_iter=k, tolerance=0, stop=stop)
+            assert optim.cg.last.n_iter == k
+            assert U.rel_l2(xk, iterates[k]) < U.REL_TOL, (name, c, k)
+
+
+def test_cg_generic_callable_path(cuda):
+    """cg() over an arbitrary callable uses the same CUDA vector kernels from a host loop."""
+    from unires_b200 import optim
+    _, recipe = U.load_golden('thickz2_scl')
+    sc = U.build(recipe, *U.port_namespaces())
+    b, lhs_o, lhs_g, x0 = _channel_problem(sc, 0, cuda)
+    xo = sc.y[0].dat.clone()
+    OO.cg(A=lhs_o, b=b, x=xo, max_iter=20, tolerance=1e-3, stop='max_gain')
+    xg = x0.clone()
+    optim.cg(A=lambda v: lhs_g(v), b=b.to(cuda), x=xg, precond=lambda v: v, max_iter=20,
+             tolerance=1e-3, stop='max_gain')
+    assert optim.cg.last.n_iter == OO.cg.last_n_iter
+    assert U.rel_l2(xg, xo) < U.REL_TOL
+
+
+@pytest.mark.parametrize('name', U.GOLDEN_NAMES)
+def test_update_admm_vs_golden_and_oracle(cuda, name):
+    from unires_b200 import _update
+    g, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    C = len(x)
+    z, w = _update._admm_aux(y, sett)
+    tmp = torch.zeros(y[0].dim, device=cuda)
+    n_it = recipe['admm_iters']
+    obj = torch.zeros(n_it, 3, dtype=torch.float64, device=cuda)
+    rho = sc.rho.to(cuda)
+    for it in range(n_it):
+        y, z, w, tmp, obj = _update._update_admm(x, y, z, w, rho, tmp, obj, it, sett)
+        iters = [i.n_iter for i in _update._update_admm.last_cg]
+        assert iters == g['cg_iters'][it].tolist(), (name, it)
+        for c in range(C):
+            assert U.rel_l2(y[c].dat, g['y%d_it%d' % (c, it)]) < U.REL_TOL, (name, it, c)
+        assert U.rel_l2(tmp, g['jtv_it%d' % it]) < 1e-3  # shrink factor: quotient of small numbers
+        zs = z.flatten()[::gen_golden.SAMPLE_STRIDE]
+        ws = w.flatten()[::gen_golden.SAMPLE_STRIDE]
+        assert U.rel_l2(zs, g['z_sample_it%d' % it]) < 1e-3
+        assert U.rel_l2(ws, g['w_sample_it%d' % it]) < 1e-3
+        assert abs(z.double().norm().item() - float(g['z_norm_it%d' % it])) < 1e-3 * float(g['z_norm_it%d' % it]) + 1e-9
+    assert np.allclose(obj.cpu().numpy(), g['obj'], rtol=1e-4)
+
+
+def test_compute_nll_vs_oracle(cuda):
+    from unires_b200 import _update
+    _, recipe = U.load_golden('sr2_rigid')
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    got = [v.item() for v in _update._compute_nll(x, y, sett, sc.rho)]
+    want = [v.item() for v in P.compute_nll(sc.x, sc.y, sc.sett, sc.rho)]
+    assert np.allclose(got, want, rtol=1e-5)
+
+
+def test_relaxation_alpha(cuda):
+    """alpha != 1 (over-relaxation, unires/_update.py:163-164,169-170,177-178,189-190)."""
+    from unires_b200 import _update
+    _, recipe = U.load_golden('thickz2_scl')
+    sc = U.build(recipe, *U.port_namespaces())
+    sc.sett.alpha = 1.5
+    x, y, sett = U.to_device(sc, cuda)
+    zo, wo = P.admm_aux(sc.y)
+    z, w = _update._admm_aux(y, sett)
+    tmp_o, tmp = torch.zeros(sc.y[0].dim), torch.zeros(y[0].dim, device=cuda)
+    obj_o = torch.zeros(2, 3, dtype=torch.float64)
+    obj = torch.zeros(2, 3, dtype=torch.float64, device=cuda)
+    for it in range(2):
+        _, zo, wo, jo, obj_o, _ = P.update_admm(sc.x, sc.y, zo, wo, sc.rho, tmp_o, obj_o, it, sc.sett)
+        y, z, w, tmp, obj = _update._update_admm(x, y, z, w, sc.rho.to(cuda), tmp, obj, it, sett)
+        assert U.rel_l2(z, zo) < 1e-3 and U.rel_l2(w, wo) < 1e-3
+        for c in range(len(x)):
+            assert U.rel_l2(y[c].dat, sc.y[c].dat) < U.REL_TOL
+
+
+def test_jtv_sharded_equals_fused(cuda):
+    """norm2 (per shard) + apply == the fused single-pass prox (multi-GPU composition)."""
+    import ctypes as C
+    from unires_b200 import _lib, _update
+    torch.manual_seed(0)
+    dim = (10, 12, 14)
+    Cn = 3
+    ys = [torch.rand(dim, device=cuda) * 100 for _ in range(Cn)]
+    lam = [0.01, 0.02, 0.015]
+    w0 = torch.rand((Cn, 3) + dim, device=cuda) - 0.5
+    z0 = torch.rand((Cn, 3) + dim, device=cuda) - 0.5
+    vx, rho = (1.0, 1.0, 1.0), 1.7
+    for alpha in (1.0, 0.8):
+        z1, w1, j1 = z0.clone(), w0.clone(), torch.empty(dim, device=cuda)
+        _lib.check(_lib.lib.ur_jtv_prox(_update._ptr_array(ys), _lib.ptr(z1), _lib.ptr(w1), _lib.ptr(j1),
+                                        Cn, _lib.farr(lam), _lib.i3(dim), _lib.f3(vx), rho, alpha,
+                                        _lib.stream()))
+        z2, w2, j2 = z0.clone(), w0.clone(), torch.empty(dim, device=cuda)
+        field = torch.empty(dim, device=cuda)
+        for k, (lo, hi) in enumerate(((0, 2), (2, 3))):  # two "ranks"
+            _lib.check(_lib.lib.ur_jtv_norm2(_update._ptr_array(ys[lo:hi]), _lib.ptr(z2[lo:hi]),
+                                             _lib.ptr(w2[lo:hi]), _lib.ptr(field), hi - lo,
+                                             _lib.farr(lam[lo:hi]), _lib.i3(dim), _lib.f3(vx), rho,
+                                             alpha, 1 if k else 0, _lib.stream()))
+        for lo, hi in ((0, 2), (2, 3)):
+            _lib.check(_lib.lib.ur_jtv_apply(_update._ptr_array(ys[lo:hi]), _lib.ptr(z2[lo:hi]),
+                                             _lib.ptr(w2[lo:hi]), _lib.ptr(field), _lib.ptr(j2), hi - lo,
+                                             _lib.farr(lam[lo:hi]), _lib.i3(dim), _lib.f3(vx), rho,
+                                             alpha, _lib.stream()))
+        assert torch.allclose(z1, z2, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(w1, w2, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(j1, j2, rtol=1e-5, atol=1e-6)

@@ -1,0 +1,48 @@
+"""The travelling oracle (oracle/unires_port.py) against the reference's OWN files
+(/root/reference/unires/*.py imported by path on the shim).  Only runs where the
+reference exists (the build container); skipped on the GPU box."""
+import pytest
+import torch
+
+from oracle import load_reference as LR
+from oracle import unires_port as P
+from tests import _util as U
+
+pytestmark = pytest.mark.skipif(not LR.available(), reason='/root/reference not present')
+
+
+@pytest.mark.parametrize('name', U.GOLDEN_NAMES)
+def test_port_matches_reference_bitwise(name):
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    _, recipe = U.load_golden(name)
+    sp = U.build(recipe, *U.port_namespaces())
+    sr = U.build(recipe, *reference_namespaces())
+    for c in range(len(sp.x)):
+        assert torch.equal(sp.x[c][0].dat, sr.x[c][0].dat)
+        assert torch.equal(sp.y[c].dat, sr.y[c].dat)
+        if sp.sett.do_proj:
+            a, b = sp.x[c][0].po, sr.x[c][0].po
+            assert a.dim_yx == b.dim_yx and a.ratio == b.ratio
+            assert torch.equal(a.smo_ker, b.smo_ker) and torch.equal(a.mat_yx, b.mat_yx)
+            assert int(a.dim_thick) == int(b.dim_thick)
+    zp, wp = P.admm_aux(sp.y)
+    zr, wr = ref._update._admm_aux(sr.y, sr.sett)
+    tp, tr = torch.zeros(sp.y[0].dim), torch.zeros(sr.y[0].dim)
+    op, orf = torch.zeros(2, 3, dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64)
+    for it in range(2):
+        _, zp, wp, jp, op, _ = P.update_admm(sp.x, sp.y, zp, wp, sp.rho, tp, op, it, sp.sett)
+        _, zr, wr, tr, orf = ref._update._update_admm(sr.x, sr.y, zr, wr, sr.rho, tr, orf, it, sr.sett)
+        for c in range(len(sp.x)):
+            assert torch.equal(sp.y[c].dat, sr.y[c].dat)
+        assert torch.equal(zp, zr) and torch.equal(wp, wr) and torch.equal(jp, tr)
+    assert torch.equal(op, orf)
+
+
+def test_step_size_matches_reference():
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    _, recipe = U.load_golden('sr3_thick_xyz')
+    sr = U.build(recipe, *reference_namespaces())
+    sr.sett.rho = None
+    assert torch.equal(P.step_size(sr.x, sr.y, sr.sett), ref._update._step_size(sr.x, sr.y, sr.sett))

@@ -77,6 +77,9 @@ _SIGNATURES = {
     'ur_last_error': (C.c_char_p, []),
     'ur_version': (C.c_int, []),
     'ur_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
+    'ur_launch_count': (C.c_uint64, []),
+    'ur_profile_matvec': (C.c_int, [C.c_int]),
+    'ur_profile_matvec_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_dtd': (C.c_int, [_p, _p, _i3, _f3, _p]),

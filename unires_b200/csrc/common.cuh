@@ -10,6 +10,7 @@ namespace ur {
 
 void set_error(const char *fmt, ...);
 int sm_count();
+void count_launch();  // bumps the process-wide kernel launch counter (ur_launch_count)
 
 #define UR_CUDA_CHECK(expr)                                                         \
   do {                                                                              \
@@ -20,7 +21,11 @@ int sm_count();
       return UR_ERR_CUDA;                                                           \
     }                                                                               \
   } while (0)
-#define UR_LAUNCH_CHECK() UR_CUDA_CHECK(cudaGetLastError())
+#define UR_LAUNCH_CHECK()                                                           \
+  do {                                                                              \
+    ur::count_launch();                                                             \
+    UR_CUDA_CHECK(cudaGetLastError());                                              \
+  } while (0)
 #define UR_REQUIRE(cond, ...)                                                       \
   do {                                                                              \
     if (!(cond)) {                                                                  \

@@ -372,6 +372,28 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   return w;
 }
 
+// ---------------------------------------------------------------------------
+// optional event instrumentation of the matvec launches (bench.py roofline)
+// ---------------------------------------------------------------------------
+struct MatvecProfile {
+  bool on = false;
+  static constexpr int kCap = 8192;
+  cudaEvent_t ev[2 * kCap];
+  int created = 0;
+  int used = 0;
+};
+static MatvecProfile g_prof;
+
+static cudaEvent_t prof_event(int which) {
+  if (!g_prof.on || g_prof.used >= MatvecProfile::kCap) return nullptr;
+  while (g_prof.created <= g_prof.used) {
+    if (cudaEventCreate(&g_prof.ev[2 * g_prof.created]) != cudaSuccess) return nullptr;
+    if (cudaEventCreate(&g_prof.ev[2 * g_prof.created + 1]) != cudaSuccess) return nullptr;
+    ++g_prof.created;
+  }
+  return g_prof.ev[2 * g_prof.used + which];
+}
+
 // Launch one lhs evaluation.  `A` carries the mode-specific pointers.
 static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs &w, LhsArgs A,
                       int variant, cudaStream_t st) {
@@ -389,6 +411,9 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   }
   A.gr = GridReduce{w.partials, w.counter};
   (void)variant;
+  cudaEvent_t e0 = mode == LHS_PLAIN ? prof_event(0) : nullptr;
+  cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
+  if (e0) cudaEventRecord(e0, st);
   switch (mode) {
     case LHS_PLAIN:
       lhs_direct_kernel<LHS_PLAIN><<<P.grid, P.block, 0, st>>>(A);
@@ -399,6 +424,10 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     default:
       lhs_direct_kernel<LHS_ENERGY><<<P.grid, P.block, 0, st>>>(A);
       break;
+  }
+  if (e1) {
+    cudaEventRecord(e1, st);
+    ++g_prof.used;
   }
   UR_LAUNCH_CHECK();
   return UR_OK;
@@ -431,6 +460,26 @@ static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 }  // namespace ur
 
 using namespace ur;
+
+extern "C" int ur_profile_matvec(int enable) {
+  g_prof.on = enable != 0;
+  g_prof.used = 0;
+  return UR_OK;
+}
+
+extern "C" int ur_profile_matvec_read(double *total_ms, int32_t *count) {
+  UR_CUDA_CHECK(cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (int i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    UR_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = g_prof.used;
+  g_prof.used = 0;
+  return UR_OK;
+}
 
 extern "C" size_t ur_lhs_workspace_bytes(const ur_lhs *lhs) {
   LhsPlan P;

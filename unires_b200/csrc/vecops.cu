@@ -17,6 +17,10 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -96,6 +100,7 @@ using namespace ur;
 
 extern "C" const char *ur_last_error(void) { return g_err; }
 extern "C" int ur_version(void) { return 100; }
+extern "C" uint64_t ur_launch_count(void) { return launches(); }
 
 extern "C" int ur_device_info(int *sm, int *major, int *minor) {
   int dev = 0;
