@@ -113,7 +113,8 @@ def test_lhs_vs_oracle_and_golden(cuda, name):
         out2 = op(vy.to(cuda), dot=dot)
         want = torch.sum(vy * ref, dtype=torch.float64).item()
         assert abs(dot.item() - want) < 1e-6 * abs(want)
-        assert torch.equal(out, out2)
+        # the general (rotated) path pushes with atomics: summation order varies run to run
+        assert U.rel_l2(out, out2) < 1e-6
 
 
 def test_lhs_two_observations_and_odd_dims(cuda):

@@ -1,0 +1,115 @@
+"""The TMA streaming lhs kernel against the direct kernel and the oracle: tile / chunk
+boundaries, FOV crops, every thick axis, even/odd scaling, volume edges, all CG epilogues."""
+import pytest
+import torch
+
+from oracle import unires_port as P
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _tune(name, value):
+    from unires_b200 import _lib
+    _lib.check(_lib.lib.ur_tune(name.encode(), int(value)))
+
+
+def _make(dim_y, fov, thick_axis, factor, scl, cuda, denoise=False):
+    """(oracle obs/rec, product obs/rec) for one channel."""
+    from unires_b200 import _project, struct, synth
+    cfg = dict(dim_y=dim_y, fov=fov, vx_y=1.0, thick=[(thick_axis, factor)])
+    dim_x, mat_x, _, mat_y = synth.geometry(cfg, 0)
+    if denoise:
+        return None
+    po_o = P.proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, scl=scl)
+    po_g = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, scl=scl, device=cuda)
+    obs_o = P.Observation(torch.zeros(dim_x), mat_x, tau=0.013, po=po_o)
+    obs_g = struct._input(tau=0.013, po=po_g)
+    rec_o = P.Recon(torch.zeros(dim_y), mat_y, lam=0.21)
+    rec_g = struct._output(dim=dim_y, mat=mat_y, lam=0.21)
+    return obs_o, rec_o, obs_g, rec_g
+
+
+CASES = [
+    # dim_y, fov, thick axis, factor, scl, stream_mc
+    ((20, 24, 132), (14, 19, 100), 0, 4, 0.0, 0),
+    ((20, 24, 132), (14, 19, 100), 0, 4, 0.1, 7),
+    ((24, 21, 136), (20, 16, 120), 1, 4, 0.05, 9),
+    ((24, 21, 136), None, 1, 2, 0.0, 0),
+    ((19, 22, 140), (15, 18, 131), 2, 4, 0.1, 6),
+    ((19, 22, 260), None, 2, 2, 0.0, 0),
+    ((33, 17, 128), None, 0, 3, 0.0, 12),
+    ((16, 40, 64), (16, 33, 60), 2, 3, 0.2, 5),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_stream_equals_direct_and_oracle(cuda, case):
+    from unires_b200 import _project
+    dim_y, fov, axis, factor, scl, mc = case
+    obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(dim_y, generator=g) - 0.4
+    vx = torch.ones(3)
+    ref = P.proj('AtA', v, [obs_o], rec_o, rho=1.7, vx_y=vx)
+    op = _project.LhsOperator([obs_g], rec_g, rho=1.7, vx_y=vx)
+    try:
+        _tune('lhs_variant', 1)
+        direct = op(v.to(cuda))
+        _tune('lhs_variant', 0)
+        _tune('stream_mc', mc)
+        dot = torch.zeros(1, dtype=torch.float64, device=cuda)
+        stream = op(v.to(cuda), dot=dot)
+    finally:
+        _tune('lhs_variant', 0)
+        _tune('stream_mc', 0)
+    assert U.rel_l2(direct, ref) < 1e-5
+    assert U.rel_l2(stream, ref) < 1e-5
+    assert U.rel_l2(stream, direct) < 1e-6
+    want = torch.sum(v * ref, dtype=torch.float64).item()
+    assert abs(dot.item() - want) < 1e-5 * abs(want)
+
+
+@pytest.mark.parametrize('dim', [(18, 20, 128), (9, 11, 12), (40, 8, 256)])
+def test_stream_denoise_lhs(cuda, dim):
+    """do_proj = False: tau * v + rho lam^2 DtD v (configs[0] path)."""
+    from unires_b200 import _project, struct
+    g = torch.Generator().manual_seed(5)
+    v = torch.rand(dim, generator=g)
+    vx = torch.tensor([1.0, 0.5, 2.0])
+    obs_o = P.Observation(torch.zeros(dim), torch.eye(4), tau=0.02, po=None)
+    rec_o = P.Recon(torch.zeros(dim), torch.eye(4), lam=0.3)
+    ref = P.proj('AtA', v, [obs_o], rec_o, do=False, rho=0.9, vx_y=vx)
+    op = _project.LhsOperator([struct._input(tau=0.02)], struct._output(dim=dim, lam=0.3), do=False,
+                              rho=0.9, vx_y=vx)
+    try:
+        _tune('stream_mc', 5)
+        out = op(v.to(cuda))
+    finally:
+        _tune('stream_mc', 0)
+    assert U.rel_l2(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize('stop', ['max_gain', 'residual'])
+def test_cg_stream_vs_direct(cuda, stop):
+    """Whole CG solves (all epilogues: residual init, energy + p update) agree between kernels."""
+    from unires_b200 import _project, optim
+    obs_o, rec_o, obs_g, rec_g = _make((24, 28, 132), (20, 22, 120), 1, 4, 0.1, cuda)
+    g = torch.Generator().manual_seed(8)
+    b = (torch.rand((24, 28, 132), generator=g) * 0.1).to(cuda)
+    x0 = torch.rand((24, 28, 132), generator=g).to(cuda)
+    op = _project.LhsOperator([obs_g], rec_g, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+    res = {}
+    try:
+        for variant in (1, 0):
+            _tune('lhs_variant', variant)
+            _tune('stream_mc', 0 if variant else 11)
+            x = x0.clone()
+            optim.cg(A=op, b=b, x=x, max_iter=20, tolerance=1e-3, stop=stop)
+            res[variant] = (x, optim.cg.last.n_iter, optim.cg.last.obj)
+    finally:
+        _tune('lhs_variant', 0)
+        _tune('stream_mc', 0)
+    assert res[0][1] == res[1][1]
+    assert U.rel_l2(res[0][0], res[1][0]) < 1e-5
+    assert all(abs(a - b_) <= 1e-7 * abs(b_) + 1e-12 for a, b_ in zip(res[0][2], res[1][2]))

@@ -80,6 +80,7 @@ _SIGNATURES = {
     'ur_launch_count': (C.c_uint64, []),
     'ur_profile_matvec': (C.c_int, [C.c_int]),
     'ur_profile_matvec_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    'ur_tune': (C.c_int, [C.c_char_p, C.c_int]),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_dtd': (C.c_int, [_p, _p, _i3, _f3, _p]),

@@ -1,0 +1,580 @@
+// TMA-staged streaming kernel for the CG left-hand side (sm_100a)
+//
+//   out = w_ident * v  +  tau * A'S^2A v  +  rho lam^2 * D'D v        (+ CG epilogue)
+//
+// for the lattice-aligned operators of solver.cuh (at most one observation term).
+// A CTA owns a (TO x TZ) = (8 x 128) column of the volume in the two non-marching axes
+// and marches along the third ("m": x, or y when the slices are thick along y) over a
+// chunk of planes.  Each plane tile (with a 1-row / hz-column halo) is brought into a
+// shared-memory ring by ONE cp.async.bulk.tensor (TMA) per plane, completing on an
+// mbarrier; out-of-volume elements are zero-filled by the TMA unit, which is exactly
+// the reference's bound='zero'.  Every thread keeps the m-1 / m / m+1 values of its own
+// z-quad in registers, so per plane it reads 3 float4 + 2 floats from shared memory for
+// the 7-point D'D stencil.  The slice-profile term is evaluated through the decimated
+// grid, as the reference does (pull -> conv -> scale -> conv' -> push), but entirely
+// on-chip:
+//   thick along m: each low-res row j is formed ONCE per thread when the march reaches
+//                  its first plane (K taps over the look-ahead planes of the ring) and
+//                  parked in a thread-private shared-memory slot until its last plane;
+//   thick along z: the low-res row segment of the NEXT plane is formed cooperatively
+//                  into a double-buffered shared array while the current plane is output.
+// HBM traffic is the algorithmic 8 bytes per voxel (+ halo re-reads served by L2).
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "solver.cuh"
+
+namespace ur {
+
+constexpr int TO = 8;      // rows of the tile (one warp per row)
+constexpr int TZ = 128;    // z extent of the tile (32 lanes x float4)
+constexpr int NTHR = 256;
+constexpr int kMaxSlots = 24;
+constexpr int kLrzPitch = TZ / 2 + 8;
+
+enum { SK_NONE = 0, SK_CROP = 1, SK_THICK_M = 2, SK_THICK_Z = 3 };
+enum { SC_NONE = 0, SC_CONV = 1, SC_M = 2, SC_O = 3, SC_Z = 4 };
+
+struct StreamTerm {
+  int kind;
+  float tau;
+  int r, K, off, nj;
+  int lo_m, hi_m, lo_o, hi_o, lo_z, hi_z;
+  int scl_kind, scl_off;
+  float s_even, s_odd;
+  float ker[UR_MAX_TAPS];
+};
+
+struct StreamArgs {
+  int nm, no, nz;
+  long long gs_m, gs_o;  // element strides of the marching / row axis in global memory
+  int march_y;
+  float iv_m, iv_o, iv_z, rl2, w_ident;
+  StreamTerm T;
+  int mc, L, B, ns, hz, sz, plane_floats, nlr;
+  const float *v;
+  float *out;
+  const float *b;
+  float *r;
+  float *p;
+  int update_p;
+  const int *done;
+  GridReduce gr;
+  FinalizeArgs fin;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ float dtd1(float lo, float c, float hi, bool has_lo, float iv) {
+  const float gi = (hi - c) * iv;
+  const float gm = has_lo ? (c - lo) * iv : 0.f;
+  return (gm - gi) * iv;
+}
+
+__device__ __forceinline__ float comp(const float4 &q, int k) {
+  return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHR)
+    lhs_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[kMaxWarps];
+  __shared__ uint64_t s_bar[kMaxSlots];
+  __shared__ float s_ker[UR_MAX_TAPS];
+  if (a.done && *a.done) return;
+
+  float *ring = reinterpret_cast<float *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  float *lrm = ring + (size_t)a.ns * a.plane_floats;  // [nlr][TO][TZ]  (thick along m)
+  float *lrz = lrm + (size_t)a.nlr * TO * TZ;         // [2][TO][kLrzPitch] (thick along z)
+
+  const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+  const int z0 = blockIdx.x * TZ, o0 = blockIdx.y * TO, m0 = blockIdx.z * a.mc;
+  const int m1 = min(m0 + a.mc, a.nm);
+  const int o = o0 + row, z = z0 + 4 * lane;
+  const bool active = (o < a.no) && (z < a.nz);
+  const StreamTerm &T = a.T;
+
+  const int u_begin = m0 - a.B;
+  const int first = u_begin - 1;
+  const int last = m1 - 1 + a.L;
+  const uint32_t plane_bytes = (uint32_t)(a.sz * (TO + 2) * sizeof(float));
+
+  if (tid < UR_MAX_TAPS) s_ker[tid] = T.ker[tid];
+  if (tid == 0) {
+    for (int s = 0; s < a.ns; ++s) mbar_init(&s_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int q) {
+    const int s = (q - first) % a.ns;
+    mbar_expect_tx(&s_bar[s], plane_bytes);
+    if (a.march_y)
+      tma_load_3d(ring + (size_t)s * a.plane_floats, &tmap, &s_bar[s], z0 - a.hz, q, o0 - 1);
+    else
+      tma_load_3d(ring + (size_t)s * a.plane_floats, &tmap, &s_bar[s], z0 - a.hz, o0 - 1, q);
+  };
+  auto wait_plane = [&](int q) {
+    const int k = q - first;
+    mbar_wait(&s_bar[k % a.ns], (uint32_t)((k / a.ns) & 1));
+  };
+  auto plane_ptr = [&](int q) -> const float * {
+    return ring + (size_t)((q - first) % a.ns) * a.plane_floats;
+  };
+  const int own = (row + 1) * a.sz + a.hz + 4 * lane;  // this thread's quad inside a plane
+  auto quad = [&](int q) -> float4 {
+    return *reinterpret_cast<const float4 *>(plane_ptr(q) + own);
+  };
+
+  if (tid == 0)
+    for (int q = first; q < first + a.ns && q <= last; ++q) issue(q);
+
+  // ---- per-thread constants of the observation term ----
+  const bool o_in = T.kind != SK_NONE && o >= T.lo_o && o < T.hi_o;
+  float4 zmask = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (T.kind != SK_NONE) {
+    zmask.x = (z + 0 >= T.lo_z && z + 0 < T.hi_z) ? 1.f : 0.f;
+    zmask.y = (z + 1 >= T.lo_z && z + 1 < T.hi_z) ? 1.f : 0.f;
+    zmask.z = (z + 2 >= T.lo_z && z + 2 < T.hi_z) ? 1.f : 0.f;
+    zmask.w = (z + 3 >= T.lo_z && z + 3 < T.hi_z) ? 1.f : 0.f;
+  }
+  // scaling that alternates along a *thin* axis is a per-voxel factor
+  float4 thin = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (T.scl_kind == SC_O) {
+    const float f = ((o - T.scl_off) & 1) ? T.s_odd : T.s_even;
+    thin = make_float4(f, f, f, f);
+  } else if (T.scl_kind == SC_Z) {
+    const float f0 = ((z - T.scl_off) & 1) ? T.s_odd : T.s_even;
+    const float f1 = ((z - T.scl_off) & 1) ? T.s_even : T.s_odd;
+    thin = make_float4(f0, f1, f0, f1);
+  }
+  // thick along z: low-res rows touching this tile
+  int jz_lo = 0, njt = 0;
+  if (T.kind == SK_THICK_Z) {
+    const int a0 = z0 - T.off - T.K + 1;
+    jz_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+    int jz_hi = (z0 + TZ - 1 - T.off) >= 0 ? (z0 + TZ - 1 - T.off) / T.r : -1;
+    if (jz_hi > T.nj - 1) jz_hi = T.nj - 1;
+    njt = jz_hi - jz_lo + 1;
+    if (njt < 0) njt = 0;
+  }
+  auto build_lrz = [&](int q) {  // low-res z-rows of plane q -> lrz[q & 1]
+    float *dst = lrz + (size_t)(q & 1) * TO * kLrzPitch;
+    const float *P = plane_ptr(q);
+    for (int idx = tid; idx < TO * njt; idx += NTHR) {
+      const int rr = idx / njt, jj = idx - rr * njt;
+      const int j = jz_lo + jj;
+      const float *src = P + (rr + 1) * a.sz + a.hz + (j * T.r + T.off - z0);
+      float acc = 0.f;
+      for (int t = 0; t < T.K; ++t) acc = fmaf(s_ker[t], src[t], acc);
+      if (T.scl_kind == SC_CONV) acc *= (j & 1) ? T.s_odd : T.s_even;
+      dst[rr * kLrzPitch + jj] = acc;
+    }
+  };
+
+  // ---- prime the pipeline ----
+  for (int q = first; q < u_begin + a.L; ++q) wait_plane(q);
+  float4 prev = quad(first), cur = quad(u_begin);
+  if (T.kind == SK_THICK_Z) {
+    // plane u_begin is resident (L >= 1 means planes up to u_begin + L - 1 >= u_begin)
+    build_lrz(u_begin);
+    __syncthreads();
+  }
+
+  double part = 0.0;
+  for (int u = u_begin; u < m1; ++u) {
+    wait_plane(u + a.L);
+    const float4 next = quad(u + 1);
+
+    if (T.kind == SK_THICK_M && o_in && active) {
+      const int t0 = u - T.off;
+      if (t0 >= 0 && t0 % T.r == 0) {
+        const int j = t0 / T.r;
+        if (j < T.nj) {  // low-res row j starts at this plane: form it once, park it
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < T.K; ++t) {
+            const float4 q = t == 0 ? cur : (t == 1 ? next : quad(u + t));
+            const float k = s_ker[t];
+            acc.x = fmaf(k, q.x, acc.x);
+            acc.y = fmaf(k, q.y, acc.y);
+            acc.z = fmaf(k, q.z, acc.z);
+            acc.w = fmaf(k, q.w, acc.w);
+          }
+          float s = 1.f;
+          if (T.scl_kind == SC_CONV) s = (j & 1) ? T.s_odd : T.s_even;
+          acc.x *= s * zmask.x;
+          acc.y *= s * zmask.y;
+          acc.z *= s * zmask.z;
+          acc.w *= s * zmask.w;
+          *reinterpret_cast<float4 *>(lrm + ((size_t)(j % a.nlr) * TO + row) * TZ + 4 * lane) = acc;
+        }
+      }
+    }
+    if (T.kind == SK_THICK_Z && u + 1 < m1) build_lrz(u + 1);
+
+    if (u >= m0 && active) {
+      const float *rowp = plane_ptr(u) + own;
+      const float4 om = *reinterpret_cast<const float4 *>(rowp - a.sz);
+      const float4 op = *reinterpret_cast<const float4 *>(rowp + a.sz);
+      const float zl = rowp[-1], zr = rowp[4];
+      const size_t gi = (size_t)u * a.gs_m + (size_t)o * a.gs_o + z;
+      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
+      if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
+      if (MODE == LHS_ENERGY && a.update_p) {
+        rq = *reinterpret_cast<const float4 *>(a.r + gi);
+        pq = *reinterpret_cast<const float4 *>(a.p + gi);
+      }
+      // observation term
+      float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
+      float mfac = T.tau;
+      if (T.scl_kind == SC_M) mfac *= ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
+      if (T.kind == SK_CROP) {
+        if (o_in && u >= T.lo_m && u < T.hi_m) {
+          dat.x = cur.x * zmask.x;
+          dat.y = cur.y * zmask.y;
+          dat.z = cur.z * zmask.z;
+          dat.w = cur.w * zmask.w;
+        }
+      } else if (T.kind == SK_THICK_M) {
+        const int up = u - T.off;
+        if (o_in && up >= 0) {
+          int j_hi = up / T.r;
+          if (j_hi > T.nj - 1) j_hi = T.nj - 1;
+          const int a0 = up - T.K + 1;
+          const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+          for (int j = j_lo; j <= j_hi; ++j) {
+            const float4 lr = *reinterpret_cast<const float4 *>(
+                lrm + ((size_t)(j % a.nlr) * TO + row) * TZ + 4 * lane);
+            const float k = s_ker[up - j * T.r];
+            dat.x = fmaf(k, lr.x, dat.x);
+            dat.y = fmaf(k, lr.y, dat.y);
+            dat.z = fmaf(k, lr.z, dat.z);
+            dat.w = fmaf(k, lr.w, dat.w);
+          }
+        }
+      } else if (T.kind == SK_THICK_Z) {
+        if (o_in && u >= T.lo_m && u < T.hi_m) {
+          const float *lr = lrz + ((size_t)(u & 1) * TO + row) * kLrzPitch;
+          float d[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int up = z + k - T.off;
+            float acc = 0.f;
+            if (up >= 0) {
+              int j_hi = up / T.r;
+              if (j_hi > T.nj - 1) j_hi = T.nj - 1;
+              const int a0 = up - T.K + 1;
+              const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+              for (int j = j_lo; j <= j_hi; ++j)
+                acc = fmaf(s_ker[up - j * T.r], lr[j - jz_lo], acc);
+            }
+            d[k] = acc;
+          }
+          dat = make_float4(d[0], d[1], d[2], d[3]);
+        }
+      }
+      const bool mlo = u > 0, olo = o > 0;
+      float val[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float c = comp(cur, k);
+        const float left = k == 0 ? zl : comp(cur, k - 1);
+        const float right = k == 3 ? zr : comp(cur, k + 1);
+        const float tm = dtd1(comp(prev, k), c, comp(next, k), mlo, a.iv_m);
+        const float to = dtd1(comp(om, k), c, comp(op, k), olo, a.iv_o);
+        const float tz = dtd1(left, c, right, (z + k) > 0, a.iv_z);
+        const float dtd = (tm + to) + tz;
+        const float data = a.w_ident * c + mfac * (comp(thin, k) * comp(dat, k));
+        val[k] = data + a.rl2 * dtd;
+      }
+      if (MODE == LHS_PLAIN) {
+        *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur, k), val[k]);
+      } else if (MODE == LHS_RESID) {
+        float4 rr;
+        rr.x = __fsub_rn(bq.x, val[0]);
+        rr.y = __fsub_rn(bq.y, val[1]);
+        rr.z = __fsub_rn(bq.z, val[2]);
+        rr.w = __fsub_rn(bq.w, val[3]);
+        *reinterpret_cast<float4 *>(a.r + gi) = rr;
+        *reinterpret_cast<float4 *>(a.p + gi) = rr;
+        part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
+                (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur, k));
+        if (a.update_p) {
+          const float beta = (float)a.fin.st->beta;
+          float4 pn;
+          pn.x = __fadd_rn(__fmul_rn(beta, pq.x), rq.x);
+          pn.y = __fadd_rn(__fmul_rn(beta, pq.y), rq.y);
+          pn.z = __fadd_rn(__fmul_rn(beta, pq.z), rq.z);
+          pn.w = __fadd_rn(__fmul_rn(beta, pq.w), rq.w);
+          *reinterpret_cast<float4 *>(a.p + gi) = pn;
+        }
+      }
+    }
+    prev = cur;
+    cur = next;
+    __syncthreads();  // everyone is done with plane u-1 (and lrz of plane u is complete)
+    if (tid == 0) {
+      const int q = u - 1 + a.ns;
+      if (q <= last) issue(q);
+    }
+  }
+  double total;
+  if (grid_sum(part, a.gr, s_red, &total) && tid == 0) finalize(a.fin, total);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault,
+                                         &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void *ptr;
+  int nx, ny, nz, sz, march_y;
+  bool operator==(const MapKey &o) const {
+    return ptr == o.ptr && nx == o.nx && ny == o.ny && nz == o.nz && sz == o.sz &&
+           march_y == o.march_y;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey &k) const {
+    size_t h = (size_t)k.ptr;
+    h = h * 1315423911u + k.nx;
+    h = h * 1315423911u + k.ny;
+    h = h * 1315423911u + k.nz;
+    h = h * 1315423911u + k.sz * 2 + k.march_y;
+    return h;
+  }
+};
+
+static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y,
+                           CUtensorMap *out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{v, nx, ny, nz, sz, march_y};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
+  cuuint64_t gstr[2] = {(cuuint64_t)nz * 4, (cuuint64_t)nz * ny * 4};
+  cuuint32_t box[3] = {(cuuint32_t)sz, march_y ? 1u : (cuuint32_t)(TO + 2),
+                       march_y ? (cuuint32_t)(TO + 2) : 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)v, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
+static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
+
+int stream_mc_override = 0;  // test / tuning hook (planes per chunk), 0 = automatic
+
+int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
+  (void)variant;
+  if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
+  if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
+  if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
+
+  StreamArgs S;
+  memset(&S, 0, sizeof(S));
+  StreamTerm &T = S.T;
+  T.kind = SK_NONE;
+  T.r = T.K = 1;
+  T.s_even = T.s_odd = 1.f;
+  int march = 0;  // 0: x, 1: y
+  int hz = 4;
+  if (A.nterm == 1) {
+    const LatticeTerm &L = A.term[0];
+    if (L.axis == 1) march = 1;
+    const int ax_m = march, ax_o = 1 - march;
+    T.tau = L.tau;
+    T.r = L.r;
+    T.K = L.K;
+    T.off = L.off;
+    T.nj = L.nj;
+    T.lo_m = L.lo[ax_m];
+    T.hi_m = L.hi[ax_m];
+    T.lo_o = L.lo[ax_o];
+    T.hi_o = L.hi[ax_o];
+    T.lo_z = L.lo[2];
+    T.hi_z = L.hi[2];
+    for (int t = 0; t < UR_MAX_TAPS; ++t) T.ker[t] = L.ker[t];
+    T.s_even = L.s_even;
+    T.s_odd = L.s_odd;
+    T.scl_off = L.scl_off;
+    if (L.axis < 0) {
+      T.kind = SK_CROP;
+    } else if (L.axis == 2) {
+      T.kind = SK_THICK_Z;
+      if (T.r < 2 || T.K - 1 > 8) return UR_ERR_UNSUPPORTED;
+      hz = (T.K - 1 + 3) / 4 * 4;
+      if (hz < 4) hz = 4;
+      T.lo_z = 0;
+      T.hi_z = A.nz;
+    } else {
+      T.kind = SK_THICK_M;
+      if (T.K - 1 > 12) return UR_ERR_UNSUPPORTED;
+      T.lo_m = 0;
+      T.hi_m = march ? A.ny : A.nx;
+    }
+    if (L.scl_axis < 0)
+      T.scl_kind = SC_NONE;
+    else if (L.scl_axis == L.axis)
+      T.scl_kind = SC_CONV;
+    else if (L.scl_axis == 2)
+      T.scl_kind = SC_Z;
+    else
+      T.scl_kind = (L.scl_axis == ax_m) ? SC_M : SC_O;
+  }
+  S.march_y = march;
+  S.nm = march ? A.ny : A.nx;
+  S.no = march ? A.nx : A.ny;
+  S.nz = A.nz;
+  S.gs_m = march ? (long long)A.nz : (long long)A.ny * A.nz;
+  S.gs_o = march ? (long long)A.ny * A.nz : (long long)A.nz;
+  S.iv_m = march ? A.ivy : A.ivx;
+  S.iv_o = march ? A.ivx : A.ivy;
+  S.iv_z = A.ivz;
+  S.rl2 = A.rl2;
+  S.w_ident = A.w_ident;
+  S.L = 1;
+  S.B = 0;
+  S.nlr = 0;
+  if (T.kind == SK_THICK_M) {
+    S.L = T.K - 1 > 1 ? T.K - 1 : 1;
+    S.B = T.K - 1;
+    S.nlr = (T.K + T.r - 1) / T.r + 1;
+    if (S.nlr > 6) return UR_ERR_UNSUPPORTED;
+  }
+  S.ns = S.L + 2 + 3;
+  if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
+  S.hz = hz;
+  S.sz = TZ + 2 * hz;
+  S.plane_floats = (S.sz * (TO + 2) + 31) / 32 * 32;
+  const size_t smem = ((size_t)S.ns * S.plane_floats + (size_t)S.nlr * TO * TZ +
+                       (T.kind == SK_THICK_Z ? 2 * TO * kLrzPitch : 0)) *
+                          sizeof(float) +
+                      128;  // slack for the 128-byte alignment of the ring
+  if (smem > 200 * 1024) return UR_ERR_UNSUPPORTED;
+
+  const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, TO);
+  int chunks = (int)((3u * (unsigned)sm_count() + gx * gy / 2) / (gx * gy));
+  if (chunks < 1) chunks = 1;
+  int mc = (S.nm + chunks - 1) / chunks;
+  const int mc_min = 4 * (S.B + S.L + 1);  // keep the warm-up planes a small fraction
+  if (mc < mc_min) mc = mc_min;
+  if (stream_mc_override > 0) mc = stream_mc_override;
+  if (mc > S.nm) mc = S.nm;
+  S.mc = mc;
+  const unsigned gz = div_up(S.nm, mc);
+
+  CUtensorMap map;
+  if (!get_tensor_map(A.v, A.nx, A.ny, A.nz, S.sz, march, &map)) return UR_ERR_UNSUPPORTED;
+
+  S.v = A.v;
+  S.out = A.out;
+  S.b = A.b;
+  S.r = A.r;
+  S.p = A.p;
+  S.update_p = A.update_p;
+  S.done = A.done;
+  S.gr = A.gr;
+  S.fin = A.fin;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_PLAIN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_RESID>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_ENERGY>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(gx, gy, gz), block(NTHR);
+  switch (mode) {
+    case LHS_PLAIN:
+      lhs_stream_kernel<LHS_PLAIN><<<grid, block, smem, st>>>(map, S);
+      break;
+    case LHS_RESID:
+      lhs_stream_kernel<LHS_RESID><<<grid, block, smem, st>>>(map, S);
+      break;
+    default:
+      lhs_stream_kernel<LHS_ENERGY><<<grid, block, smem, st>>>(map, S);
+      break;
+  }
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+}  // namespace ur

@@ -22,39 +22,9 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
                        void *d_ws, size_t ws_bytes, cudaStream_t st);
 int scratch_reduce(GridReduce *gr);  // vecops.cu
 
-constexpr int kMaxFused = 4;
-
-struct LatticeTerm {
-  float tau;
-  int axis;  // correlation axis, -1 = pure crop
-  int r, K, off, nj;
-  int lo[3], hi[3];
-  int scl_axis;  // -1 = no even/odd scaling
-  int scl_off;
-  float s_even, s_odd;
-  float ker[UR_MAX_TAPS];
-};
-
-enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2 };
-
-struct LhsArgs {
-  int nx, ny, nz;
-  float ivx, ivy, ivz;
-  float rl2;      // rho * lam^2
-  float w_ident;  // sum of tau over identity observations (do_proj = 0)
-  const float *acc;
-  int nterm;
-  LatticeTerm term[kMaxFused];
-  const float *v;
-  float *out;      // PLAIN: A v
-  const float *b;  // RESID / ENERGY
-  float *r;        // RESID: r = b - A v ; ENERGY (p update): read
-  float *p;        // RESID: p = r       ; ENERGY (p update): p = beta p + r
-  int update_p;    // ENERGY only
-  const int *done;
-  GridReduce gr;
-  FinalizeArgs fin;
-};
+// lhs_stream.cu: TMA-staged streaming kernel.  Returns UR_ERR_UNSUPPORTED (without
+// setting an error) when the problem does not fit it, so the caller falls back.
+int lhs_stream_launch(int mode, const LhsArgs &a, int variant, cudaStream_t st);
 
 __device__ __forceinline__ float eval_term(const LatticeTerm &T, const float *__restrict__ v,
                                            const int (&i)[3], size_t lin, const int (&n)[3],
@@ -375,6 +345,9 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 // ---------------------------------------------------------------------------
 // optional event instrumentation of the matvec launches (bench.py roofline)
 // ---------------------------------------------------------------------------
+extern int stream_mc_override;  // lhs_stream.cu
+static int g_lhs_variant = 0;
+
 struct MatvecProfile {
   bool on = false;
   static constexpr int kCap = 8192;
@@ -410,10 +383,21 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
   }
   A.gr = GridReduce{w.partials, w.counter};
-  (void)variant;
   cudaEvent_t e0 = mode == LHS_PLAIN ? prof_event(0) : nullptr;
   cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
   if (e0) cudaEventRecord(e0, st);
+  // variant 0 = automatic (TMA streaming kernel when it applies), 1 = force the direct kernel
+  if (variant == 0) variant = g_lhs_variant;
+  if (variant != 1) {
+    const int rc = lhs_stream_launch(mode, A, variant, st);
+    if (rc != UR_ERR_UNSUPPORTED) {
+      if (e1 && rc == UR_OK) {
+        cudaEventRecord(e1, st);
+        ++g_prof.used;
+      }
+      return rc;
+    }
+  }
   switch (mode) {
     case LHS_PLAIN:
       lhs_direct_kernel<LHS_PLAIN><<<P.grid, P.block, 0, st>>>(A);
@@ -460,6 +444,19 @@ static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 }  // namespace ur
 
 using namespace ur;
+
+extern "C" int ur_tune(const char *name, int value) {
+  UR_REQUIRE(name != nullptr, "ur_tune: null name");
+  if (!strcmp(name, "lhs_variant")) {
+    g_lhs_variant = value;
+  } else if (!strcmp(name, "stream_mc")) {
+    stream_mc_override = value;
+  } else {
+    set_error("ur_tune: unknown knob '%s'", name);
+    return UR_ERR_ARG;
+  }
+  return UR_OK;
+}
 
 extern "C" int ur_profile_matvec(int enable) {
   g_prof.on = enable != 0;

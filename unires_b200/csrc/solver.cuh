@@ -47,6 +47,46 @@ __device__ __forceinline__ void record_objective(CgState *st, int n, double o, d
   if (fabs(gain) < tol) st->done = 1;
 }
 
+// ---------------------------------------------------------------------------
+// lhs kernel arguments (shared by the direct and the streaming kernels)
+// ---------------------------------------------------------------------------
+constexpr int kMaxFused = 4;
+
+// One "lattice" observation (identity rotation, integer shift): along `axis`
+//   x[j] = s_j * sum_t ker[t] * v[j*r + t + off],  0 <= j < nj   (v = 0 outside the grid)
+// and a plain crop [lo, hi) on the other two axes.
+struct LatticeTerm {
+  float tau;
+  int axis;  // correlation axis, -1 = pure crop
+  int r, K, off, nj;
+  int lo[3], hi[3];
+  int scl_axis;  // -1 = no even/odd scaling
+  int scl_off;
+  float s_even, s_odd;
+  float ker[UR_MAX_TAPS];
+};
+
+enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2 };
+
+struct LhsArgs {
+  int nx, ny, nz;
+  float ivx, ivy, ivz;
+  float rl2;      // rho * lam^2
+  float w_ident;  // sum of tau over identity observations (do_proj = 0)
+  const float *acc;
+  int nterm;
+  LatticeTerm term[kMaxFused];
+  const float *v;
+  float *out;      // PLAIN: A v
+  const float *b;  // RESID / ENERGY
+  float *r;        // RESID: r = b - A v ; ENERGY (p update): read
+  float *p;        // RESID: p = r       ; ENERGY (p update): p = beta p + r
+  int update_p;    // ENERGY only
+  const int *done;
+  GridReduce gr;
+  FinalizeArgs fin;
+};
+
 // Executed by ONE thread of the last block.
 __device__ __forceinline__ void finalize(const FinalizeArgs &f, double total) {
   CgState *st = f.st;

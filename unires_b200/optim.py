@@ -45,6 +45,9 @@ def stop_rule(stop, tolerance, verbose=False):
     return _lib.UR_STOP_RESIDUAL if stop[0].lower() == 'e' else _lib.UR_STOP_ENERGY
 
 
+_STATE_BYTES = 4096  # >= sizeof(CgState) in csrc/solver.cuh
+
+
 class CgInfo:
     """Result handle of the last device-side solve (lazy: reading syncs)."""
 
@@ -85,7 +88,10 @@ def cg_fused(A, b, x, max_iter, tolerance, rule, variant=0, ws=None):
     opts = _lib.ur_cg_opts(int(max_iter), int(rule), float(tolerance or 0.0), int(variant))
     st = stream()
     check(lib.ur_cg_solve(C.byref(A.c), ptr(b), ptr(x), ptr(ws), ws.numel(), C.byref(opts), st))
-    return CgInfo(ws, st)
+    # the workspace is shared by consecutive solves: keep a stream-ordered snapshot of the
+    # device-side CG state (head of the workspace) for this solve's result handle
+    snap = ws[:_STATE_BYTES].clone()
+    return CgInfo(snap, st)
 
 
 def cg(A, b, x=None, precond=None, max_iter=None, tolerance=1e-5, verbose=False,
