@@ -34,6 +34,9 @@ constexpr int TO = 8;      // rows of the tile (one warp per row)
 constexpr int TZ = 128;    // z extent of the tile (32 lanes x float4)
 constexpr int NTHR = 256;
 constexpr int kMaxSlots = 24;
+#ifndef UR_STREAM_MIN_BLOCKS
+#define UR_STREAM_MIN_BLOCKS 3
+#endif
 constexpr int kLrzPitch = TZ / 2 + 8;
 
 enum { SK_NONE = 0, SK_CROP = 1, SK_THICK_M = 2, SK_THICK_Z = 3 };
@@ -55,7 +58,10 @@ struct StreamArgs {
   int march_y;
   float iv_m, iv_o, iv_z, rl2, w_ident;
   StreamTerm T;
-  int mc, L, B, ns, hz, sz, plane_floats, nlr;
+  int q;     // plane-tiles per CTA: contiguous range in (column, plane) order
+  int ncol;  // number of (o, z) columns
+  int gx;    // columns along z
+  int L, B, ns, hz, sz, plane_floats, nlr;
   const float *v;
   float *out;
   const float *b;
@@ -101,18 +107,31 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
-__device__ __forceinline__ float dtd1(float lo, float c, float hi, bool has_lo, float iv) {
-  const float gi = (hi - c) * iv;
-  const float gm = has_lo ? (c - lo) * iv : 0.f;
-  return (gm - gi) * iv;
-}
-
 __device__ __forceinline__ float comp(const float4 &q, int k) {
   return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(NTHR)
+// Position in the shared-memory ring: slot index and mbarrier phase parity, advanced
+// incrementally (no integer division in the plane loop).
+struct RingPos {
+  int slot;
+  uint32_t par;
+  __device__ __forceinline__ void inc(int ns) {
+    if (++slot == ns) {
+      slot = 0;
+      par ^= 1u;
+    }
+  }
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+  int q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB)
     lhs_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kMaxWarps];
@@ -126,244 +145,290 @@ __global__ void __launch_bounds__(NTHR)
   float *lrz = lrm + (size_t)a.nlr * TO * TZ;         // [2][TO][kLrzPitch] (thick along z)
 
   const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
-  const int z0 = blockIdx.x * TZ, o0 = blockIdx.y * TO, m0 = blockIdx.z * a.mc;
-  const int m1 = min(m0 + a.mc, a.nm);
-  const int o = o0 + row, z = z0 + 4 * lane;
-  const bool active = (o < a.no) && (z < a.nz);
   const StreamTerm &T = a.T;
-
-  const int u_begin = m0 - a.B;
-  const int first = u_begin - 1;
-  const int last = m1 - 1 + a.L;
+  const int ns = a.ns;
   const uint32_t plane_bytes = (uint32_t)(a.sz * (TO + 2) * sizeof(float));
+  const int own = (row + 1) * a.sz + a.hz + 4 * lane;  // this thread's quad inside a plane
 
   if (tid < UR_MAX_TAPS) s_ker[tid] = T.ker[tid];
   if (tid == 0) {
-    for (int s = 0; s < a.ns; ++s) mbar_init(&s_bar[s], 1);
+    for (int s = 0; s < ns; ++s) mbar_init(&s_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  auto issue = [&](int q) {
-    const int s = (q - first) % a.ns;
-    mbar_expect_tx(&s_bar[s], plane_bytes);
-    if (a.march_y)
-      tma_load_3d(ring + (size_t)s * a.plane_floats, &tmap, &s_bar[s], z0 - a.hz, q, o0 - 1);
-    else
-      tma_load_3d(ring + (size_t)s * a.plane_floats, &tmap, &s_bar[s], z0 - a.hz, o0 - 1, q);
-  };
-  auto wait_plane = [&](int q) {
-    const int k = q - first;
-    mbar_wait(&s_bar[k % a.ns], (uint32_t)((k / a.ns) & 1));
-  };
-  auto plane_ptr = [&](int q) -> const float * {
-    return ring + (size_t)((q - first) % a.ns) * a.plane_floats;
-  };
-  const int own = (row + 1) * a.sz + a.hz + 4 * lane;  // this thread's quad inside a plane
-  auto quad = [&](int q) -> float4 {
-    return *reinterpret_cast<const float4 *>(plane_ptr(q) + own);
+  auto wrap = [&](int s) { return s >= ns ? s - ns : s; };
+  auto quad_at = [&](int slot) -> float4 {
+    return *reinterpret_cast<const float4 *>(ring + (size_t)slot * a.plane_floats + own);
   };
 
-  if (tid == 0)
-    for (int q = first; q < first + a.ns && q <= last; ++q) issue(q);
+  // contiguous range of plane-tiles (column-major: column, then plane) of this CTA
+  const long long total = (long long)a.ncol * a.nm;
+  const long long t_begin = (long long)blockIdx.x * a.q;
+  const long long t_end = t_begin + a.q < total ? t_begin + a.q : total;
 
-  // ---- per-thread constants of the observation term ----
-  const bool o_in = T.kind != SK_NONE && o >= T.lo_o && o < T.hi_o;
-  float4 zmask = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (T.kind != SK_NONE) {
-    zmask.x = (z + 0 >= T.lo_z && z + 0 < T.hi_z) ? 1.f : 0.f;
-    zmask.y = (z + 1 >= T.lo_z && z + 1 < T.hi_z) ? 1.f : 0.f;
-    zmask.z = (z + 2 >= T.lo_z && z + 2 < T.hi_z) ? 1.f : 0.f;
-    zmask.w = (z + 3 >= T.lo_z && z + 3 < T.hi_z) ? 1.f : 0.f;
-  }
-  // scaling that alternates along a *thin* axis is a per-voxel factor
-  float4 thin = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (T.scl_kind == SC_O) {
-    const float f = ((o - T.scl_off) & 1) ? T.s_odd : T.s_even;
-    thin = make_float4(f, f, f, f);
-  } else if (T.scl_kind == SC_Z) {
-    const float f0 = ((z - T.scl_off) & 1) ? T.s_odd : T.s_even;
-    const float f1 = ((z - T.scl_off) & 1) ? T.s_even : T.s_odd;
-    thin = make_float4(f0, f1, f0, f1);
-  }
-  // thick along z: low-res rows touching this tile
-  int jz_lo = 0, njt = 0;
-  if (T.kind == SK_THICK_Z) {
-    const int a0 = z0 - T.off - T.K + 1;
-    jz_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
-    int jz_hi = (z0 + TZ - 1 - T.off) >= 0 ? (z0 + TZ - 1 - T.off) / T.r : -1;
-    if (jz_hi > T.nj - 1) jz_hi = T.nj - 1;
-    njt = jz_hi - jz_lo + 1;
-    if (njt < 0) njt = 0;
-  }
-  auto build_lrz = [&](int q) {  // low-res z-rows of plane q -> lrz[q & 1]
-    float *dst = lrz + (size_t)(q & 1) * TO * kLrzPitch;
-    const float *P = plane_ptr(q);
-    for (int idx = tid; idx < TO * njt; idx += NTHR) {
-      const int rr = idx / njt, jj = idx - rr * njt;
-      const int j = jz_lo + jj;
-      const float *src = P + (rr + 1) * a.sz + a.hz + (j * T.r + T.off - z0);
-      float acc = 0.f;
-      for (int t = 0; t < T.K; ++t) acc = fmaf(s_ker[t], src[t], acc);
-      if (T.scl_kind == SC_CONV) acc *= (j & 1) ? T.s_odd : T.s_even;
-      dst[rr * kLrzPitch + jj] = acc;
-    }
-  };
-
-  // ---- prime the pipeline ----
-  for (int q = first; q < u_begin + a.L; ++q) wait_plane(q);
-  float4 prev = quad(first), cur = quad(u_begin);
-  if (T.kind == SK_THICK_Z) {
-    // plane u_begin is resident (L >= 1 means planes up to u_begin + L - 1 >= u_begin)
-    build_lrz(u_begin);
-    __syncthreads();
-  }
-
+  RingPos ip{0, 0u};  // producer position (thread 0)
+  RingPos wp{0, 0u};  // consumer position (every thread)
   double part = 0.0;
-  for (int u = u_begin; u < m1; ++u) {
-    wait_plane(u + a.L);
-    const float4 next = quad(u + 1);
 
-    if (T.kind == SK_THICK_M && o_in && active) {
-      const int t0 = u - T.off;
-      if (t0 >= 0 && t0 % T.r == 0) {
-        const int j = t0 / T.r;
-        if (j < T.nj) {  // low-res row j starts at this plane: form it once, park it
+  for (long long t = t_begin; t < t_end;) {
+    const int col = (int)(t / a.nm);
+    const int m0 = (int)(t - (long long)col * a.nm);
+    const long long left_tiles = t_end - t;
+    const int m1 = (left_tiles < (long long)(a.nm - m0)) ? m0 + (int)left_tiles : a.nm;
+    t += m1 - m0;
+    const int cz = col % a.gx, co = col / a.gx;
+    const int z0 = cz * TZ, o0 = co * TO;
+    const int o = o0 + row, z = z0 + 4 * lane;
+    const bool active = (o < a.no) && (z < a.nz);
+
+    const int u_begin = m0 - a.B;
+    const int first = u_begin - 1;
+    const int last = m1 - 1 + a.L;
+
+    int iq = first;  // next plane to issue
+    auto issue_next = [&]() {
+      uint64_t *bar = &s_bar[ip.slot];
+      mbar_expect_tx(bar, plane_bytes);
+      float *dst = ring + (size_t)ip.slot * a.plane_floats;
+      if (a.march_y)
+        tma_load_3d(dst, &tmap, bar, z0 - a.hz, iq, o0 - 1);
+      else
+        tma_load_3d(dst, &tmap, bar, z0 - a.hz, o0 - 1, iq);
+      ip.inc(ns);
+      ++iq;
+    };
+    if (tid == 0)
+      for (int n = 0; n < ns && iq <= last; ++n) issue_next();
+
+    // ---- per-thread constants of the observation term ----
+    const bool o_in = T.kind != SK_NONE && o >= T.lo_o && o < T.hi_o;
+    float4 zmask = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (T.kind != SK_NONE) {
+      zmask.x = (z + 0 >= T.lo_z && z + 0 < T.hi_z) ? 1.f : 0.f;
+      zmask.y = (z + 1 >= T.lo_z && z + 1 < T.hi_z) ? 1.f : 0.f;
+      zmask.z = (z + 2 >= T.lo_z && z + 2 < T.hi_z) ? 1.f : 0.f;
+      zmask.w = (z + 3 >= T.lo_z && z + 3 < T.hi_z) ? 1.f : 0.f;
+    }
+    // scaling that alternates along a *thin* axis is a per-voxel factor
+    float4 thin = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (T.scl_kind == SC_O) {
+      const float f = ((o - T.scl_off) & 1) ? T.s_odd : T.s_even;
+      thin = make_float4(f, f, f, f);
+    } else if (T.scl_kind == SC_Z) {
+      const float f0 = ((z - T.scl_off) & 1) ? T.s_odd : T.s_even;
+      const float f1 = ((z - T.scl_off) & 1) ? T.s_even : T.s_odd;
+      thin = make_float4(f0, f1, f0, f1);
+    }
+    // thick along z: low-res rows touching this tile and, per component of this thread's
+    // quad, the local index of its highest row and the tap that row contributes
+    int jz_lo = 0, njt = 0;
+    int zj0[4] = {0, 0, 0, 0}, zt0[4] = {UR_MAX_TAPS, UR_MAX_TAPS, UR_MAX_TAPS, UR_MAX_TAPS};
+    if (T.kind == SK_THICK_Z) {
+      const int a0 = z0 - T.off - T.K + 1;
+      jz_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+      int jz_hi = (z0 + TZ - 1 - T.off) >= 0 ? (z0 + TZ - 1 - T.off) / T.r : -1;
+      if (jz_hi > T.nj - 1) jz_hi = T.nj - 1;
+      njt = jz_hi - jz_lo + 1;
+      if (njt < 0) njt = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int up = z + k - T.off;
+        if (up >= 0) {
+          int j_hi = up / T.r;
+          if (j_hi > T.nj - 1) j_hi = T.nj - 1;
+          zj0[k] = j_hi - jz_lo;
+          zt0[k] = up - j_hi * T.r;
+        }
+      }
+    }
+    auto build_lrz = [&](int slot, int buf) {  // low-res z-rows of one plane, one warp per row
+      float *dst = lrz + ((size_t)buf * TO + row) * kLrzPitch;
+      const float *src0 = ring + (size_t)slot * a.plane_floats + (row + 1) * a.sz + a.hz +
+                          (jz_lo * T.r + T.off - z0);
+      for (int jj = lane; jj < njt; jj += 32) {
+        const float *src = src0 + jj * T.r;
+        float acc = 0.f;
+        for (int tt = 0; tt < T.K; ++tt) acc = fmaf(s_ker[tt], src[tt], acc);
+        if (T.scl_kind == SC_CONV) acc *= ((jz_lo + jj) & 1) ? T.s_odd : T.s_even;
+        dst[jj] = acc;
+      }
+    };
+
+    // ---- prime the pipeline: planes first .. u_begin + L - 1 ----
+    const int s_first = wp.slot;
+    for (int n = 0; n < a.L + 1; ++n) {
+      mbar_wait(&s_bar[wp.slot], wp.par);
+      wp.inc(ns);
+    }
+    float4 prev = quad_at(s_first);
+    int su = wrap(s_first + 1);
+    float4 cur = quad_at(su);
+
+    int ph = 0, jrow = 0, jslot = 0;  // thick along m: phase / current row / its parking slot
+    if (T.kind == SK_THICK_M) {
+      const int t0 = u_begin - T.off;
+      jrow = floordiv(t0, T.r);
+      ph = t0 - jrow * T.r;
+      jslot = jrow - floordiv(jrow, a.nlr) * a.nlr;
+    }
+    if (T.kind == SK_THICK_Z) {
+      build_lrz(su, u_begin & 1);
+      __syncthreads();
+    }
+
+    for (int u = u_begin; u < m1; ++u) {
+      mbar_wait(&s_bar[wp.slot], wp.par);  // plane u + L has landed
+      wp.inc(ns);
+      const int sn = wrap(su + 1);
+      const float4 next = quad_at(sn);
+
+      if (T.kind == SK_THICK_M) {
+        if (ph == 0 && jrow >= 0 && jrow < T.nj && o_in && active) {
+          // low-res row jrow starts at this plane: form it once and park it
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int t = 0; t < T.K; ++t) {
-            const float4 q = t == 0 ? cur : (t == 1 ? next : quad(u + t));
-            const float k = s_ker[t];
+          int s = su;
+          for (int tt = 0; tt < T.K; ++tt) {
+            const float4 q = tt == 0 ? cur : (tt == 1 ? next : quad_at(s));
+            const float k = s_ker[tt];
             acc.x = fmaf(k, q.x, acc.x);
             acc.y = fmaf(k, q.y, acc.y);
             acc.z = fmaf(k, q.z, acc.z);
             acc.w = fmaf(k, q.w, acc.w);
+            s = wrap(s + 1);
           }
-          float s = 1.f;
-          if (T.scl_kind == SC_CONV) s = (j & 1) ? T.s_odd : T.s_even;
-          acc.x *= s * zmask.x;
-          acc.y *= s * zmask.y;
-          acc.z *= s * zmask.z;
-          acc.w *= s * zmask.w;
-          *reinterpret_cast<float4 *>(lrm + ((size_t)(j % a.nlr) * TO + row) * TZ + 4 * lane) = acc;
-        }
-      }
-    }
-    if (T.kind == SK_THICK_Z && u + 1 < m1) build_lrz(u + 1);
-
-    if (u >= m0 && active) {
-      const float *rowp = plane_ptr(u) + own;
-      const float4 om = *reinterpret_cast<const float4 *>(rowp - a.sz);
-      const float4 op = *reinterpret_cast<const float4 *>(rowp + a.sz);
-      const float zl = rowp[-1], zr = rowp[4];
-      const size_t gi = (size_t)u * a.gs_m + (size_t)o * a.gs_o + z;
-      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
-      if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
-      if (MODE == LHS_ENERGY && a.update_p) {
-        rq = *reinterpret_cast<const float4 *>(a.r + gi);
-        pq = *reinterpret_cast<const float4 *>(a.p + gi);
-      }
-      // observation term
-      float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
-      float mfac = T.tau;
-      if (T.scl_kind == SC_M) mfac *= ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
-      if (T.kind == SK_CROP) {
-        if (o_in && u >= T.lo_m && u < T.hi_m) {
-          dat.x = cur.x * zmask.x;
-          dat.y = cur.y * zmask.y;
-          dat.z = cur.z * zmask.z;
-          dat.w = cur.w * zmask.w;
-        }
-      } else if (T.kind == SK_THICK_M) {
-        const int up = u - T.off;
-        if (o_in && up >= 0) {
-          int j_hi = up / T.r;
-          if (j_hi > T.nj - 1) j_hi = T.nj - 1;
-          const int a0 = up - T.K + 1;
-          const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
-          for (int j = j_lo; j <= j_hi; ++j) {
-            const float4 lr = *reinterpret_cast<const float4 *>(
-                lrm + ((size_t)(j % a.nlr) * TO + row) * TZ + 4 * lane);
-            const float k = s_ker[up - j * T.r];
-            dat.x = fmaf(k, lr.x, dat.x);
-            dat.y = fmaf(k, lr.y, dat.y);
-            dat.z = fmaf(k, lr.z, dat.z);
-            dat.w = fmaf(k, lr.w, dat.w);
-          }
+          float sc = 1.f;
+          if (T.scl_kind == SC_CONV) sc = (jrow & 1) ? T.s_odd : T.s_even;
+          acc.x *= sc * zmask.x;
+          acc.y *= sc * zmask.y;
+          acc.z *= sc * zmask.z;
+          acc.w *= sc * zmask.w;
+          *reinterpret_cast<float4 *>(lrm + ((size_t)jslot * TO + row) * TZ + 4 * lane) = acc;
         }
       } else if (T.kind == SK_THICK_Z) {
-        if (o_in && u >= T.lo_m && u < T.hi_m) {
-          const float *lr = lrz + ((size_t)(u & 1) * TO + row) * kLrzPitch;
-          float d[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int up = z + k - T.off;
-            float acc = 0.f;
-            if (up >= 0) {
-              int j_hi = up / T.r;
-              if (j_hi > T.nj - 1) j_hi = T.nj - 1;
-              const int a0 = up - T.K + 1;
-              const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
-              for (int j = j_lo; j <= j_hi; ++j)
-                acc = fmaf(s_ker[up - j * T.r], lr[j - jz_lo], acc);
-            }
-            d[k] = acc;
+        if (u + 1 < m1) build_lrz(sn, (u + 1) & 1);
+      }
+
+      if (u >= m0 && active) {
+        const float *rowp = ring + (size_t)su * a.plane_floats + own;
+        float4 om = *reinterpret_cast<const float4 *>(rowp - a.sz);
+        const float4 op = *reinterpret_cast<const float4 *>(rowp + a.sz);
+        float zl = rowp[-1];
+        const float zr = rowp[4];
+        const size_t gi = (size_t)u * a.gs_m + (size_t)o * a.gs_o + z;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
+        if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
+        if (MODE == LHS_ENERGY && a.update_p) {
+          rq = *reinterpret_cast<const float4 *>(a.r + gi);
+          pq = *reinterpret_cast<const float4 *>(a.p + gi);
+        }
+        // ---- observation term through the decimated grid ----
+        float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
+        float mfac = T.tau;
+        if (T.scl_kind == SC_M) mfac *= ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
+        if (T.kind == SK_CROP) {
+          if (o_in && u >= T.lo_m && u < T.hi_m) {
+            dat.x = cur.x * zmask.x;
+            dat.y = cur.y * zmask.y;
+            dat.z = cur.z * zmask.z;
+            dat.w = cur.w * zmask.w;
           }
-          dat = make_float4(d[0], d[1], d[2], d[3]);
+        } else if (T.kind == SK_THICK_M) {
+          if (o_in) {
+            int jr = jrow, js = jslot;
+            for (int tap = ph; tap < T.K; tap += T.r) {
+              if (jr >= 0 && jr < T.nj) {
+                const float4 lr = *reinterpret_cast<const float4 *>(
+                    lrm + ((size_t)js * TO + row) * TZ + 4 * lane);
+                const float k = s_ker[tap];
+                dat.x = fmaf(k, lr.x, dat.x);
+                dat.y = fmaf(k, lr.y, dat.y);
+                dat.z = fmaf(k, lr.z, dat.z);
+                dat.w = fmaf(k, lr.w, dat.w);
+              }
+              --jr;
+              js = js == 0 ? a.nlr - 1 : js - 1;
+            }
+          }
+        } else if (T.kind == SK_THICK_Z) {
+          if (o_in && u >= T.lo_m && u < T.hi_m) {
+            const float *lr = lrz + ((size_t)(u & 1) * TO + row) * kLrzPitch;
+            float d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float acc = 0.f;
+              int jl = zj0[k];
+              for (int tap = zt0[k]; tap < T.K && jl >= 0; tap += T.r, --jl)
+                acc = fmaf(s_ker[tap], lr[jl], acc);
+              d[k] = acc;
+            }
+            dat = make_float4(d[0], d[1], d[2], d[3]);
+          }
+        }
+        // ---- D'D: per axis (2c - lo - hi) / vx^2 with the "lo" term dropped on the low
+        //      edge; values past the high edge are the TMA's zero fill (bound = zero) ----
+        const float4 pv = u > 0 ? prev : cur;
+        if (o == 0) om = cur;
+        if (z == 0) zl = cur.x;
+        float val[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float c = comp(cur, k);
+          const float lft = k == 0 ? zl : comp(cur, k - 1);
+          const float rgt = k == 3 ? zr : comp(cur, k + 1);
+          const float d_m = (c - comp(pv, k)) + (c - comp(next, k));
+          const float d_o = (c - comp(om, k)) + (c - comp(op, k));
+          const float d_z = (c - lft) + (c - rgt);
+          const float dtd = fmaf(d_z, a.iv_z, fmaf(d_o, a.iv_o, d_m * a.iv_m));
+          const float data = fmaf(mfac * comp(thin, k), comp(dat, k), a.w_ident * c);
+          val[k] = fmaf(a.rl2, dtd, data);
+        }
+        if (MODE == LHS_PLAIN) {
+          *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur, k), val[k]);
+        } else if (MODE == LHS_RESID) {
+          float4 rr;
+          rr.x = __fsub_rn(bq.x, val[0]);
+          rr.y = __fsub_rn(bq.y, val[1]);
+          rr.z = __fsub_rn(bq.z, val[2]);
+          rr.w = __fsub_rn(bq.w, val[3]);
+          *reinterpret_cast<float4 *>(a.r + gi) = rr;
+          *reinterpret_cast<float4 *>(a.p + gi) = rr;
+          part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
+                  (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur, k));
+          if (a.update_p) {
+            const float beta = (float)a.fin.st->beta;
+            float4 pn;
+            pn.x = __fadd_rn(__fmul_rn(beta, pq.x), rq.x);
+            pn.y = __fadd_rn(__fmul_rn(beta, pq.y), rq.y);
+            pn.z = __fadd_rn(__fmul_rn(beta, pq.z), rq.z);
+            pn.w = __fadd_rn(__fmul_rn(beta, pq.w), rq.w);
+            *reinterpret_cast<float4 *>(a.p + gi) = pn;
+          }
         }
       }
-      const bool mlo = u > 0, olo = o > 0;
-      float val[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float c = comp(cur, k);
-        const float left = k == 0 ? zl : comp(cur, k - 1);
-        const float right = k == 3 ? zr : comp(cur, k + 1);
-        const float tm = dtd1(comp(prev, k), c, comp(next, k), mlo, a.iv_m);
-        const float to = dtd1(comp(om, k), c, comp(op, k), olo, a.iv_o);
-        const float tz = dtd1(left, c, right, (z + k) > 0, a.iv_z);
-        const float dtd = (tm + to) + tz;
-        const float data = a.w_ident * c + mfac * (comp(thin, k) * comp(dat, k));
-        val[k] = data + a.rl2 * dtd;
-      }
-      if (MODE == LHS_PLAIN) {
-        *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur, k), val[k]);
-      } else if (MODE == LHS_RESID) {
-        float4 rr;
-        rr.x = __fsub_rn(bq.x, val[0]);
-        rr.y = __fsub_rn(bq.y, val[1]);
-        rr.z = __fsub_rn(bq.z, val[2]);
-        rr.w = __fsub_rn(bq.w, val[3]);
-        *reinterpret_cast<float4 *>(a.r + gi) = rr;
-        *reinterpret_cast<float4 *>(a.p + gi) = rr;
-        part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
-                (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur, k));
-        if (a.update_p) {
-          const float beta = (float)a.fin.st->beta;
-          float4 pn;
-          pn.x = __fadd_rn(__fmul_rn(beta, pq.x), rq.x);
-          pn.y = __fadd_rn(__fmul_rn(beta, pq.y), rq.y);
-          pn.z = __fadd_rn(__fmul_rn(beta, pq.z), rq.z);
-          pn.w = __fadd_rn(__fmul_rn(beta, pq.w), rq.w);
-          *reinterpret_cast<float4 *>(a.p + gi) = pn;
+      // ---- advance ----
+      prev = cur;
+      cur = next;
+      su = sn;
+      if (T.kind == SK_THICK_M) {
+        if (++ph == T.r) {
+          ph = 0;
+          ++jrow;
+          if (++jslot == a.nlr) jslot = 0;
         }
       }
-    }
-    prev = cur;
-    cur = next;
-    __syncthreads();  // everyone is done with plane u-1 (and lrz of plane u is complete)
-    if (tid == 0) {
-      const int q = u - 1 + a.ns;
-      if (q <= last) issue(q);
+      __syncthreads();  // every warp is done with plane u - 1; lrz of plane u + 1 is complete
+      if (tid == 0 && iq <= last) issue_next();
     }
   }
-  double total;
-  if (grid_sum(part, a.gr, s_red, &total) && tid == 0) finalize(a.fin, total);
+  double total_sum;
+  if (grid_sum(part, a.gr, s_red, &total_sum) && tid == 0) finalize(a.fin, total_sum);
 }
 
 // ------------------------------------------------------------------ host side
@@ -437,7 +502,9 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
-int stream_mc_override = 0;  // test / tuning hook (planes per chunk), 0 = automatic
+int stream_mc_override = 0;  // test / tuning hook (plane-tiles per CTA), 0 = automatic
+int stream_min_blocks = 3;   // register budget variant: 3 (<= 80 regs) or 2 CTAs per SM
+typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
   (void)variant;
@@ -502,9 +569,9 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   S.nz = A.nz;
   S.gs_m = march ? (long long)A.nz : (long long)A.ny * A.nz;
   S.gs_o = march ? (long long)A.ny * A.nz : (long long)A.nz;
-  S.iv_m = march ? A.ivy : A.ivx;
-  S.iv_o = march ? A.ivx : A.ivy;
-  S.iv_z = A.ivz;
+  S.iv_m = march ? A.ivy * A.ivy : A.ivx * A.ivx;  // 1 / vx^2 per axis
+  S.iv_o = march ? A.ivx * A.ivx : A.ivy * A.ivy;
+  S.iv_z = A.ivz * A.ivz;
   S.rl2 = A.rl2;
   S.w_ident = A.w_ident;
   S.L = 1;
@@ -527,16 +594,39 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
                       128;  // slack for the 128-byte alignment of the ring
   if (smem > 200 * 1024) return UR_ERR_UNSUPPORTED;
 
+  static StreamKernel table[3][2] = {
+      {lhs_stream_kernel<LHS_PLAIN, 2>, lhs_stream_kernel<LHS_PLAIN, 3>},
+      {lhs_stream_kernel<LHS_RESID, 2>, lhs_stream_kernel<LHS_RESID, 3>},
+      {lhs_stream_kernel<LHS_ENERGY, 2>, lhs_stream_kernel<LHS_ENERGY, 3>}};
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j)
+        UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)table[i][j],
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+    attr_set = true;
+  }
+  const int mi = mode == LHS_PLAIN ? 0 : (mode == LHS_RESID ? 1 : 2);
+  StreamKernel kernel = table[mi][stream_min_blocks == 2 ? 0 : 1];
+  // One wave of equally loaded CTAs: the (column, plane) tiles are cut into contiguous
+  // ranges, one per resident CTA slot (occupancy x SM count).
   const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, TO);
-  int chunks = (int)((3u * (unsigned)sm_count() + gx * gy / 2) / (gx * gy));
-  if (chunks < 1) chunks = 1;
-  int mc = (S.nm + chunks - 1) / chunks;
-  const int mc_min = 4 * (S.B + S.L + 1);  // keep the warm-up planes a small fraction
-  if (mc < mc_min) mc = mc_min;
-  if (stream_mc_override > 0) mc = stream_mc_override;
-  if (mc > S.nm) mc = S.nm;
-  S.mc = mc;
-  const unsigned gz = div_up(S.nm, mc);
+  S.gx = (int)gx;
+  S.ncol = (int)(gx * gy);
+  const long long total = (long long)S.ncol * S.nm;
+  int resident = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, (const void *)kernel,
+                                                                 NTHR, smem);
+  if (oe != cudaSuccess || resident < 1) resident = 1;
+  const long long slots = (long long)resident * sm_count();
+  const long long q_min = 4 * (S.B + S.L + 1);  // keep the warm-up planes a small fraction
+  long long q = (total + slots - 1) / slots;
+  if (q < q_min) q = q_min;
+  if (stream_mc_override > 0) q = stream_mc_override;
+  if (q > total) q = total;
+  S.q = (int)q;
+  const unsigned n_cta = (unsigned)((total + q - 1) / q);
 
   CUtensorMap map;
   if (!get_tensor_map(A.v, A.nx, A.ny, A.nz, S.sz, march, &map)) return UR_ERR_UNSUPPORTED;
@@ -551,28 +641,7 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   S.gr = A.gr;
   S.fin = A.fin;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_PLAIN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_RESID>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    UR_CUDA_CHECK(cudaFuncSetAttribute(lhs_stream_kernel<LHS_ENERGY>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  dim3 grid(gx, gy, gz), block(NTHR);
-  switch (mode) {
-    case LHS_PLAIN:
-      lhs_stream_kernel<LHS_PLAIN><<<grid, block, smem, st>>>(map, S);
-      break;
-    case LHS_RESID:
-      lhs_stream_kernel<LHS_RESID><<<grid, block, smem, st>>>(map, S);
-      break;
-    default:
-      lhs_stream_kernel<LHS_ENERGY><<<grid, block, smem, st>>>(map, S);
-      break;
-  }
+  kernel<<<dim3(n_cta), dim3(NTHR), smem, st>>>(map, S);
   UR_LAUNCH_CHECK();
   return UR_OK;
 }
