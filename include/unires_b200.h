@@ -58,7 +58,7 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count);
 /* Tuning / test knobs (process-wide).  "lhs_variant": 0 automatic, 1 force the
  * direct (non-TMA) lhs kernel; "stream_mc": planes per CTA chunk of the TMA
  * streaming kernel (0 automatic); "stream_minb": its register-budget variant
- * (2 or 3 resident CTAs per SM).  Returns UR_ERR_ARG for unknown names.    */
+ * (3 or 4 resident CTAs per SM).  Returns UR_ERR_ARG for unknown names.    */
 int ur_tune(const char *name, int value);
 
 /* ---------------------------------------------------------------- finite

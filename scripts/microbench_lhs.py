@@ -42,7 +42,7 @@ def main():
     for c in range(len(sc.x)):
         op = _project.LhsOperator(sc.x[c], sc.y[c], method=sc.sett.method, do=sc.sett.do_proj,
                                   rho=sc.rho, vx_y=vx)
-        for variant, minb in ((0, 3), (0, 2)):
+        for variant, minb in ((0, 3), (0, 4)):
             for mc in mcs:
                 tune('lhs_variant', variant)
                 tune('stream_mc', mc)
@@ -56,7 +56,7 @@ def main():
     # denoise lhs (no projection)
     op = _project.LhsOperator([struct._input(tau=0.01)], struct._output(dim=dim, lam=0.1), do=False,
                               rho=1.0, vx_y=vx)
-    for minb in (3, 2):
+    for minb in (3, 4):
         for mc in mcs:
             tune('stream_mc', mc)
             tune('stream_minb', minb)

@@ -111,18 +111,54 @@ __device__ __forceinline__ float comp(const float4 &q, int k) {
   return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
 }
 
-// Position in the shared-memory ring: slot index and mbarrier phase parity, advanced
-// incrementally (no integer division in the plane loop).
-struct RingPos {
-  int slot;
-  uint32_t par;
-  __device__ __forceinline__ void inc(int ns) {
-    if (++slot == ns) {
-      slot = 0;
-      par ^= 1u;
-    }
-  }
-};
+// Shared memory is addressed through 32-bit shared-window addresses and explicit
+// ld.shared / st.shared: the ring base is computed at run time (128-byte aligned), which
+// would otherwise demote every access to a generic load.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                              int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
@@ -130,7 +166,27 @@ __device__ __forceinline__ int floordiv(int a, int b) {
   return q;
 }
 
-template <int MODE, int MINB>
+// Ring geometry in shared-window addresses.
+struct Ring {
+  uint32_t base, end, plane_b;  // planes
+  uint32_t bar, bar_end;        // mbarriers (8 bytes each)
+};
+
+// One position of the ring: plane address, its mbarrier and the phase parity to wait for.
+struct RingPos {
+  uint32_t pa, ba, par;
+  __device__ __forceinline__ void inc(const Ring &R) {
+    pa += R.plane_b;
+    ba += 8u;
+    if (pa == R.end) {
+      pa = R.base;
+      ba = R.bar;
+      par ^= 1u;
+    }
+  }
+};
+
+template <int MODE, int KIND, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB)
     lhs_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -139,16 +195,25 @@ __global__ void __launch_bounds__(NTHR, MINB)
   __shared__ float s_ker[UR_MAX_TAPS];
   if (a.done && *a.done) return;
 
-  float *ring = reinterpret_cast<float *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
-  float *lrm = ring + (size_t)a.ns * a.plane_floats;  // [nlr][TO][TZ]  (thick along m)
-  float *lrz = lrm + (size_t)a.nlr * TO * TZ;         // [2][TO][kLrzPitch] (thick along z)
-
   const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
   const StreamTerm &T = a.T;
   const int ns = a.ns;
+
+  Ring R;
+  R.base = (smem_u32(smem_raw) + 127u) & ~127u;
+  R.plane_b = (uint32_t)a.plane_floats * 4u;
+  R.end = R.base + (uint32_t)ns * R.plane_b;
+  R.bar = smem_u32(s_bar);
+  R.bar_end = R.bar + 8u * (uint32_t)ns;
+  const uint32_t lrm_a = R.end;  // [nlr][TO][TZ] floats (thick along m)
+  const uint32_t lrm_stride = TO * TZ * 4u;
+  const uint32_t lrm_end = lrm_a + (uint32_t)a.nlr * lrm_stride;
+  const uint32_t lrz_a = lrm_end;  // [2][TO][kLrzPitch] floats (thick along z)
+
   const uint32_t plane_bytes = (uint32_t)(a.sz * (TO + 2) * sizeof(float));
-  const int own = (row + 1) * a.sz + a.hz + 4 * lane;  // this thread's quad inside a plane
+  const uint32_t sz_b = (uint32_t)a.sz * 4u;
+  const uint32_t own_b = (uint32_t)((row + 1) * a.sz + a.hz + 4 * lane) * 4u;  // own quad
+  const uint32_t lr_own = (uint32_t)(row * TZ + 4 * lane) * 4u;
 
   if (tid < UR_MAX_TAPS) s_ker[tid] = T.ker[tid];
   if (tid == 0) {
@@ -157,18 +222,13 @@ __global__ void __launch_bounds__(NTHR, MINB)
   }
   __syncthreads();
 
-  auto wrap = [&](int s) { return s >= ns ? s - ns : s; };
-  auto quad_at = [&](int slot) -> float4 {
-    return *reinterpret_cast<const float4 *>(ring + (size_t)slot * a.plane_floats + own);
-  };
-
   // contiguous range of plane-tiles (column-major: column, then plane) of this CTA
   const long long total = (long long)a.ncol * a.nm;
   const long long t_begin = (long long)blockIdx.x * a.q;
   const long long t_end = t_begin + a.q < total ? t_begin + a.q : total;
 
-  RingPos ip{0, 0u};  // producer position (thread 0)
-  RingPos wp{0, 0u};  // consumer position (every thread)
+  RingPos ip{R.base, R.bar, 0u};  // producer position (thread 0)
+  RingPos wp{R.base, R.bar, 0u};  // consumer position (every thread)
   double part = 0.0;
 
   for (long long t = t_begin; t < t_end;) {
@@ -188,43 +248,44 @@ __global__ void __launch_bounds__(NTHR, MINB)
 
     int iq = first;  // next plane to issue
     auto issue_next = [&]() {
-      uint64_t *bar = &s_bar[ip.slot];
-      mbar_expect_tx(bar, plane_bytes);
-      float *dst = ring + (size_t)ip.slot * a.plane_floats;
+      mbar_expect_tx_a(ip.ba, plane_bytes);
       if (a.march_y)
-        tma_load_3d(dst, &tmap, bar, z0 - a.hz, iq, o0 - 1);
+        tma_load_3d_a(ip.pa, &tmap, ip.ba, z0 - a.hz, iq, o0 - 1);
       else
-        tma_load_3d(dst, &tmap, bar, z0 - a.hz, o0 - 1, iq);
-      ip.inc(ns);
+        tma_load_3d_a(ip.pa, &tmap, ip.ba, z0 - a.hz, o0 - 1, iq);
+      ip.inc(R);
       ++iq;
     };
     if (tid == 0)
       for (int n = 0; n < ns && iq <= last; ++n) issue_next();
 
     // ---- per-thread constants of the observation term ----
-    const bool o_in = T.kind != SK_NONE && o >= T.lo_o && o < T.hi_o;
+    const bool o_in = KIND != SK_NONE && o >= T.lo_o && o < T.hi_o;
     float4 zmask = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (T.kind != SK_NONE) {
+    if (KIND == SK_CROP || KIND == SK_THICK_M) {
       zmask.x = (z + 0 >= T.lo_z && z + 0 < T.hi_z) ? 1.f : 0.f;
       zmask.y = (z + 1 >= T.lo_z && z + 1 < T.hi_z) ? 1.f : 0.f;
       zmask.z = (z + 2 >= T.lo_z && z + 2 < T.hi_z) ? 1.f : 0.f;
       zmask.w = (z + 3 >= T.lo_z && z + 3 < T.hi_z) ? 1.f : 0.f;
     }
-    // scaling that alternates along a *thin* axis is a per-voxel factor
-    float4 thin = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (T.scl_kind == SC_O) {
-      const float f = ((o - T.scl_off) & 1) ? T.s_odd : T.s_even;
-      thin = make_float4(f, f, f, f);
-    } else if (T.scl_kind == SC_Z) {
-      const float f0 = ((z - T.scl_off) & 1) ? T.s_odd : T.s_even;
-      const float f1 = ((z - T.scl_off) & 1) ? T.s_even : T.s_odd;
-      thin = make_float4(f0, f1, f0, f1);
+    // scaling that alternates along a *thin* axis is a per-voxel factor (tau folded in)
+    float4 thin = make_float4(T.tau, T.tau, T.tau, T.tau);
+    if (KIND != SK_NONE) {
+      if (T.scl_kind == SC_O) {
+        const float f = T.tau * (((o - T.scl_off) & 1) ? T.s_odd : T.s_even);
+        thin = make_float4(f, f, f, f);
+      } else if (T.scl_kind == SC_Z) {
+        const float f0 = T.tau * (((z - T.scl_off) & 1) ? T.s_odd : T.s_even);
+        const float f1 = T.tau * (((z - T.scl_off) & 1) ? T.s_even : T.s_odd);
+        thin = make_float4(f0, f1, f0, f1);
+      }
     }
     // thick along z: low-res rows touching this tile and, per component of this thread's
     // quad, the local index of its highest row and the tap that row contributes
     int jz_lo = 0, njt = 0;
     int zj0[4] = {0, 0, 0, 0}, zt0[4] = {UR_MAX_TAPS, UR_MAX_TAPS, UR_MAX_TAPS, UR_MAX_TAPS};
-    if (T.kind == SK_THICK_Z) {
+    uint32_t lrz_src_off = 0;
+    if (KIND == SK_THICK_Z) {
       const int a0 = z0 - T.off - T.K + 1;
       jz_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
       int jz_hi = (z0 + TZ - 1 - T.off) >= 0 ? (z0 + TZ - 1 - T.off) / T.r : -1;
@@ -241,61 +302,70 @@ __global__ void __launch_bounds__(NTHR, MINB)
           zt0[k] = up - j_hi * T.r;
         }
       }
+      lrz_src_off = (uint32_t)((row + 1) * a.sz + a.hz + (jz_lo * T.r + T.off - z0)) * 4u;
     }
-    auto build_lrz = [&](int slot, int buf) {  // low-res z-rows of one plane, one warp per row
-      float *dst = lrz + ((size_t)buf * TO + row) * kLrzPitch;
-      const float *src0 = ring + (size_t)slot * a.plane_floats + (row + 1) * a.sz + a.hz +
-                          (jz_lo * T.r + T.off - z0);
+    auto build_lrz = [&](uint32_t plane_a, int buf) {  // low-res z-rows, one warp per row
+      const uint32_t dst = lrz_a + (uint32_t)((buf * TO + row) * kLrzPitch) * 4u;
       for (int jj = lane; jj < njt; jj += 32) {
-        const float *src = src0 + jj * T.r;
+        const uint32_t src = plane_a + lrz_src_off + (uint32_t)(jj * T.r) * 4u;
         float acc = 0.f;
-        for (int tt = 0; tt < T.K; ++tt) acc = fmaf(s_ker[tt], src[tt], acc);
+        for (int tt = 0; tt < T.K; ++tt) acc = fmaf(s_ker[tt], lds32(src + 4u * tt), acc);
         if (T.scl_kind == SC_CONV) acc *= ((jz_lo + jj) & 1) ? T.s_odd : T.s_even;
-        dst[jj] = acc;
+        sts32(dst + 4u * jj, acc);
       }
     };
 
     // ---- prime the pipeline: planes first .. u_begin + L - 1 ----
-    const int s_first = wp.slot;
+    const uint32_t a_first = wp.pa;
     for (int n = 0; n < a.L + 1; ++n) {
-      mbar_wait(&s_bar[wp.slot], wp.par);
-      wp.inc(ns);
+      mbar_wait_a(wp.ba, wp.par);
+      wp.inc(R);
     }
-    float4 prev = quad_at(s_first);
-    int su = wrap(s_first + 1);
-    float4 cur = quad_at(su);
+    float4 prev = lds128(a_first + own_b);
+    uint32_t au = a_first + R.plane_b;  // plane u
+    if (au == R.end) au = R.base;
+    float4 cur = lds128(au + own_b);
 
-    int ph = 0, jrow = 0, jslot = 0;  // thick along m: phase / current row / its parking slot
-    if (T.kind == SK_THICK_M) {
+    int ph = 0, jrow = 0;  // thick along m: phase inside the stride / current low-res row
+    uint32_t jaddr = lrm_a;  // parking slot of row jrow
+    if (KIND == SK_THICK_M) {
       const int t0 = u_begin - T.off;
       jrow = floordiv(t0, T.r);
       ph = t0 - jrow * T.r;
-      jslot = jrow - floordiv(jrow, a.nlr) * a.nlr;
+      jaddr = lrm_a + (uint32_t)(jrow - floordiv(jrow, a.nlr) * a.nlr) * lrm_stride;
     }
-    if (T.kind == SK_THICK_Z) {
-      build_lrz(su, u_begin & 1);
+    if (KIND == SK_THICK_Z) {
+      build_lrz(au, u_begin & 1);
       __syncthreads();
     }
+    const bool o_is0 = o == 0, z_is0 = z == 0;
 
     for (int u = u_begin; u < m1; ++u) {
-      mbar_wait(&s_bar[wp.slot], wp.par);  // plane u + L has landed
-      wp.inc(ns);
-      const int sn = wrap(su + 1);
-      const float4 next = quad_at(sn);
+      mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
+      wp.inc(R);
+      uint32_t an = au + R.plane_b;  // plane u + 1
+      if (an == R.end) an = R.base;
+      const float4 next = lds128(an + own_b);
+      // z neighbours of the quad come from the adjacent lanes; only the tile edges read smem
+      float zl = __shfl_up_sync(0xffffffffu, cur.w, 1);
+      float zr = __shfl_down_sync(0xffffffffu, cur.x, 1);
+      if (lane == 0) zl = lds32(au + own_b - 4u);
+      if (lane == 31) zr = lds32(au + own_b + 16u);
 
-      if (T.kind == SK_THICK_M) {
+      if (KIND == SK_THICK_M) {
         if (ph == 0 && jrow >= 0 && jrow < T.nj && o_in && active) {
           // low-res row jrow starts at this plane: form it once and park it
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          int s = su;
+          uint32_t s = au;
           for (int tt = 0; tt < T.K; ++tt) {
-            const float4 q = tt == 0 ? cur : (tt == 1 ? next : quad_at(s));
+            const float4 q = tt == 0 ? cur : (tt == 1 ? next : lds128(s + own_b));
             const float k = s_ker[tt];
             acc.x = fmaf(k, q.x, acc.x);
             acc.y = fmaf(k, q.y, acc.y);
             acc.z = fmaf(k, q.z, acc.z);
             acc.w = fmaf(k, q.w, acc.w);
-            s = wrap(s + 1);
+            s += R.plane_b;
+            if (s == R.end) s = R.base;
           }
           float sc = 1.f;
           if (T.scl_kind == SC_CONV) sc = (jrow & 1) ? T.s_odd : T.s_even;
@@ -303,18 +373,15 @@ __global__ void __launch_bounds__(NTHR, MINB)
           acc.y *= sc * zmask.y;
           acc.z *= sc * zmask.z;
           acc.w *= sc * zmask.w;
-          *reinterpret_cast<float4 *>(lrm + ((size_t)jslot * TO + row) * TZ + 4 * lane) = acc;
+          sts128(jaddr + lr_own, acc);
         }
-      } else if (T.kind == SK_THICK_Z) {
-        if (u + 1 < m1) build_lrz(sn, (u + 1) & 1);
+      } else if (KIND == SK_THICK_Z) {
+        if (u + 1 < m1) build_lrz(an, (u + 1) & 1);
       }
 
       if (u >= m0 && active) {
-        const float *rowp = ring + (size_t)su * a.plane_floats + own;
-        float4 om = *reinterpret_cast<const float4 *>(rowp - a.sz);
-        const float4 op = *reinterpret_cast<const float4 *>(rowp + a.sz);
-        float zl = rowp[-1];
-        const float zr = rowp[4];
+        float4 om = lds128(au + own_b - sz_b);
+        const float4 op = lds128(au + own_b + sz_b);
         const size_t gi = (size_t)u * a.gs_m + (size_t)o * a.gs_o + z;
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
         if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
@@ -324,22 +391,23 @@ __global__ void __launch_bounds__(NTHR, MINB)
         }
         // ---- observation term through the decimated grid ----
         float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
-        float mfac = T.tau;
-        if (T.scl_kind == SC_M) mfac *= ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
-        if (T.kind == SK_CROP) {
+        float mfac = 1.f;
+        if (KIND != SK_NONE && T.scl_kind == SC_M)
+          mfac = ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
+        if (KIND == SK_CROP) {
           if (o_in && u >= T.lo_m && u < T.hi_m) {
             dat.x = cur.x * zmask.x;
             dat.y = cur.y * zmask.y;
             dat.z = cur.z * zmask.z;
             dat.w = cur.w * zmask.w;
           }
-        } else if (T.kind == SK_THICK_M) {
+        } else if (KIND == SK_THICK_M) {
           if (o_in) {
-            int jr = jrow, js = jslot;
+            int jr = jrow;
+            uint32_t js = jaddr;
             for (int tap = ph; tap < T.K; tap += T.r) {
               if (jr >= 0 && jr < T.nj) {
-                const float4 lr = *reinterpret_cast<const float4 *>(
-                    lrm + ((size_t)js * TO + row) * TZ + 4 * lane);
+                const float4 lr = lds128(js + lr_own);
                 const float k = s_ker[tap];
                 dat.x = fmaf(k, lr.x, dat.x);
                 dat.y = fmaf(k, lr.y, dat.y);
@@ -347,19 +415,19 @@ __global__ void __launch_bounds__(NTHR, MINB)
                 dat.w = fmaf(k, lr.w, dat.w);
               }
               --jr;
-              js = js == 0 ? a.nlr - 1 : js - 1;
+              js = (js == lrm_a ? lrm_end : js) - lrm_stride;
             }
           }
-        } else if (T.kind == SK_THICK_Z) {
+        } else if (KIND == SK_THICK_Z) {
           if (o_in && u >= T.lo_m && u < T.hi_m) {
-            const float *lr = lrz + ((size_t)(u & 1) * TO + row) * kLrzPitch;
+            const uint32_t lr = lrz_a + (uint32_t)(((u & 1) * TO + row) * kLrzPitch) * 4u;
             float d[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               float acc = 0.f;
               int jl = zj0[k];
               for (int tap = zt0[k]; tap < T.K && jl >= 0; tap += T.r, --jl)
-                acc = fmaf(s_ker[tap], lr[jl], acc);
+                acc = fmaf(s_ker[tap], lds32(lr + 4u * jl), acc);
               d[k] = acc;
             }
             dat = make_float4(d[0], d[1], d[2], d[3]);
@@ -368,8 +436,8 @@ __global__ void __launch_bounds__(NTHR, MINB)
         // ---- D'D: per axis (2c - lo - hi) / vx^2 with the "lo" term dropped on the low
         //      edge; values past the high edge are the TMA's zero fill (bound = zero) ----
         const float4 pv = u > 0 ? prev : cur;
-        if (o == 0) om = cur;
-        if (z == 0) zl = cur.x;
+        if (o_is0) om = cur;
+        if (z_is0) zl = cur.x;
         float val[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -380,7 +448,8 @@ __global__ void __launch_bounds__(NTHR, MINB)
           const float d_o = (c - comp(om, k)) + (c - comp(op, k));
           const float d_z = (c - lft) + (c - rgt);
           const float dtd = fmaf(d_z, a.iv_z, fmaf(d_o, a.iv_o, d_m * a.iv_m));
-          const float data = fmaf(mfac * comp(thin, k), comp(dat, k), a.w_ident * c);
+          float data = a.w_ident * c;
+          if (KIND != SK_NONE) data = fmaf(mfac * comp(thin, k), comp(dat, k), data);
           val[k] = fmaf(a.rl2, dtd, data);
         }
         if (MODE == LHS_PLAIN) {
@@ -415,12 +484,13 @@ __global__ void __launch_bounds__(NTHR, MINB)
       // ---- advance ----
       prev = cur;
       cur = next;
-      su = sn;
-      if (T.kind == SK_THICK_M) {
+      au = an;
+      if (KIND == SK_THICK_M) {
         if (++ph == T.r) {
           ph = 0;
           ++jrow;
-          if (++jslot == a.nlr) jslot = 0;
+          jaddr += lrm_stride;
+          if (jaddr == lrm_end) jaddr = lrm_a;
         }
       }
       __syncthreads();  // every warp is done with plane u - 1; lrz of plane u + 1 is complete
@@ -503,7 +573,7 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
 int stream_mc_override = 0;  // test / tuning hook (plane-tiles per CTA), 0 = automatic
-int stream_min_blocks = 3;   // register budget variant: 3 (<= 80 regs) or 2 CTAs per SM
+int stream_min_blocks = 3;   // register budget variant: 3 (<= 80 regs) or 4 (<= 64) CTAs/SM
 typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
@@ -594,21 +664,28 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
                       128;  // slack for the 128-byte alignment of the ring
   if (smem > 200 * 1024) return UR_ERR_UNSUPPORTED;
 
-  static StreamKernel table[3][2] = {
-      {lhs_stream_kernel<LHS_PLAIN, 2>, lhs_stream_kernel<LHS_PLAIN, 3>},
-      {lhs_stream_kernel<LHS_RESID, 2>, lhs_stream_kernel<LHS_RESID, 3>},
-      {lhs_stream_kernel<LHS_ENERGY, 2>, lhs_stream_kernel<LHS_ENERGY, 3>}};
+#define UR_SK_ROW(M)                                                                         \
+  {                                                                                         \
+    {lhs_stream_kernel<M, SK_NONE, 3>, lhs_stream_kernel<M, SK_NONE, 4>},                   \
+        {lhs_stream_kernel<M, SK_CROP, 3>, lhs_stream_kernel<M, SK_CROP, 4>},               \
+        {lhs_stream_kernel<M, SK_THICK_M, 3>, lhs_stream_kernel<M, SK_THICK_M, 4>},         \
+        {lhs_stream_kernel<M, SK_THICK_Z, 3>, lhs_stream_kernel<M, SK_THICK_Z, 4>},         \
+  }
+  static StreamKernel table[3][4][2] = {UR_SK_ROW(LHS_PLAIN), UR_SK_ROW(LHS_RESID),
+                                        UR_SK_ROW(LHS_ENERGY)};
+#undef UR_SK_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 2; ++j)
-        UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)table[i][j],
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 2; ++j)
+          UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)table[i][k][j],
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
     attr_set = true;
   }
   const int mi = mode == LHS_PLAIN ? 0 : (mode == LHS_RESID ? 1 : 2);
-  StreamKernel kernel = table[mi][stream_min_blocks == 2 ? 0 : 1];
+  StreamKernel kernel = table[mi][T.kind][stream_min_blocks == 4 ? 1 : 0];
   // One wave of equally loaded CTAs: the (column, plane) tiles are cut into contiguous
   // ranges, one per resident CTA slot (occupancy x SM count).
   const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, TO);

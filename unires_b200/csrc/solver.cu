@@ -453,7 +453,7 @@ extern "C" int ur_tune(const char *name, int value) {
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
   } else if (!strcmp(name, "stream_minb")) {
-    stream_min_blocks = value == 2 ? 2 : 3;
+    stream_min_blocks = value == 4 ? 4 : 3;
   } else {
     set_error("ur_tune: unknown knob '%s'", name);
     return UR_ERR_ARG;
