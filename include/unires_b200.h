@@ -57,8 +57,9 @@ int ur_profile_matvec(int enable);
 int ur_profile_matvec_read(double *total_ms, int32_t *count);
 /* Tuning / test knobs (process-wide).  "lhs_variant": 0 automatic, 1 force the
  * direct (non-TMA) lhs kernel; "stream_mc": planes per CTA chunk of the TMA
- * streaming kernel (0 automatic); "stream_minb": its register-budget variant
- * (3 or 4 resident CTAs per SM).  Returns UR_ERR_ARG for unknown names.    */
+ * streaming kernel (0 automatic); "stream_rpt": rows per thread of that
+ * kernel (0 automatic, 1 = 8-row tiles, 2 = 16-row tiles).  Unknown names
+ * return UR_ERR_ARG.                                                        */
 int ur_tune(const char *name, int value);
 
 /* ---------------------------------------------------------------- finite

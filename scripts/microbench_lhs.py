@@ -42,28 +42,28 @@ def main():
     for c in range(len(sc.x)):
         op = _project.LhsOperator(sc.x[c], sc.y[c], method=sc.sett.method, do=sc.sett.do_proj,
                                   rho=sc.rho, vx_y=vx)
-        for variant, minb in ((0, 3), (0, 4)):
+        for variant, rpt in ((0, 1), (0, 2)):
             for mc in mcs:
                 tune('lhs_variant', variant)
                 tune('stream_mc', mc)
-                tune('stream_minb', minb)
+                tune('stream_rpt', rpt)
                 us = time_op(op, v)
-                print('channel %d stream minb %d q %3d: %8.1f us  %7.1f GB/s  frac %.3f'
-                      % (c, minb, mc, us, 8 * n / us / 1e3, 8 * n / us / 1e3 / peak), flush=True)
-    tune('stream_minb', 3)
+                print('channel %d stream rpt %d q %3d: %8.1f us  %7.1f GB/s  frac %.3f'
+                      % (c, rpt, mc, us, 8 * n / us / 1e3, 8 * n / us / 1e3 / peak), flush=True)
+    tune('stream_rpt', 0)
     tune('lhs_variant', 0)
     tune('stream_mc', 0)
     # denoise lhs (no projection)
     op = _project.LhsOperator([struct._input(tau=0.01)], struct._output(dim=dim, lam=0.1), do=False,
                               rho=1.0, vx_y=vx)
-    for minb in (3, 4):
+    for rpt in (1, 2):
         for mc in mcs:
             tune('stream_mc', mc)
-            tune('stream_minb', minb)
+            tune('stream_rpt', rpt)
             us = time_op(op, v)
-            print('denoise stream minb %d q %3d: %8.1f us  %7.1f GB/s  frac %.3f'
-                  % (minb, mc, us, 8 * n / us / 1e3, 8 * n / us / 1e3 / peak), flush=True)
-    tune('stream_minb', 3)
+            print('denoise stream rpt %d q %3d: %8.1f us  %7.1f GB/s  frac %.3f'
+                  % (rpt, mc, us, 8 * n / us / 1e3, 8 * n / us / 1e3 / peak), flush=True)
+    tune('stream_rpt', 0)
     tune('stream_mc', 0)
     # plain copy for reference
     a = torch.empty_like(v)

@@ -43,8 +43,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('rpt', [1, 2])
 @pytest.mark.parametrize('case', CASES)
-def test_stream_equals_direct_and_oracle(cuda, case):
+def test_stream_equals_direct_and_oracle(cuda, case, rpt):
     from unires_b200 import _project
     dim_y, fov, axis, factor, scl, mc = case
     obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
@@ -58,11 +59,13 @@ def test_stream_equals_direct_and_oracle(cuda, case):
         direct = op(v.to(cuda))
         _tune('lhs_variant', 0)
         _tune('stream_mc', mc)
+        _tune('stream_rpt', rpt)
         dot = torch.zeros(1, dtype=torch.float64, device=cuda)
         stream = op(v.to(cuda), dot=dot)
     finally:
         _tune('lhs_variant', 0)
         _tune('stream_mc', 0)
+        _tune('stream_rpt', 0)
     assert U.rel_l2(direct, ref) < 1e-5
     assert U.rel_l2(stream, ref) < 1e-5
     assert U.rel_l2(stream, direct) < 1e-6

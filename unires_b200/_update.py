@@ -171,6 +171,7 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett)
+    from . import parallel
     dim, vx = _geometry(y)
     n_vox = dim[0] * dim[1] * dim[2]
     rho_f = float(rho)
@@ -180,15 +181,20 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     field = torch.empty(dim, dtype=torch.float32, device=tmp.device)
     if sett.tolerance > 0:
         row = torch.zeros(3, dtype=torch.float64, device=tmp.device)
-        _nll_terms(x, y, sett, row, prior_field=field)
-        dist.all_reduce(field, group=group)
-        dist.all_reduce(row[1:2], group=group)
-        check(lib.ur_sqrt_sum(ptr(field), n_vox, ptr(row[2:3]), stream()))
-        row[0] = row[1] + row[2]
+
+        def sqrt_sum(f):
+            check(lib.ur_sqrt_sum(ptr(f), n_vox, ptr(row[2:3]), stream()))
+            return row[2].clone()
+
+        parallel.coupled_objective(
+            row, field, lambda r, f: _nll_terms(x, y, sett, r, prior_field=f), sqrt_sum, group)
         obj[n_iter, :] = row.to(obj.device, obj.dtype)
-    check(lib.ur_jtv_norm2(_ptr_array(ys), ptr(z), ptr(w), ptr(field), len(ys), lam, i3(dim),
-                           f3(vx), rho_f, float(sett.alpha), 0, stream()))
-    dist.all_reduce(field, group=group)
-    check(lib.ur_jtv_apply(_ptr_array(ys), ptr(z), ptr(w), ptr(field), ptr(tmp), len(ys), lam,
-                           i3(dim), f3(vx), rho_f, float(sett.alpha), stream()))
+    alpha = float(sett.alpha)
+    parallel.coupled_prox(
+        field,
+        lambda f: check(lib.ur_jtv_norm2(_ptr_array(ys), ptr(z), ptr(w), ptr(f), len(ys), lam,
+                                         i3(dim), f3(vx), rho_f, alpha, 0, stream())),
+        lambda f: check(lib.ur_jtv_apply(_ptr_array(ys), ptr(z), ptr(w), ptr(f), ptr(tmp), len(ys),
+                                         lam, i3(dim), f3(vx), rho_f, alpha, stream())),
+        group)
     return y, z, w, tmp, obj

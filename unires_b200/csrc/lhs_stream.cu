@@ -3,22 +3,26 @@
 //   out = w_ident * v  +  tau * A'S^2A v  +  rho lam^2 * D'D v        (+ CG epilogue)
 //
 // for the lattice-aligned operators of solver.cuh (at most one observation term).
-// A CTA owns a (TO x TZ) = (8 x 128) column of the volume in the two non-marching axes
-// and marches along the third ("m": x, or y when the slices are thick along y) over a
-// chunk of planes.  Each plane tile (with a 1-row / hz-column halo) is brought into a
+// A CTA owns a (TO x TZ) column of the volume in the two non-marching axes (TO = 8 or 16
+// rows, TZ = 128: 8 warps, RPT rows per warp, one float4 per lane and row) and marches
+// along the third axis ("m": x, or y when the slices are thick along y) over a contiguous
+// range of planes.  Each plane tile (with a 1-row / hz-column halo) is brought into a
 // shared-memory ring by ONE cp.async.bulk.tensor (TMA) per plane, completing on an
-// mbarrier; out-of-volume elements are zero-filled by the TMA unit, which is exactly
-// the reference's bound='zero'.  Every thread keeps the m-1 / m / m+1 values of its own
-// z-quad in registers, so per plane it reads 3 float4 + 2 floats from shared memory for
-// the 7-point D'D stencil.  The slice-profile term is evaluated through the decimated
-// grid, as the reference does (pull -> conv -> scale -> conv' -> push), but entirely
-// on-chip:
+// mbarrier; out-of-volume elements are zero-filled by the TMA unit, which is exactly the
+// reference's bound='zero'.  Every thread keeps the m-1 / m / m+1 values of its own
+// z-quads in registers and takes its z neighbours from the adjacent lanes by shuffle, so
+// per plane it reads only the next plane's quads and the two row-halo quads from shared
+// memory for the 7-point D'D stencil.  The slice-profile term is evaluated through the
+// decimated grid, as the reference does (pull -> conv -> scale -> conv' -> push), but
+// entirely on-chip:
 //   thick along m: each low-res row j is formed ONCE per thread when the march reaches
 //                  its first plane (K taps over the look-ahead planes of the ring) and
 //                  parked in a thread-private shared-memory slot until its last plane;
 //   thick along z: the low-res row segment of the NEXT plane is formed cooperatively
 //                  into a double-buffered shared array while the current plane is output.
-// HBM traffic is the algorithmic 8 bytes per voxel (+ halo re-reads served by L2).
+// The (column, plane) tiles are cut into equal contiguous ranges, one per resident CTA
+// slot, so the grid is exactly one balanced wave.  HBM traffic is the algorithmic 8 bytes
+// per voxel (+ halo re-reads served by L2).
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
@@ -30,13 +34,10 @@
 
 namespace ur {
 
-constexpr int TO = 8;      // rows of the tile (one warp per row)
-constexpr int TZ = 128;    // z extent of the tile (32 lanes x float4)
+constexpr int TZ = 128;  // z extent of the tile (32 lanes x float4)
 constexpr int NTHR = 256;
+constexpr int NWARP = NTHR / 32;
 constexpr int kMaxSlots = 24;
-#ifndef UR_STREAM_MIN_BLOCKS
-#define UR_STREAM_MIN_BLOCKS 3
-#endif
 constexpr int kLrzPitch = TZ / 2 + 8;
 
 enum { SK_NONE = 0, SK_CROP = 1, SK_THICK_M = 2, SK_THICK_Z = 3 };
@@ -56,7 +57,7 @@ struct StreamArgs {
   int nm, no, nz;
   long long gs_m, gs_o;  // element strides of the marching / row axis in global memory
   int march_y;
-  float iv_m, iv_o, iv_z, rl2, w_ident;
+  float iv_m, iv_o, iv_z, rl2, w_ident;  // iv_* = 1 / vx^2
   StreamTerm T;
   int q;     // plane-tiles per CTA: contiguous range in (column, plane) order
   int ncol;  // number of (o, z) columns
@@ -74,46 +75,15 @@ struct StreamArgs {
 };
 
 // ------------------------------------------------------------------ PTX helpers
+// Shared memory is addressed through 32-bit shared-window addresses and explicit
+// ld.shared / st.shared: the ring base is computed at run time (128-byte aligned), which
+// would otherwise demote every access to a generic load.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-__device__ __forceinline__ float comp(const float4 &q, int k) {
-  return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
-}
-
-// Shared memory is addressed through 32-bit shared-window addresses and explicit
-// ld.shared / st.shared: the ring base is computed at run time (128-byte aligned), which
-// would otherwise demote every access to a generic load.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -160,6 +130,10 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *m
       : "memory");
 }
 
+__device__ __forceinline__ float comp(const float4 &q, int k) {
+  return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
+}
+
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
   if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
@@ -169,7 +143,7 @@ __device__ __forceinline__ int floordiv(int a, int b) {
 // Ring geometry in shared-window addresses.
 struct Ring {
   uint32_t base, end, plane_b;  // planes
-  uint32_t bar, bar_end;        // mbarriers (8 bytes each)
+  uint32_t bar;                 // mbarriers (8 bytes each)
 };
 
 // One position of the ring: plane address, its mbarrier and the phase parity to wait for.
@@ -186,16 +160,19 @@ struct RingPos {
   }
 };
 
-template <int MODE, int KIND, int MINB>
-__global__ void __launch_bounds__(NTHR, MINB)
+// MODE: LhsMode epilogue.  KIND: observation term (SK_*).  RPT: rows per thread (1 | 2).
+template <int MODE, int KIND, int RPT>
+__global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     lhs_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
+  constexpr int TO = NWARP * RPT;  // rows of the tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kMaxWarps];
   __shared__ uint64_t s_bar[kMaxSlots];
   __shared__ float s_ker[UR_MAX_TAPS];
   if (a.done && *a.done) return;
 
-  const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = warp * RPT;  // first tile row of this thread
   const StreamTerm &T = a.T;
   const int ns = a.ns;
 
@@ -204,7 +181,6 @@ __global__ void __launch_bounds__(NTHR, MINB)
   R.plane_b = (uint32_t)a.plane_floats * 4u;
   R.end = R.base + (uint32_t)ns * R.plane_b;
   R.bar = smem_u32(s_bar);
-  R.bar_end = R.bar + 8u * (uint32_t)ns;
   const uint32_t lrm_a = R.end;  // [nlr][TO][TZ] floats (thick along m)
   const uint32_t lrm_stride = TO * TZ * 4u;
   const uint32_t lrm_end = lrm_a + (uint32_t)a.nlr * lrm_stride;
@@ -212,8 +188,9 @@ __global__ void __launch_bounds__(NTHR, MINB)
 
   const uint32_t plane_bytes = (uint32_t)(a.sz * (TO + 2) * sizeof(float));
   const uint32_t sz_b = (uint32_t)a.sz * 4u;
-  const uint32_t own_b = (uint32_t)((row + 1) * a.sz + a.hz + 4 * lane) * 4u;  // own quad
-  const uint32_t lr_own = (uint32_t)(row * TZ + 4 * lane) * 4u;
+  // first own quad inside a plane (tile row row0 is plane row row0 + 1); next rows: + sz_b
+  const uint32_t own_b = (uint32_t)((row0 + 1) * a.sz + a.hz + 4 * lane) * 4u;
+  const uint32_t lr_own = (uint32_t)(row0 * TZ + 4 * lane) * 4u;  // next rows: + TZ * 4
 
   if (tid < UR_MAX_TAPS) s_ker[tid] = T.ker[tid];
   if (tid == 0) {
@@ -239,8 +216,8 @@ __global__ void __launch_bounds__(NTHR, MINB)
     t += m1 - m0;
     const int cz = col % a.gx, co = col / a.gx;
     const int z0 = cz * TZ, o0 = co * TO;
-    const int o = o0 + row, z = z0 + 4 * lane;
-    const bool active = (o < a.no) && (z < a.nz);
+    const int o_first = o0 + row0, z = z0 + 4 * lane;
+    const bool z_ok = z < a.nz;
 
     const int u_begin = m0 - a.B;
     const int first = u_begin - 1;
@@ -260,25 +237,31 @@ __global__ void __launch_bounds__(NTHR, MINB)
       for (int n = 0; n < ns && iq <= last; ++n) issue_next();
 
     // ---- per-thread constants of the observation term ----
-    const bool o_in = KIND != SK_NONE && o >= T.lo_o && o < T.hi_o;
+    bool active[RPT], o_in[RPT];
+    float4 thin[RPT];  // tau x (scaling that alternates along a thin axis): per-voxel factor
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int o = o_first + i;
+      active[i] = z_ok && o < a.no;
+      o_in[i] = KIND != SK_NONE && o >= T.lo_o && o < T.hi_o;
+      thin[i] = make_float4(T.tau, T.tau, T.tau, T.tau);
+      if (KIND != SK_NONE) {
+        if (T.scl_kind == SC_O) {
+          const float f = T.tau * (((o - T.scl_off) & 1) ? T.s_odd : T.s_even);
+          thin[i] = make_float4(f, f, f, f);
+        } else if (T.scl_kind == SC_Z) {
+          const float f0 = T.tau * (((z - T.scl_off) & 1) ? T.s_odd : T.s_even);
+          const float f1 = T.tau * (((z - T.scl_off) & 1) ? T.s_even : T.s_odd);
+          thin[i] = make_float4(f0, f1, f0, f1);
+        }
+      }
+    }
     float4 zmask = make_float4(0.f, 0.f, 0.f, 0.f);
     if (KIND == SK_CROP || KIND == SK_THICK_M) {
       zmask.x = (z + 0 >= T.lo_z && z + 0 < T.hi_z) ? 1.f : 0.f;
       zmask.y = (z + 1 >= T.lo_z && z + 1 < T.hi_z) ? 1.f : 0.f;
       zmask.z = (z + 2 >= T.lo_z && z + 2 < T.hi_z) ? 1.f : 0.f;
       zmask.w = (z + 3 >= T.lo_z && z + 3 < T.hi_z) ? 1.f : 0.f;
-    }
-    // scaling that alternates along a *thin* axis is a per-voxel factor (tau folded in)
-    float4 thin = make_float4(T.tau, T.tau, T.tau, T.tau);
-    if (KIND != SK_NONE) {
-      if (T.scl_kind == SC_O) {
-        const float f = T.tau * (((o - T.scl_off) & 1) ? T.s_odd : T.s_even);
-        thin = make_float4(f, f, f, f);
-      } else if (T.scl_kind == SC_Z) {
-        const float f0 = T.tau * (((z - T.scl_off) & 1) ? T.s_odd : T.s_even);
-        const float f1 = T.tau * (((z - T.scl_off) & 1) ? T.s_even : T.s_odd);
-        thin = make_float4(f0, f1, f0, f1);
-      }
     }
     // thick along z: low-res rows touching this tile and, per component of this thread's
     // quad, the local index of its highest row and the tap that row contributes
@@ -302,16 +285,19 @@ __global__ void __launch_bounds__(NTHR, MINB)
           zt0[k] = up - j_hi * T.r;
         }
       }
-      lrz_src_off = (uint32_t)((row + 1) * a.sz + a.hz + (jz_lo * T.r + T.off - z0)) * 4u;
+      lrz_src_off = (uint32_t)((row0 + 1) * a.sz + a.hz + (jz_lo * T.r + T.off - z0)) * 4u;
     }
-    auto build_lrz = [&](uint32_t plane_a, int buf) {  // low-res z-rows, one warp per row
-      const uint32_t dst = lrz_a + (uint32_t)((buf * TO + row) * kLrzPitch) * 4u;
-      for (int jj = lane; jj < njt; jj += 32) {
-        const uint32_t src = plane_a + lrz_src_off + (uint32_t)(jj * T.r) * 4u;
-        float acc = 0.f;
-        for (int tt = 0; tt < T.K; ++tt) acc = fmaf(s_ker[tt], lds32(src + 4u * tt), acc);
-        if (T.scl_kind == SC_CONV) acc *= ((jz_lo + jj) & 1) ? T.s_odd : T.s_even;
-        sts32(dst + 4u * jj, acc);
+    auto build_lrz = [&](uint32_t plane_a, int buf) {  // low-res z-rows, RPT rows per warp
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const uint32_t dst = lrz_a + (uint32_t)((buf * TO + row0 + i) * kLrzPitch) * 4u;
+        for (int jj = lane; jj < njt; jj += 32) {
+          const uint32_t src = plane_a + lrz_src_off + i * sz_b + (uint32_t)(jj * T.r) * 4u;
+          float acc = 0.f;
+          for (int tt = 0; tt < T.K; ++tt) acc = fmaf(s_ker[tt], lds32(src + 4u * tt), acc);
+          if (T.scl_kind == SC_CONV) acc *= ((jz_lo + jj) & 1) ? T.s_odd : T.s_even;
+          sts32(dst + 4u * jj, acc);
+        }
       }
     };
 
@@ -321,12 +307,16 @@ __global__ void __launch_bounds__(NTHR, MINB)
       mbar_wait_a(wp.ba, wp.par);
       wp.inc(R);
     }
-    float4 prev = lds128(a_first + own_b);
     uint32_t au = a_first + R.plane_b;  // plane u
     if (au == R.end) au = R.base;
-    float4 cur = lds128(au + own_b);
+    float4 prev[RPT], cur[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      prev[i] = lds128(a_first + own_b + i * sz_b);
+      cur[i] = lds128(au + own_b + i * sz_b);
+    }
 
-    int ph = 0, jrow = 0;  // thick along m: phase inside the stride / current low-res row
+    int ph = 0, jrow = 0;    // thick along m: phase inside the stride / current low-res row
     uint32_t jaddr = lrm_a;  // parking slot of row jrow
     if (KIND == SK_THICK_M) {
       const int t0 = u_begin - T.off;
@@ -338,152 +328,175 @@ __global__ void __launch_bounds__(NTHR, MINB)
       build_lrz(au, u_begin & 1);
       __syncthreads();
     }
-    const bool o_is0 = o == 0, z_is0 = z == 0;
+    const bool o_is0 = o_first == 0, z_is0 = z == 0;
 
     for (int u = u_begin; u < m1; ++u) {
       mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
       wp.inc(R);
       uint32_t an = au + R.plane_b;  // plane u + 1
       if (an == R.end) an = R.base;
-      const float4 next = lds128(an + own_b);
-      // z neighbours of the quad come from the adjacent lanes; only the tile edges read smem
-      float zl = __shfl_up_sync(0xffffffffu, cur.w, 1);
-      float zr = __shfl_down_sync(0xffffffffu, cur.x, 1);
-      if (lane == 0) zl = lds32(au + own_b - 4u);
-      if (lane == 31) zr = lds32(au + own_b + 16u);
+      float4 next[RPT];
+      float zl[RPT], zr[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        next[i] = lds128(an + own_b + i * sz_b);
+        // z neighbours of the quad come from the adjacent lanes; only the tile edges read smem
+        zl[i] = __shfl_up_sync(0xffffffffu, cur[i].w, 1);
+        zr[i] = __shfl_down_sync(0xffffffffu, cur[i].x, 1);
+        if (lane == 0) zl[i] = lds32(au + own_b + i * sz_b - 4u);
+        if (lane == 31) zr[i] = lds32(au + own_b + i * sz_b + 16u);
+      }
 
       if (KIND == SK_THICK_M) {
-        if (ph == 0 && jrow >= 0 && jrow < T.nj && o_in && active) {
+        if (ph == 0 && jrow >= 0 && jrow < T.nj) {
           // low-res row jrow starts at this plane: form it once and park it
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          uint32_t s = au;
-          for (int tt = 0; tt < T.K; ++tt) {
-            const float4 q = tt == 0 ? cur : (tt == 1 ? next : lds128(s + own_b));
-            const float k = s_ker[tt];
-            acc.x = fmaf(k, q.x, acc.x);
-            acc.y = fmaf(k, q.y, acc.y);
-            acc.z = fmaf(k, q.z, acc.z);
-            acc.w = fmaf(k, q.w, acc.w);
-            s += R.plane_b;
-            if (s == R.end) s = R.base;
-          }
           float sc = 1.f;
           if (T.scl_kind == SC_CONV) sc = (jrow & 1) ? T.s_odd : T.s_even;
-          acc.x *= sc * zmask.x;
-          acc.y *= sc * zmask.y;
-          acc.z *= sc * zmask.z;
-          acc.w *= sc * zmask.w;
-          sts128(jaddr + lr_own, acc);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            if (o_in[i] && active[i]) {
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              uint32_t s = au;
+              for (int tt = 0; tt < T.K; ++tt) {
+                const float4 q =
+                    tt == 0 ? cur[i] : (tt == 1 ? next[i] : lds128(s + own_b + i * sz_b));
+                const float k = s_ker[tt];
+                acc.x = fmaf(k, q.x, acc.x);
+                acc.y = fmaf(k, q.y, acc.y);
+                acc.z = fmaf(k, q.z, acc.z);
+                acc.w = fmaf(k, q.w, acc.w);
+                s += R.plane_b;
+                if (s == R.end) s = R.base;
+              }
+              acc.x *= sc * zmask.x;
+              acc.y *= sc * zmask.y;
+              acc.z *= sc * zmask.z;
+              acc.w *= sc * zmask.w;
+              sts128(jaddr + lr_own + i * (TZ * 4u), acc);
+            }
+          }
         }
       } else if (KIND == SK_THICK_Z) {
         if (u + 1 < m1) build_lrz(an, (u + 1) & 1);
       }
 
-      if (u >= m0 && active) {
-        float4 om = lds128(au + own_b - sz_b);
-        const float4 op = lds128(au + own_b + sz_b);
-        const size_t gi = (size_t)u * a.gs_m + (size_t)o * a.gs_o + z;
-        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
-        if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
-        if (MODE == LHS_ENERGY && a.update_p) {
-          rq = *reinterpret_cast<const float4 *>(a.r + gi);
-          pq = *reinterpret_cast<const float4 *>(a.p + gi);
-        }
-        // ---- observation term through the decimated grid ----
-        float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u >= m0) {
+        // row halos: above the first own row, below the last own row
+        float4 om_edge = lds128(au + own_b - sz_b);
+        const float4 op_edge = lds128(au + own_b + RPT * sz_b);
+        if (o_is0) om_edge = cur[0];
         float mfac = 1.f;
         if (KIND != SK_NONE && T.scl_kind == SC_M)
           mfac = ((u - T.scl_off) & 1) ? T.s_odd : T.s_even;
-        if (KIND == SK_CROP) {
-          if (o_in && u >= T.lo_m && u < T.hi_m) {
-            dat.x = cur.x * zmask.x;
-            dat.y = cur.y * zmask.y;
-            dat.z = cur.z * zmask.z;
-            dat.w = cur.w * zmask.w;
+        const bool m_in = KIND != SK_NONE && u >= T.lo_m && u < T.hi_m;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          if (!active[i]) continue;
+          const size_t gi = (size_t)u * a.gs_m + (size_t)(o_first + i) * a.gs_o + z;
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
+          if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
+          if (MODE == LHS_ENERGY && a.update_p) {
+            rq = *reinterpret_cast<const float4 *>(a.r + gi);
+            pq = *reinterpret_cast<const float4 *>(a.p + gi);
           }
-        } else if (KIND == SK_THICK_M) {
-          if (o_in) {
-            int jr = jrow;
-            uint32_t js = jaddr;
-            for (int tap = ph; tap < T.K; tap += T.r) {
-              if (jr >= 0 && jr < T.nj) {
-                const float4 lr = lds128(js + lr_own);
-                const float k = s_ker[tap];
-                dat.x = fmaf(k, lr.x, dat.x);
-                dat.y = fmaf(k, lr.y, dat.y);
-                dat.z = fmaf(k, lr.z, dat.z);
-                dat.w = fmaf(k, lr.w, dat.w);
+          // ---- observation term through the decimated grid ----
+          float4 dat = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (KIND == SK_CROP) {
+            if (o_in[i] && m_in) {
+              dat.x = cur[i].x * zmask.x;
+              dat.y = cur[i].y * zmask.y;
+              dat.z = cur[i].z * zmask.z;
+              dat.w = cur[i].w * zmask.w;
+            }
+          } else if (KIND == SK_THICK_M) {
+            if (o_in[i]) {
+              int jr = jrow;
+              uint32_t js = jaddr;
+              for (int tap = ph; tap < T.K; tap += T.r) {
+                if (jr >= 0 && jr < T.nj) {
+                  const float4 lr = lds128(js + lr_own + i * (TZ * 4u));
+                  const float k = s_ker[tap];
+                  dat.x = fmaf(k, lr.x, dat.x);
+                  dat.y = fmaf(k, lr.y, dat.y);
+                  dat.z = fmaf(k, lr.z, dat.z);
+                  dat.w = fmaf(k, lr.w, dat.w);
+                }
+                --jr;
+                js = (js == lrm_a ? lrm_end : js) - lrm_stride;
               }
-              --jr;
-              js = (js == lrm_a ? lrm_end : js) - lrm_stride;
+            }
+          } else if (KIND == SK_THICK_Z) {
+            if (o_in[i] && m_in) {
+              const uint32_t lr =
+                  lrz_a + (uint32_t)(((u & 1) * TO + row0 + i) * kLrzPitch) * 4u;
+              float d[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float acc = 0.f;
+                int jl = zj0[k];
+                for (int tap = zt0[k]; tap < T.K && jl >= 0; tap += T.r, --jl)
+                  acc = fmaf(s_ker[tap], lds32(lr + 4u * jl), acc);
+                d[k] = acc;
+              }
+              dat = make_float4(d[0], d[1], d[2], d[3]);
             }
           }
-        } else if (KIND == SK_THICK_Z) {
-          if (o_in && u >= T.lo_m && u < T.hi_m) {
-            const uint32_t lr = lrz_a + (uint32_t)(((u & 1) * TO + row) * kLrzPitch) * 4u;
-            float d[4];
+          // ---- D'D: per axis (2c - lo - hi) / vx^2 with the "lo" term dropped on the low
+          //      edge; values past the high edge are the TMA's zero fill (bound = zero) ----
+          const float4 pv = u > 0 ? prev[i] : cur[i];
+          const float4 om = i == 0 ? om_edge : cur[i > 0 ? i - 1 : 0];
+          const float4 op = i == RPT - 1 ? op_edge : cur[i < RPT - 1 ? i + 1 : 0];
+          const float zlv = z_is0 ? cur[i].x : zl[i];
+          float val[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float acc = 0.f;
-              int jl = zj0[k];
-              for (int tap = zt0[k]; tap < T.K && jl >= 0; tap += T.r, --jl)
-                acc = fmaf(s_ker[tap], lds32(lr + 4u * jl), acc);
-              d[k] = acc;
-            }
-            dat = make_float4(d[0], d[1], d[2], d[3]);
+          for (int k = 0; k < 4; ++k) {
+            const float c = comp(cur[i], k);
+            const float lft = k == 0 ? zlv : comp(cur[i], k - 1);
+            const float rgt = k == 3 ? zr[i] : comp(cur[i], k + 1);
+            const float d_m = (c - comp(pv, k)) + (c - comp(next[i], k));
+            const float d_o = (c - comp(om, k)) + (c - comp(op, k));
+            const float d_z = (c - lft) + (c - rgt);
+            const float dtd = fmaf(d_z, a.iv_z, fmaf(d_o, a.iv_o, d_m * a.iv_m));
+            float data = a.w_ident * c;
+            if (KIND != SK_NONE) data = fmaf(mfac * comp(thin[i], k), comp(dat, k), data);
+            val[k] = fmaf(a.rl2, dtd, data);
           }
-        }
-        // ---- D'D: per axis (2c - lo - hi) / vx^2 with the "lo" term dropped on the low
-        //      edge; values past the high edge are the TMA's zero fill (bound = zero) ----
-        const float4 pv = u > 0 ? prev : cur;
-        if (o_is0) om = cur;
-        if (z_is0) zl = cur.x;
-        float val[4];
+          if (MODE == LHS_PLAIN) {
+            *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float c = comp(cur, k);
-          const float lft = k == 0 ? zl : comp(cur, k - 1);
-          const float rgt = k == 3 ? zr : comp(cur, k + 1);
-          const float d_m = (c - comp(pv, k)) + (c - comp(next, k));
-          const float d_o = (c - comp(om, k)) + (c - comp(op, k));
-          const float d_z = (c - lft) + (c - rgt);
-          const float dtd = fmaf(d_z, a.iv_z, fmaf(d_o, a.iv_o, d_m * a.iv_m));
-          float data = a.w_ident * c;
-          if (KIND != SK_NONE) data = fmaf(mfac * comp(thin, k), comp(dat, k), data);
-          val[k] = fmaf(a.rl2, dtd, data);
-        }
-        if (MODE == LHS_PLAIN) {
-          *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
+            for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur[i], k), val[k]);
+          } else if (MODE == LHS_RESID) {
+            float4 rr;
+            rr.x = __fsub_rn(bq.x, val[0]);
+            rr.y = __fsub_rn(bq.y, val[1]);
+            rr.z = __fsub_rn(bq.z, val[2]);
+            rr.w = __fsub_rn(bq.w, val[3]);
+            *reinterpret_cast<float4 *>(a.r + gi) = rr;
+            *reinterpret_cast<float4 *>(a.p + gi) = rr;
+            part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
+                    (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur, k), val[k]);
-        } else if (MODE == LHS_RESID) {
-          float4 rr;
-          rr.x = __fsub_rn(bq.x, val[0]);
-          rr.y = __fsub_rn(bq.y, val[1]);
-          rr.z = __fsub_rn(bq.z, val[2]);
-          rr.w = __fsub_rn(bq.w, val[3]);
-          *reinterpret_cast<float4 *>(a.r + gi) = rr;
-          *reinterpret_cast<float4 *>(a.p + gi) = rr;
-          part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
-                  (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur, k));
-          if (a.update_p) {
-            const float beta = (float)a.fin.st->beta;
-            float4 pn;
-            pn.x = __fadd_rn(__fmul_rn(beta, pq.x), rq.x);
-            pn.y = __fadd_rn(__fmul_rn(beta, pq.y), rq.y);
-            pn.z = __fadd_rn(__fmul_rn(beta, pq.z), rq.z);
-            pn.w = __fadd_rn(__fmul_rn(beta, pq.w), rq.w);
-            *reinterpret_cast<float4 *>(a.p + gi) = pn;
+            for (int k = 0; k < 4; ++k)
+              part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur[i], k));
+            if (a.update_p) {
+              const float beta = (float)a.fin.st->beta;
+              float4 pn;
+              pn.x = __fadd_rn(__fmul_rn(beta, pq.x), rq.x);
+              pn.y = __fadd_rn(__fmul_rn(beta, pq.y), rq.y);
+              pn.z = __fadd_rn(__fmul_rn(beta, pq.z), rq.z);
+              pn.w = __fadd_rn(__fmul_rn(beta, pq.w), rq.w);
+              *reinterpret_cast<float4 *>(a.p + gi) = pn;
+            }
           }
         }
       }
       // ---- advance ----
-      prev = cur;
-      cur = next;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        prev[i] = cur[i];
+        cur[i] = next[i];
+      }
       au = an;
       if (KIND == SK_THICK_M) {
         if (++ph == T.r) {
@@ -524,10 +537,10 @@ static EncodeTiledFn encode_fn() {
 
 struct MapKey {
   const void *ptr;
-  int nx, ny, nz, sz, march_y;
+  int nx, ny, nz, sz, march_y, rows;
   bool operator==(const MapKey &o) const {
     return ptr == o.ptr && nx == o.nx && ny == o.ny && nz == o.nz && sz == o.sz &&
-           march_y == o.march_y;
+           march_y == o.march_y && rows == o.rows;
   }
 };
 struct MapKeyHash {
@@ -537,15 +550,18 @@ struct MapKeyHash {
     h = h * 1315423911u + k.ny;
     h = h * 1315423911u + k.nz;
     h = h * 1315423911u + k.sz * 2 + k.march_y;
+    h = h * 1315423911u + k.rows;
     return h;
   }
 };
 
-static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y,
+// 3-D tensor map over the (X, Y, Z) float volume with a box of one plane tile:
+// sz floats along z, `rows` rows along the non-marching axis, 1 plane along the march.
+static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
                            CUtensorMap *out) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{v, nx, ny, nz, sz, march_y};
+  MapKey key{v, nx, ny, nz, sz, march_y, rows};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -556,8 +572,8 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
   if (!fn) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
   cuuint64_t gstr[2] = {(cuuint64_t)nz * 4, (cuuint64_t)nz * ny * 4};
-  cuuint32_t box[3] = {(cuuint32_t)sz, march_y ? 1u : (cuuint32_t)(TO + 2),
-                       march_y ? (cuuint32_t)(TO + 2) : 1u};
+  cuuint32_t box[3] = {(cuuint32_t)sz, march_y ? 1u : (cuuint32_t)rows,
+                       march_y ? (cuuint32_t)rows : 1u};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)v, gdim, gstr, box, estr,
@@ -573,7 +589,7 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
 int stream_mc_override = 0;  // test / tuning hook (plane-tiles per CTA), 0 = automatic
-int stream_min_blocks = 3;   // register budget variant: 3 (<= 80 regs) or 4 (<= 64) CTAs/SM
+int stream_rpt = 0;          // rows per thread: 0 automatic, 1 (8-row tiles), 2 (16-row tiles)
 typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
@@ -653,23 +669,36 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
     S.nlr = (T.K + T.r - 1) / T.r + 1;
     if (S.nlr > 6) return UR_ERR_UNSUPPORTED;
   }
-  S.ns = S.L + 2 + 3;
-  if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
-  S.hz = hz;
-  S.sz = TZ + 2 * hz;
-  S.plane_floats = (S.sz * (TO + 2) + 31) / 32 * 32;
-  const size_t smem = ((size_t)S.ns * S.plane_floats + (size_t)S.nlr * TO * TZ +
-                       (T.kind == SK_THICK_Z ? 2 * TO * kLrzPitch : 0)) *
-                          sizeof(float) +
-                      128;  // slack for the 128-byte alignment of the ring
-  if (smem > 200 * 1024) return UR_ERR_UNSUPPORTED;
+  // rows per thread: 16-row tiles halve the per-plane bookkeeping per voxel; fall back to
+  // 8-row tiles when the volume has few rows or the ring would not fit twice per SM
+  // (measured at 256^3: 16-row tiles win without a thick term, 8-row tiles with one --
+  // the thick kernels need 3 resident CTAs per SM to hide the ring latency)
+  int rpt = (T.kind == SK_THICK_M || T.kind == SK_THICK_Z) ? 1 : 2;
+  if (stream_rpt == 1 || stream_rpt == 2) rpt = stream_rpt;
+  if (S.no <= NWARP) rpt = 1;
+  size_t smem = 0;
+  for (;; rpt = 1) {
+    const int to = NWARP * rpt;
+    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2);
+    if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
+    S.hz = hz;
+    S.sz = TZ + 2 * hz;
+    S.plane_floats = (S.sz * (to + 2) + 31) / 32 * 32;
+    smem = ((size_t)S.ns * S.plane_floats + (size_t)S.nlr * to * TZ +
+            (T.kind == SK_THICK_Z ? 2 * to * kLrzPitch : 0)) *
+               sizeof(float) +
+           128;  // slack for the 128-byte alignment of the ring
+    if (smem <= (rpt == 1 ? 200u : 112u) * 1024u) break;
+    if (rpt == 1) return UR_ERR_UNSUPPORTED;
+  }
+  const int to = NWARP * rpt;
 
-#define UR_SK_ROW(M)                                                                         \
+#define UR_SK_ROW(M)                                                                        \
   {                                                                                         \
-    {lhs_stream_kernel<M, SK_NONE, 3>, lhs_stream_kernel<M, SK_NONE, 4>},                   \
-        {lhs_stream_kernel<M, SK_CROP, 3>, lhs_stream_kernel<M, SK_CROP, 4>},               \
-        {lhs_stream_kernel<M, SK_THICK_M, 3>, lhs_stream_kernel<M, SK_THICK_M, 4>},         \
-        {lhs_stream_kernel<M, SK_THICK_Z, 3>, lhs_stream_kernel<M, SK_THICK_Z, 4>},         \
+    {lhs_stream_kernel<M, SK_NONE, 1>, lhs_stream_kernel<M, SK_NONE, 2>},                   \
+        {lhs_stream_kernel<M, SK_CROP, 1>, lhs_stream_kernel<M, SK_CROP, 2>},               \
+        {lhs_stream_kernel<M, SK_THICK_M, 1>, lhs_stream_kernel<M, SK_THICK_M, 2>},         \
+        {lhs_stream_kernel<M, SK_THICK_Z, 1>, lhs_stream_kernel<M, SK_THICK_Z, 2>},         \
   }
   static StreamKernel table[3][4][2] = {UR_SK_ROW(LHS_PLAIN), UR_SK_ROW(LHS_RESID),
                                         UR_SK_ROW(LHS_ENERGY)};
@@ -685,10 +714,10 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
     attr_set = true;
   }
   const int mi = mode == LHS_PLAIN ? 0 : (mode == LHS_RESID ? 1 : 2);
-  StreamKernel kernel = table[mi][T.kind][stream_min_blocks == 4 ? 1 : 0];
+  StreamKernel kernel = table[mi][T.kind][rpt - 1];
   // One wave of equally loaded CTAs: the (column, plane) tiles are cut into contiguous
   // ranges, one per resident CTA slot (occupancy x SM count).
-  const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, TO);
+  const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, to);
   S.gx = (int)gx;
   S.ncol = (int)(gx * gy);
   const long long total = (long long)S.ncol * S.nm;
@@ -706,7 +735,8 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   const unsigned n_cta = (unsigned)((total + q - 1) / q);
 
   CUtensorMap map;
-  if (!get_tensor_map(A.v, A.nx, A.ny, A.nz, S.sz, march, &map)) return UR_ERR_UNSUPPORTED;
+  if (!get_tensor_map(A.v, A.nx, A.ny, A.nz, S.sz, march, to + 2, &map))
+    return UR_ERR_UNSUPPORTED;
 
   S.v = A.v;
   S.out = A.out;

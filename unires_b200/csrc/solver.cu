@@ -346,7 +346,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 // optional event instrumentation of the matvec launches (bench.py roofline)
 // ---------------------------------------------------------------------------
 extern int stream_mc_override;  // lhs_stream.cu
-extern int stream_min_blocks;   // lhs_stream.cu
+extern int stream_rpt;          // lhs_stream.cu
 static int g_lhs_variant = 0;
 
 struct MatvecProfile {
@@ -452,8 +452,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_lhs_variant = value;
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
-  } else if (!strcmp(name, "stream_minb")) {
-    stream_min_blocks = value == 4 ? 4 : 3;
+  } else if (!strcmp(name, "stream_rpt")) {
+    stream_rpt = (value == 1 || value == 2) ? value : 0;
   } else {
     set_error("ur_tune: unknown knob '%s'", name);
     return UR_ERR_ARG;
