@@ -115,4 +115,6 @@ def test_cg_stream_vs_direct(cuda, stop):
         _tune('stream_mc', 0)
     assert res[0][1] == res[1][1]
     assert U.rel_l2(res[0][0], res[1][0]) < 1e-5
-    assert all(abs(a - b_) <= 1e-7 * abs(b_) + 1e-12 for a, b_ in zip(res[0][2], res[1][2]))
+    # the two kernels round D'D differently; sqrt(r.r) of the recursively updated residual
+    # amplifies that towards convergence
+    assert all(abs(a - b_) <= 1e-4 * abs(b_) + 1e-12 for a, b_ in zip(res[0][2], res[1][2]))

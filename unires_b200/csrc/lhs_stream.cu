@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       __syncthreads();
     }
     const bool o_is0 = o_first == 0, z_is0 = z == 0;
+    // global element offset of this thread's first quad in plane u (advanced per output plane)
+    size_t goff = (size_t)m0 * a.gs_m + (size_t)o_first * a.gs_o + z;
+    int pend = 0;  // planes consumed since the ring was last refilled
 
     for (int u = u_begin; u < m1; ++u) {
       mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           if (!active[i]) continue;
-          const size_t gi = (size_t)u * a.gs_m + (size_t)(o_first + i) * a.gs_o + z;
+          const size_t gi = goff + (size_t)i * a.gs_o;
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
           if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
           if (MODE == LHS_ENERGY && a.update_p) {
@@ -453,9 +456,11 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             const float c = comp(cur[i], k);
             const float lft = k == 0 ? zlv : comp(cur[i], k - 1);
             const float rgt = k == 3 ? zr[i] : comp(cur[i], k + 1);
-            const float d_m = (c - comp(pv, k)) + (c - comp(next[i], k));
-            const float d_o = (c - comp(om, k)) + (c - comp(op, k));
-            const float d_z = (c - lft) + (c - rgt);
+            // (2c - lo) - hi per axis: one FFMA + one FADD; on a low edge lo := c makes the
+            // first term exactly c
+            const float d_m = fmaf(2.f, c, -comp(pv, k)) - comp(next[i], k);
+            const float d_o = fmaf(2.f, c, -comp(om, k)) - comp(op, k);
+            const float d_z = fmaf(2.f, c, -lft) - rgt;
             const float dtd = fmaf(d_z, a.iv_z, fmaf(d_o, a.iv_o, d_m * a.iv_m));
             float data = a.w_ident * c;
             if (KIND != SK_NONE) data = fmaf(mfac * comp(thin[i], k), comp(dat, k), data);
@@ -506,8 +511,17 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
           if (jaddr == lrm_end) jaddr = lrm_a;
         }
       }
-      __syncthreads();  // every warp is done with plane u - 1; lrz of plane u + 1 is complete
-      if (tid == 0 && iq <= last) issue_next();
+      if (u >= m0) goff += a.gs_m;
+      // Refill the ring every kRefill planes (every plane for the z-thick kernel, whose lrz
+      // double buffer needs the barrier anyway): after the barrier every warp is done with
+      // the planes up to u - 1, so that many slots are free again.
+      constexpr int kRefill = KIND == SK_THICK_Z ? 1 : 2;
+      if (++pend == kRefill || u == m1 - 1) {
+        __syncthreads();
+        if (tid == 0)
+          for (int k = 0; k < pend && iq <= last; ++k) issue_next();
+        pend = 0;
+      }
     }
   }
   double total_sum;
@@ -590,6 +604,7 @@ static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 
 
 int stream_mc_override = 0;  // test / tuning hook (plane-tiles per CTA), 0 = automatic
 int stream_rpt = 0;          // rows per thread: 0 automatic, 1 (8-row tiles), 2 (16-row tiles)
+int stream_pf = 0;           // extra prefetch slots of the ring on top of the default
 typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
@@ -679,7 +694,8 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   size_t smem = 0;
   for (;; rpt = 1) {
     const int to = NWARP * rpt;
-    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2);
+    // window [u-1, u+L] + prefetch + one slot of slack for the every-other-plane refill
+    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2) + (T.kind == SK_THICK_Z ? 0 : 1) + stream_pf;
     if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
     S.hz = hz;
     S.sz = TZ + 2 * hz;

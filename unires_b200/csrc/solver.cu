@@ -193,6 +193,82 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Residual / no-stop rule: x is not needed until the direction is rebuilt, so the sweep is
+// split to touch every vector once (40 instead of 44 bytes per voxel and iteration; the
+// per-element arithmetic and its order are unchanged, hence bitwise identical iterates):
+//   cg_update_r_kernel : r -= alpha Ap ; sum r*r                      (12 B/voxel)
+//   cg_update_xp_kernel: x += alpha p ; p = beta p + r                (20 B/voxel)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    cg_update_r_kernel(float *__restrict__ r, const float *__restrict__ Ap, size_t n,
+                       const double *alpha_ptr, const int *done, GridReduce gr, FinalizeArgs fin) {
+  __shared__ double s_red[kMaxWarps];
+  if (done && *done) return;
+  const float alpha = (float)(*alpha_ptr);
+  double part = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    const size_t n4 = n / 4;
+    float4 *r4 = reinterpret_cast<float4 *>(r);
+    const float4 *A4 = reinterpret_cast<const float4 *>(Ap);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 rv = r4[i];
+      const float4 av = A4[i];
+      rv.x = __fsub_rn(rv.x, __fmul_rn(alpha, av.x));
+      rv.y = __fsub_rn(rv.y, __fmul_rn(alpha, av.y));
+      rv.z = __fsub_rn(rv.z, __fmul_rn(alpha, av.z));
+      rv.w = __fsub_rn(rv.w, __fmul_rn(alpha, av.w));
+      r4[i] = rv;
+      part += (double)__fmul_rn(rv.x, rv.x) + (double)__fmul_rn(rv.y, rv.y) +
+              (double)__fmul_rn(rv.z, rv.z) + (double)__fmul_rn(rv.w, rv.w);
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float rv = __fsub_rn(r[i], __fmul_rn(alpha, Ap[i]));
+      r[i] = rv;
+      part += (double)__fmul_rn(rv, rv);
+    }
+  }
+  double total;
+  if (grid_sum(part, gr, s_red, &total) && threadIdx.x == 0) finalize(fin, total);
+}
+
+// Runs for iteration `iter` even when the stop test of that same iteration has just set
+// `done` (the x update of the last iteration must not be lost).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    cg_update_xp_kernel(float *__restrict__ x, float *__restrict__ p, const float *__restrict__ r,
+                        size_t n, const CgState *st, int iter) {
+  if (st->done && st->done_iter != iter) return;
+  const float alpha = (float)st->alpha, beta = (float)st->beta;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    const size_t n4 = n / 4;
+    float4 *x4 = reinterpret_cast<float4 *>(x), *p4 = reinterpret_cast<float4 *>(p);
+    const float4 *r4 = reinterpret_cast<const float4 *>(r);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 xv = x4[i], pv = p4[i];
+      const float4 rv = r4[i];
+      xv.x = __fadd_rn(xv.x, __fmul_rn(alpha, pv.x));
+      xv.y = __fadd_rn(xv.y, __fmul_rn(alpha, pv.y));
+      xv.z = __fadd_rn(xv.z, __fmul_rn(alpha, pv.z));
+      xv.w = __fadd_rn(xv.w, __fmul_rn(alpha, pv.w));
+      pv.x = __fadd_rn(__fmul_rn(beta, pv.x), rv.x);
+      pv.y = __fadd_rn(__fmul_rn(beta, pv.y), rv.y);
+      pv.z = __fadd_rn(__fmul_rn(beta, pv.z), rv.z);
+      pv.w = __fadd_rn(__fmul_rn(beta, pv.w), rv.w);
+      x4[i] = xv;
+      p4[i] = pv;
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float pv = p[i];
+      x[i] = __fadd_rn(x[i], __fmul_rn(alpha, pv));
+      p[i] = __fadd_rn(__fmul_rn(beta, pv), r[i]);
+    }
+  }
+}
+
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 static unsigned vec_blocks(size_t n) {
@@ -347,6 +423,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 // ---------------------------------------------------------------------------
 extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
+extern int stream_pf;           // lhs_stream.cu
 static int g_lhs_variant = 0;
 
 struct MatvecProfile {
@@ -452,6 +529,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_lhs_variant = value;
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
+  } else if (!strcmp(name, "stream_pf")) {
+    stream_pf = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {
     stream_rpt = (value == 1 || value == 2) ? value : 0;
   } else {
@@ -568,7 +647,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
       rc = launch_lhs(LHS_PLAIN, lhs, P, lw, A, opts->variant, st);
       if (rc) return rc;
     }
-    {  // x += alpha p ; r -= alpha Ap ; beta = rz'/rz
+    if (stop == UR_STOP_ENERGY) {  // x += alpha p ; r -= alpha Ap ; beta = rz'/rz
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
       if (vec)
         cg_update_xr_kernel<4><<<vblocks, 256, 0, st>>>(d_x, cw.r, cw.p, cw.Ap, n, &cw.st->alpha,
@@ -576,6 +655,18 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
       else
         cg_update_xr_kernel<1><<<vblocks, 256, 0, st>>>(d_x, cw.r, cw.p, cw.Ap, n, &cw.st->alpha,
                                                         done, gr, fin);
+      UR_LAUNCH_CHECK();
+    } else {  // r -= alpha Ap ; beta = rz'/rz   then   x += alpha p ; p = beta p + r
+      FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
+      if (vec) {
+        cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+        UR_LAUNCH_CHECK();
+        cg_update_xp_kernel<4><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
+      } else {
+        cg_update_r_kernel<1><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+        UR_LAUNCH_CHECK();
+        cg_update_xp_kernel<1><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
+      }
       UR_LAUNCH_CHECK();
     }
     if (stop == UR_STOP_ENERGY) {  // obj = 0.5 (A x - 2 b).x  fused with p = beta p + r
@@ -589,12 +680,6 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
       A.fin = FinalizeArgs{FIN_ENERGY, it, stop, tol, cw.st, nullptr};
       rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
       if (rc) return rc;
-    } else {
-      if (vec)
-        cg_update_p_kernel<4><<<vblocks, 256, 0, st>>>(cw.p, cw.r, n, &cw.st->beta, done);
-      else
-        cg_update_p_kernel<1><<<vblocks, 256, 0, st>>>(cw.p, cw.r, n, &cw.st->beta, done);
-      UR_LAUNCH_CHECK();
     }
   }
   return UR_OK;

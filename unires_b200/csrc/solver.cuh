@@ -11,6 +11,8 @@ struct CgState {
   double obj_min, obj_max;
   int n_iter;  // completed iterations
   int done;    // set on the device when |gain| < tolerance
+  int done_iter;  // iteration whose stop test set `done`
+  int pad_;
   double obj[UR_CG_MAX_ITER + 1];
 };
 
@@ -44,7 +46,10 @@ __device__ __forceinline__ void record_objective(CgState *st, int n, double o, d
   st->obj_min = mn;
   st->obj_max = mx;
   const double gain = (st->obj[n - 1] - o) / (mx - mn);
-  if (fabs(gain) < tol) st->done = 1;
+  if (fabs(gain) < tol) {
+    st->done = 1;
+    st->done_iter = n;
+  }
 }
 
 // ---------------------------------------------------------------------------
