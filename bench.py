@@ -7,7 +7,7 @@
 One *step* = one pass of the y-update of `_update_admm` (unires/_update.py:122-150) over one
 subject: for every channel build the right-hand side (sum tau At x - lam div(w - rho z)) and run
 the CG solve with a FIXED trip count (tolerance 0, SURVEY.md 8d "throughput mode": no stop test,
-44 N bytes per CG iteration).  Workload at N=1: BASELINE.json configs[1], "3-channel 1 mm
+36 N bytes per CG iteration: fused matvec 24 + residual update 12).  Workload at N=1: BASELINE.json configs[1], "3-channel 1 mm
 super-resolution, 256^3 recon grid" (synthetic BrainWeb-like phantom, 181x217x181 scanner FOV,
 each channel thick-sliced x4 along a different axis).  N>1: one independent subject per GPU
 (weak scaling, no data-path collective).  value = CG iterations of all ranks / max-over-ranks
@@ -150,16 +150,18 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         reset()  # restart from the same initial estimate (3 device copies, <1% of a step)
         y_update(sc.x, sc.y, z, w, rho, tmp, sett, vx, dim)
+    host_ms = (time.perf_counter() - t_host0) * 1e3  # host enqueue time (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.ur_launch_count() - l0
     import ctypes as C_
-    tot, cnt = C_.c_double(0), C_.c_int32(0)
-    _lib.check(_lib.lib.ur_profile_matvec_read(C_.byref(tot), C_.byref(cnt)))
+    tot, cnt, bpv = C_.c_double(0), C_.c_int32(0), C_.c_double(0)
+    _lib.check(_lib.lib.ur_profile_matvec_read(C_.byref(tot), C_.byref(cnt), C_.byref(bpv)))
     _lib.lib.ur_profile_matvec(0)
     clocks = sampler.result()
 
@@ -201,7 +203,10 @@ def run_ours(args):
     total_its = world * its_per_step * args.steps
     peak, peak_src = peaks()
     mv_ms = tot.value / max(cnt.value, 1)
-    achieved = 8.0 * n_vox / (mv_ms * 1e-3) / 1e9 if cnt.value else None
+    # algorithmic bytes per voxel of the average matvec launch: 8 (read p, write Ap) for a plain
+    # launch, 24 when the direction and x updates are fused in (read p, r, x; write p, Ap, x)
+    mv_bpv = bpv.value / max(cnt.value, 1)
+    achieved = mv_bpv * n_vox / (mv_ms * 1e-3) / 1e9 if cnt.value else None
     line = {
         'metric': METRIC, 'value': total_its / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
@@ -217,12 +222,15 @@ def run_ours(args):
         'e2e': {'value': total_its / (ms_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches),
+        'host_enqueue_ms_per_step': host_ms / args.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'lhs matvec (A p = sum tau AtA p + rho lam^2 DtD p, '
-                                               'fused p.Ap epilogue)',
+        'roofline': {'bound': 'hbm', 'kernel': 'lhs_stream_kernel: CG matvec A p = sum tau AtA p + rho lam^2 '
+                                               'DtD p with p = beta p + r, x += alpha p and p.Ap '
+                                               'fused in (first iteration of a solve: plain matvec)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None, 'traffic': None,
-                     'algorithmic_bytes_per_launch': 8 * n_vox,
+                     'algorithmic_bytes_per_launch': mv_bpv * n_vox,
+                     'algorithmic_bytes_per_voxel': mv_bpv,
                      'avg_launch_ms': mv_ms, 'launches_timed': cnt.value, 'peak_source': peak_src},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -51,10 +51,13 @@ int ur_device_info(int *sm_count, int *cc_major, int *cc_minor);
 uint64_t ur_launch_count(void);
 /* Instrumentation for bench.py's roofline: while enabled, every CG matvec
  * launch (the lhs kernel producing A p) is bracketed by CUDA events on its own
- * stream.  ur_profile_matvec_read synchronises, returns the summed duration
- * and the number of launches since the last read, and resets.            */
+ * stream.  ur_profile_matvec_read synchronises, returns the summed duration,
+ * the number of launches since the last read and the sum over those launches
+ * of their algorithmic HBM bytes per voxel (8 for A p; 24 when the direction
+ * and x updates are fused into the matvec), and resets.                   */
 int ur_profile_matvec(int enable);
-int ur_profile_matvec_read(double *total_ms, int32_t *count);
+int ur_profile_matvec_read(double *total_ms, int32_t *count,
+                           double *bytes_per_voxel_sum);
 /* Tuning / test knobs (process-wide).  "lhs_variant": 0 automatic, 1 force the
  * direct (non-TMA) lhs kernel; "stream_mc": planes per CTA chunk of the TMA
  * streaming kernel (0 automatic); "stream_rpt": rows per thread of that

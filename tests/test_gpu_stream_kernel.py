@@ -118,3 +118,55 @@ def test_cg_stream_vs_direct(cuda, stop):
     # the two kernels round D'D differently; sqrt(r.r) of the recursively updated residual
     # amplifies that towards convergence
     assert all(abs(a - b_) <= 1e-4 * abs(b_) + 1e-12 for a, b_ in zip(res[0][2], res[1][2]))
+
+
+FUSE_CASES = [
+    # dim_y, fov, thick axis (None = no projection), factor, scl, rpt
+    ((24, 28, 132), (20, 22, 120), 1, 4, 0.1, 0),
+    ((24, 28, 132), (20, 22, 120), 0, 4, 0.0, 2),
+    ((21, 19, 140), (17, 15, 128), 2, 4, 0.1, 0),
+    ((21, 35, 136), None, 2, 2, 0.0, 2),
+    ((18, 34, 128), None, None, 1, 0.0, 0),
+    ((18, 34, 128), None, None, 1, 0.0, 1),
+]
+
+
+@pytest.mark.parametrize('case', FUSE_CASES)
+@pytest.mark.parametrize('stop,tol', [('residual', 1e-3), ('max_gain', 0.0)])
+def test_cg_fused_direction_update(cuda, case, stop, tol):
+    """Matvec with p = beta p + r and x += alpha p folded in (two sweeps per iteration) against
+    the unfused three-sweep iteration and the oracle: same trip count, same iterate."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim, struct
+    dim_y, fov, axis, factor, scl, rpt = case
+    g = torch.Generator().manual_seed(11)
+    b = torch.rand(dim_y, generator=g) * 0.1
+    x0 = torch.rand(dim_y, generator=g)
+    if axis is None:
+        obs_o = P.Observation(torch.zeros(dim_y), torch.eye(4), tau=0.02, po=None)
+        rec_o = P.Recon(torch.zeros(dim_y), torch.eye(4), lam=0.3)
+        op = _project.LhsOperator([struct._input(tau=0.02)], struct._output(dim=dim_y, lam=0.3),
+                                  do=False, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+        lhs_o = lambda v: P.proj('AtA', v, [obs_o], rec_o, do=False, rho=1.3, vx_y=torch.ones(3))
+    else:
+        obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
+        op = _project.LhsOperator([obs_g], rec_g, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+        lhs_o = lambda v: P.proj('AtA', v, [obs_o], rec_o, rho=1.3, vx_y=torch.ones(3))
+    xo = x0.clone()
+    OO.cg(A=lhs_o, b=b, x=xo, max_iter=12, tolerance=tol, stop=stop)
+    res = {}
+    try:
+        _tune('stream_rpt', rpt)
+        _tune('stream_mc', 13)
+        for fuse in (0, 1):
+            _tune('cg_fuse', fuse)
+            x = x0.clone().to(cuda)
+            optim.cg(A=op, b=b.to(cuda), x=x, max_iter=12, tolerance=tol, stop=stop)
+            res[fuse] = (x, optim.cg.last.n_iter)
+    finally:
+        _tune('cg_fuse', 1)
+        _tune('stream_rpt', 0)
+        _tune('stream_mc', 0)
+    assert res[0][1] == res[1][1] == OO.cg.last_n_iter
+    assert U.rel_l2(res[1][0], res[0][0]) < 1e-6
+    assert U.rel_l2(res[1][0], xo) < U.REL_TOL

@@ -6,6 +6,7 @@ import fails loudly, and every operator refuses non-CUDA tensors.
 import ctypes as C
 import os
 import re
+import weakref
 
 import torch
 
@@ -79,7 +80,8 @@ _SIGNATURES = {
     'ur_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'ur_launch_count': (C.c_uint64, []),
     'ur_profile_matvec': (C.c_int, [C.c_int]),
-    'ur_profile_matvec_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    'ur_profile_matvec_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_double)]),
     'ur_tune': (C.c_int, [C.c_char_p, C.c_int]),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
@@ -174,6 +176,37 @@ def require_cuda_f32(t, name='tensor'):
     if t.dtype != torch.float32:
         raise TypeError('unires_b200: %s must be float32, got %s' % (name, t.dtype))
     return t if t.is_contiguous() else t.contiguous()
+
+
+_host_cache = {}
+
+
+def host_values(v):
+    """Python floats of a scalar / small tensor WITHOUT a device sync on repeat calls.
+
+    UniRes keeps tau, lam, rho, scl and the affine matrices as (often CUDA) tensors; reading
+    them with float() / .tolist() synchronises the stream, which would serialise host and
+    device in the ADMM loop.  Values are cached per tensor object and in-place version."""
+    if isinstance(v, torch.Tensor):
+        if not v.is_cuda:
+            return v.detach().reshape(-1).to(torch.float64).tolist()
+        # keyed by object id, validated by a weak reference (ids and device addresses are
+        # recycled after garbage collection) and by the in-place version counter
+        hit = _host_cache.get(id(v))
+        if hit is not None and hit[0]() is v and hit[1] == v._version:
+            return hit[2]
+        if len(_host_cache) > 4096:
+            _host_cache.clear()
+        vals = v.detach().reshape(-1).to('cpu', torch.float64).tolist()
+        _host_cache[id(v)] = (weakref.ref(v), v._version, vals)
+        return vals
+    if isinstance(v, (int, float)):
+        return [float(v)]
+    return [float(a) for a in v]
+
+
+def host_scalar(v):
+    return host_values(v)[0]
 
 
 _ws_cache = {}

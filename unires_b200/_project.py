@@ -95,6 +95,8 @@ def proj_struct(po, method):
                                    po.dim_thick)
     cache = po.__dict__.setdefault('_c_cache', {})
     hit = cache.get(method)
+    # the cache entry keeps the tensors it was built from alive, so an equal (id, version)
+    # key can only mean the very same, unmodified tensors
     if hit is not None and hit[0] == key:
         return hit[1]
     cpu = lambda t: torch.as_tensor(t).detach().to('cpu', _F64)
@@ -115,9 +117,9 @@ def proj_struct(po, method):
             s.ker[a][t] = v
     for k, v in enumerate(vox[:3, :].reshape(-1).tolist()):
         s.mat[k] = v
-    s.scl = float(po.scl) if po.scl is not None else 0.0
-    s.dim_thick = int(po.dim_thick) if po.dim_thick is not None else 0
-    cache[method] = (key, s)
+    s.scl = _lib.host_scalar(po.scl) if po.scl is not None else 0.0
+    s.dim_thick = int(_lib.host_scalar(po.dim_thick)) if po.dim_thick is not None else 0
+    cache[method] = (key, s, (po.mat_y, src_mat, po.rigid, po.smo_ker, po.scl, po.dim_thick))
     return s
 
 
@@ -176,12 +178,8 @@ def _DtD(dat, vx_y, bound='zero', diff='forward'):
 
 
 def _floats(v, n=None):
-    if isinstance(v, torch.Tensor):
-        v = v.detach().to('cpu', torch.float32).flatten().tolist()
-    elif isinstance(v, (int, float)):
-        v = [float(v)]
-    else:
-        v = [float(a) for a in v]
+    """Host floats of a scalar / small tensor (float32 values; cached: no repeated sync)."""
+    v = [float(np.float32(a)) for a in _lib.host_values(v)]
     if n is not None and len(v) == 1:
         v = v * n
     return v
@@ -189,7 +187,7 @@ def _floats(v, n=None):
 
 def _f32(v):
     """Python/torch scalar -> numpy float32 (value as the reference holds it)."""
-    return np.float32(float(v))
+    return np.float32(_lib.host_scalar(v))
 
 
 # ---------------------------------------------------------------------------
@@ -221,7 +219,7 @@ class LhsOperator:
         s.do_proj = 1 if do else 0
         s.n_obs = len(x)
         for n, obs in enumerate(x):
-            s.tau[n] = float(obs.tau)
+            s.tau[n] = _lib.host_scalar(obs.tau)
             if do:
                 C.memmove(C.byref(s.obs[n]), C.byref(proj_struct(obs.po, method)),
                           C.sizeof(_lib.ur_proj))

@@ -16,6 +16,7 @@ cross NVLink.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -23,6 +24,8 @@ from ._lib import lib, check, ptr, i3, f3, stream, require_cuda_f32
 from ._project import LhsOperator, _proj, _floats, proj_struct
 from .optim import cg, cg_fused, stop_rule
 from .spatial import voxel_size
+
+_hs = _lib.host_scalar  # host float of a (possibly CUDA) scalar tensor, cached: no repeated sync
 
 
 def _admm_aux(y, sett):
@@ -42,7 +45,7 @@ def _step_size(x, y, sett, verbose=False):
     rho = 1.0 if _has_ct(x) else sett.rho
     if rho is not None:
         return torch.tensor(rho, device=sett.device, dtype=torch.float32)
-    lam = torch.tensor([float(yc.lam) for yc in y], dtype=torch.float32, device=sett.device)
+    lam = torch.tensor([_hs(yc.lam) for yc in y], dtype=torch.float32, device=sett.device)
     tau = torch.tensor([float(o.tau) for xc in x for o in xc], dtype=torch.float32,
                        device=sett.device)
     return sett.rho_scl * torch.sqrt(torch.mean(tau)) / torch.mean(lam)
@@ -57,7 +60,11 @@ def _ptr_array(tensors):
 
 def _geometry(y):
     dim = tuple(y[0].dim) if y[0].dim is not None else tuple(y[0].dat.shape)
-    vx = _floats(voxel_size(y[0].mat).float(), 3)
+    # voxel_size(y[0].mat).float() (unires/_update.py:111) from the cached host copy of mat
+    m = _lib.host_values(y[0].mat)
+    n = int(round(len(m) ** 0.5))
+    vx = [float(np.float32(sum(m[i * n + a] ** 2 for i in range(n - 1)) ** 0.5))
+          for a in range(n - 1)]
     return dim, vx
 
 
@@ -75,10 +82,10 @@ def _nll_terms(x, y, sett, out, prior_field=None, accumulate_prior=False):
             dat = require_cuda_f32(obs.dat, 'x.dat')
             Ay = _proj('A', y[c].dat, x[c], y[c], n=n, method=sett.method, do=sett.do_proj,
                        bound=sett.bound, interpolation=sett.interpolation)
-            check(lib.ur_nll_data(ptr(dat), ptr(Ay), dat.numel(), float(obs.tau),
+            check(lib.ur_nll_data(ptr(dat), ptr(Ay), dat.numel(), _hs(obs.tau),
                                   ptr(out[1:2]), 1, stream()))
     ys = [require_cuda_f32(yc.dat, 'y.dat') for yc in y]
-    lam = _lib.farr([float(yc.lam) for yc in y])
+    lam = _lib.farr([_hs(yc.lam) for yc in y])
     field = prior_field
     if field is None:
         field = _lib.workspace(4 * n_vox, ys[0].device, 'prior').view(torch.float32)[:n_vox]
@@ -108,14 +115,14 @@ def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
     for n, obs in enumerate(xc):
         dat = require_cuda_f32(obs.dat, 'x.dat')
         if not sett.do_proj:
-            check(lib.ur_axpy(ptr(tmp), ptr(dat), float(obs.tau), n_vox, stream()))
+            check(lib.ur_axpy(ptr(tmp), ptr(dat), _hs(obs.tau), n_vox, stream()))
             continue
         s = proj_struct(obs.po, sett.method)
         ws = _lib.workspace(lib.ur_proj_workspace_bytes(C.byref(s)), tmp.device, 'proj')
         check(lib.ur_proj_accumulate(_lib.UR_OP_AT, C.byref(s), ptr(dat), ptr(tmp),
-                                     float(obs.tau), ptr(ws), ws.numel(), stream()))
-    check(lib.ur_admm_rhs(ptr(tmp), ptr(w_c), ptr(z_c), i3(dim), f3(vx), float(yc.lam),
-                          float(rho), stream()))
+                                     _hs(obs.tau), ptr(ws), ws.numel(), stream()))
+    check(lib.ur_admm_rhs(ptr(tmp), ptr(w_c), ptr(z_c), i3(dim), f3(vx), _hs(yc.lam),
+                          _hs(rho), stream()))
 
 
 def _solve_y(x, y, z, w, rho, tmp, sett, dim, vx):
@@ -142,7 +149,7 @@ def _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett):
     z = require_cuda_f32(z, 'z')
     w = require_cuda_f32(w, 'w')
     tmp = require_cuda_f32(tmp, 'tmp')
-    rho_f = float(rho)
+    rho_f = _hs(rho)
     _update_admm.last_cg = _solve_y(x, y, z, w, rho_f, tmp, sett, dim, vx)
     if sett.tolerance > 0:
         row = torch.zeros(3, dtype=torch.float64, device=tmp.device)
@@ -154,7 +161,7 @@ def _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett):
     if len(ys) > _lib.UR_MAX_CHANNELS:
         raise NotImplementedError('more than %d channels' % _lib.UR_MAX_CHANNELS)
     check(lib.ur_jtv_prox(_ptr_array(ys), ptr(z), ptr(w), ptr(tmp), len(ys),
-                          _lib.farr([float(yc.lam) for yc in y]), i3(dim), f3(vx), rho_f,
+                          _lib.farr([_hs(yc.lam) for yc in y]), i3(dim), f3(vx), rho_f,
                           float(sett.alpha), stream()))
     return y, z, w, tmp, obj
 
@@ -174,10 +181,10 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     from . import parallel
     dim, vx = _geometry(y)
     n_vox = dim[0] * dim[1] * dim[2]
-    rho_f = float(rho)
+    rho_f = _hs(rho)
     _update_admm.last_cg = _solve_y(x, y, z, w, rho_f, tmp, sett, dim, vx)
     ys = [yc.dat for yc in y]
-    lam = _lib.farr([float(yc.lam) for yc in y])
+    lam = _lib.farr([_hs(yc.lam) for yc in y])
     field = torch.empty(dim, dtype=torch.float32, device=tmp.device)
     if sett.tolerance > 0:
         row = torch.zeros(3, dtype=torch.float64, device=tmp.device)

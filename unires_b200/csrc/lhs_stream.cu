@@ -69,6 +69,9 @@ struct StreamArgs {
   float *r;
   float *p;
   int update_p;
+  const float *rres;  // COMBINE: residual r
+  float *p_out;       // COMBINE: new direction p = beta p_old + r
+  float *xup;         // COMBINE: x += alpha_prev p_old
   const int *done;
   GridReduce gr;
   FinalizeArgs fin;
@@ -225,6 +228,8 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 
     int iq = first;  // next plane to issue
     auto issue_next = [&]() {
+      // COMBINE rewrote the slot with generic-proxy stores: order them before the TMA write
+      if (MODE == LHS_COMBINE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx_a(ip.ba, plane_bytes);
       if (a.march_y)
         tma_load_3d_a(ip.pa, &tmap, ip.ba, z0 - a.hz, iq, o0 - 1);
@@ -301,11 +306,107 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       }
     };
 
-    // ---- prime the pipeline: planes first .. u_begin + L - 1 ----
+    // ---- COMBINE: p = beta p_old + r on the whole staged tile (own quads + halo) ----
+    // Every thread owns its RPT interior quads and (threads < halo_n) one halo quad of the
+    // tile.  r (and x for the delayed x += alpha p_old) come straight from global memory,
+    // software-pipelined one plane ahead; p_old is what the TMA brought into the ring slot
+    // and is overwritten in place by the new direction.
+    float beta_c = 0.f, alpha_c = 0.f;
+    uint32_t h_off = 0;
+    size_t h_g = 0;
+    bool h_has = false, h_in = false;
+    size_t g_own = 0;
+    if (MODE == LHS_COMBINE) {
+      beta_c = (float)a.fin.st->beta;
+      alpha_c = (float)a.fin.st->alpha;
+      const int sz4 = a.sz >> 2, hz4 = a.hz >> 2;
+      const int halo_n = 2 * sz4 + TO * 2 * hz4;
+      h_has = tid < halo_n;
+      int h_row = 0, h_c4 = 0;
+      if (tid < sz4) {
+        h_row = 0;
+        h_c4 = tid;
+      } else if (tid < 2 * sz4) {
+        h_row = TO + 1;
+        h_c4 = tid - sz4;
+      } else {
+        const int k = tid - 2 * sz4;
+        h_row = 1 + k / (2 * hz4);
+        const int s = k - (h_row - 1) * (2 * hz4);
+        h_c4 = s < hz4 ? s : sz4 - 2 * hz4 + s;
+      }
+      h_off = (uint32_t)(h_row * a.sz + 4 * h_c4) * 4u;
+      const int h_o = o0 - 1 + h_row, h_z = z0 - a.hz + 4 * h_c4;
+      h_in = h_has && h_o >= 0 && h_o < a.no && h_z >= 0 && h_z < a.nz;
+      h_g = h_in ? (size_t)h_o * a.gs_o + h_z : 0;
+      g_own = (size_t)o_first * a.gs_o + z;
+    }
+    float4 cr_own[RPT], cx_own[RPT], cr_h;  // prefetched r / x quads of the plane to combine
+    auto fetch_rx = [&](int q) {
+      const bool q_in = q >= 0 && q < a.nm;
+      const bool q_own = q >= m0 && q < m1;
+      const size_t gq = (size_t)(q_in ? q : 0) * a.gs_m;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const size_t gi = gq + g_own + (size_t)i * a.gs_o;
+        cr_own[i] = (q_in && active[i]) ? *reinterpret_cast<const float4 *>(a.rres + gi)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        cx_own[i] = (q_own && active[i]) ? *reinterpret_cast<const float4 *>(a.xup + gi)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cr_h = (q_in && h_in) ? *reinterpret_cast<const float4 *>(a.rres + gq + h_g)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto combine = [&](int q, uint32_t aq) {
+      const bool q_own = q >= m0 && q < m1;
+      const size_t gq = (size_t)(q > 0 ? q : 0) * a.gs_m;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const uint32_t sa = aq + own_b + i * sz_b;
+        const float4 po = lds128(sa);
+        float4 pn;  // torch: p *= beta; p += r  (two roundings)
+        pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), cr_own[i].x);
+        pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), cr_own[i].y);
+        pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), cr_own[i].z);
+        pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), cr_own[i].w);
+        sts128(sa, pn);
+        if (q_own && active[i]) {
+          const size_t gi = gq + g_own + (size_t)i * a.gs_o;
+          *reinterpret_cast<float4 *>(a.p_out + gi) = pn;
+          float4 xn;  // the previous iteration's x += alpha p, done now that p_old is at hand
+          xn.x = __fadd_rn(cx_own[i].x, __fmul_rn(alpha_c, po.x));
+          xn.y = __fadd_rn(cx_own[i].y, __fmul_rn(alpha_c, po.y));
+          xn.z = __fadd_rn(cx_own[i].z, __fmul_rn(alpha_c, po.z));
+          xn.w = __fadd_rn(cx_own[i].w, __fmul_rn(alpha_c, po.w));
+          *reinterpret_cast<float4 *>(a.xup + gi) = xn;
+        }
+      }
+      if (h_has) {
+        const float4 po = lds128(aq + h_off);
+        float4 pn;
+        pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), cr_h.x);
+        pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), cr_h.y);
+        pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), cr_h.z);
+        pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), cr_h.w);
+        sts128(aq + h_off, pn);
+      }
+    };
+
+    // ---- prime the pipeline: planes first .. u_begin + L - 1 (COMBINE: one more, each
+    //      combined as it lands) ----
     const uint32_t a_first = wp.pa;
-    for (int n = 0; n < a.L + 1; ++n) {
+    for (int n = 0; n < a.L + 1 + (MODE == LHS_COMBINE ? 1 : 0); ++n) {
+      const uint32_t aq = wp.pa;
       mbar_wait_a(wp.ba, wp.par);
       wp.inc(R);
+      if (MODE == LHS_COMBINE) {
+        fetch_rx(first + n);
+        combine(first + n, aq);
+      }
+    }
+    if (MODE == LHS_COMBINE) {
+      __syncthreads();  // halo quads of the primed planes were written by other threads
+      fetch_rx(u_begin + a.L + 1);
     }
     uint32_t au = a_first + R.plane_b;  // plane u
     if (au == R.end) au = R.base;
@@ -334,8 +435,21 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     int pend = 0;  // planes consumed since the ring was last refilled
 
     for (int u = u_begin; u < m1; ++u) {
-      mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
-      wp.inc(R);
+      if (MODE == LHS_COMBINE) {
+        // plane u + L + 1 lands now and is combined one iteration before its first use (the
+        // barrier at the end of this iteration publishes the halo quads)
+        const int qc = u + a.L + 1;
+        if (qc <= last) {
+          const uint32_t aq = wp.pa;
+          mbar_wait_a(wp.ba, wp.par);
+          wp.inc(R);
+          combine(qc, aq);
+          if (qc + 1 <= last) fetch_rx(qc + 1);
+        }
+      } else {
+        mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
+        wp.inc(R);
+      }
       uint32_t an = au + R.plane_b;  // plane u + 1
       if (an == R.end) an = R.base;
       float4 next[RPT];
@@ -397,7 +511,8 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
           if (!active[i]) continue;
           const size_t gi = goff + (size_t)i * a.gs_o;
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
-          if (MODE != LHS_PLAIN) bq = *reinterpret_cast<const float4 *>(a.b + gi);
+          if (MODE == LHS_RESID || MODE == LHS_ENERGY)
+            bq = *reinterpret_cast<const float4 *>(a.b + gi);
           if (MODE == LHS_ENERGY && a.update_p) {
             rq = *reinterpret_cast<const float4 *>(a.r + gi);
             pq = *reinterpret_cast<const float4 *>(a.p + gi);
@@ -466,7 +581,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             if (KIND != SK_NONE) data = fmaf(mfac * comp(thin[i], k), comp(dat, k), data);
             val[k] = fmaf(a.rl2, dtd, data);
           }
-          if (MODE == LHS_PLAIN) {
+          if (MODE == LHS_PLAIN || MODE == LHS_COMBINE) {
             *reinterpret_cast<float4 *>(a.out + gi) = make_float4(val[0], val[1], val[2], val[3]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(comp(cur[i], k), val[k]);
@@ -480,7 +595,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             *reinterpret_cast<float4 *>(a.p + gi) = rr;
             part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
                     (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
-          } else {
+          } else if (MODE == LHS_ENERGY) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * comp(bq, k)), comp(cur[i], k));
@@ -515,7 +630,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       // Refill the ring every kRefill planes (every plane for the z-thick kernel, whose lrz
       // double buffer needs the barrier anyway): after the barrier every warp is done with
       // the planes up to u - 1, so that many slots are free again.
-      constexpr int kRefill = KIND == SK_THICK_Z ? 1 : 2;
+      constexpr int kRefill = (KIND == SK_THICK_Z || MODE == LHS_COMBINE) ? 1 : 2;
       if (++pend == kRefill || u == m1 - 1) {
         __syncthreads();
         if (tid == 0)
@@ -607,11 +722,14 @@ int stream_rpt = 0;          // rows per thread: 0 automatic, 1 (8-row tiles), 2
 int stream_pf = 0;           // extra prefetch slots of the ring on top of the default
 typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 
+// variant < 0: dry run (eligibility check only, nothing is launched)
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
-  (void)variant;
+  const bool dry_run = variant < 0;
   if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
   if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
   if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
+  if (!a16(A.rres) || !a16(A.p_out) || !a16(A.xup)) return UR_ERR_UNSUPPORTED;
+  const bool combine = mode == LHS_COMBINE;
 
   StreamArgs S;
   memset(&S, 0, sizeof(S));
@@ -695,7 +813,10 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   for (;; rpt = 1) {
     const int to = NWARP * rpt;
     // window [u-1, u+L] + prefetch + one slot of slack for the every-other-plane refill
-    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2) + (T.kind == SK_THICK_Z ? 0 : 1) + stream_pf;
+    // (COMBINE looks one plane further ahead and refills every plane)
+    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2) + stream_pf +
+           (combine ? 1 : (T.kind == SK_THICK_Z ? 0 : 1));
+    if (combine && 2 * ((TZ + 2 * hz) / 4) + to * 2 * (hz / 4) > NTHR) return UR_ERR_UNSUPPORTED;
     if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
     S.hz = hz;
     S.sz = TZ + 2 * hz;
@@ -716,12 +837,14 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
         {lhs_stream_kernel<M, SK_THICK_M, 1>, lhs_stream_kernel<M, SK_THICK_M, 2>},         \
         {lhs_stream_kernel<M, SK_THICK_Z, 1>, lhs_stream_kernel<M, SK_THICK_Z, 2>},         \
   }
-  static StreamKernel table[3][4][2] = {UR_SK_ROW(LHS_PLAIN), UR_SK_ROW(LHS_RESID),
-                                        UR_SK_ROW(LHS_ENERGY)};
+  static StreamKernel table[4][4][2] = {UR_SK_ROW(LHS_PLAIN), UR_SK_ROW(LHS_RESID),
+                                        UR_SK_ROW(LHS_ENERGY), UR_SK_ROW(LHS_COMBINE)};
 #undef UR_SK_ROW
+  if (!encode_fn()) return UR_ERR_UNSUPPORTED;  // no cuTensorMapEncodeTiled: no TMA path
+  if (dry_run) return UR_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
       for (int k = 0; k < 4; ++k)
         for (int j = 0; j < 2; ++j)
           UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)table[i][k][j],
@@ -729,7 +852,7 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
                                              200 * 1024));
     attr_set = true;
   }
-  const int mi = mode == LHS_PLAIN ? 0 : (mode == LHS_RESID ? 1 : 2);
+  const int mi = mode == LHS_PLAIN ? 0 : (mode == LHS_RESID ? 1 : (mode == LHS_ENERGY ? 2 : 3));
   StreamKernel kernel = table[mi][T.kind][rpt - 1];
   // One wave of equally loaded CTAs: the (column, plane) tiles are cut into contiguous
   // ranges, one per resident CTA slot (occupancy x SM count).
@@ -738,9 +861,22 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   S.ncol = (int)(gx * gy);
   const long long total = (long long)S.ncol * S.nm;
   int resident = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, (const void *)kernel,
-                                                                 NTHR, smem);
-  if (oe != cudaSuccess || resident < 1) resident = 1;
+  {
+    // the occupancy query costs several microseconds of host time: remember the answer
+    static std::unordered_map<size_t, int> occ_cache;
+    static std::mutex occ_mu;
+    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull);
+    std::lock_guard<std::mutex> lock(occ_mu);
+    auto it = occ_cache.find(key);
+    if (it != occ_cache.end()) {
+      resident = it->second;
+    } else {
+      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &resident, (const void *)kernel, NTHR, smem);
+      if (oe != cudaSuccess || resident < 1) resident = 1;
+      occ_cache[key] = resident;
+    }
+  }
   const long long slots = (long long)resident * sm_count();
   const long long q_min = 4 * (S.B + S.L + 1);  // keep the warm-up planes a small fraction
   long long q = (total + slots - 1) / slots;
@@ -760,6 +896,9 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   S.r = A.r;
   S.p = A.p;
   S.update_p = A.update_p;
+  S.rres = A.rres;
+  S.p_out = A.p_out;
+  S.xup = A.xup;
   S.done = A.done;
   S.gr = A.gr;
   S.fin = A.fin;

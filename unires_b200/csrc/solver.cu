@@ -269,6 +269,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fused direction update: x lags by one iteration; complete it with the last alpha and the
+// direction buffer the device state points at (valid after an early stop as well).
+__global__ void __launch_bounds__(256)
+    cg_final_x_kernel(float *__restrict__ x, const float *__restrict__ p0,
+                      const float *__restrict__ p1, size_t n, const CgState *st) {
+  const float alpha = (float)st->alpha;
+  const float4 *p4 = reinterpret_cast<const float4 *>(st->p_cur ? p1 : p0);
+  float4 *x4 = reinterpret_cast<float4 *>(x);
+  const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 xv = x4[i];
+    const float4 pv = p4[i];
+    xv.x = __fadd_rn(xv.x, __fmul_rn(alpha, pv.x));
+    xv.y = __fadd_rn(xv.y, __fmul_rn(alpha, pv.y));
+    xv.z = __fadd_rn(xv.z, __fmul_rn(alpha, pv.z));
+    xv.w = __fadd_rn(xv.w, __fmul_rn(alpha, pv.w));
+    x4[i] = xv;
+  }
+}
+
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 static unsigned vec_blocks(size_t n) {
@@ -425,6 +445,7 @@ extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
 static int g_lhs_variant = 0;
+static int g_cg_fuse = 1;  // fold the direction / x updates into the matvec when possible
 
 struct MatvecProfile {
   bool on = false;
@@ -432,6 +453,7 @@ struct MatvecProfile {
   cudaEvent_t ev[2 * kCap];
   int created = 0;
   int used = 0;
+  double bytes_per_voxel = 0.0;  // summed algorithmic bytes/voxel of the recorded launches
 };
 static MatvecProfile g_prof;
 
@@ -461,18 +483,23 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
   }
   A.gr = GridReduce{w.partials, w.counter};
-  cudaEvent_t e0 = mode == LHS_PLAIN ? prof_event(0) : nullptr;
+  const bool is_matvec = mode == LHS_PLAIN || mode == LHS_COMBINE;
+  cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
   cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
   if (e0) cudaEventRecord(e0, st);
   // variant 0 = automatic (TMA streaming kernel when it applies), 1 = force the direct kernel
   if (variant == 0) variant = g_lhs_variant;
-  if (variant != 1) {
-    const int rc = lhs_stream_launch(mode, A, variant, st);
-    if (rc != UR_ERR_UNSUPPORTED) {
+  if (variant != 1 || mode == LHS_COMBINE) {
+    const int rc = lhs_stream_launch(mode, A, variant == 1 ? 0 : variant, st);
+    if (rc != UR_ERR_UNSUPPORTED || mode == LHS_COMBINE) {
       if (e1 && rc == UR_OK) {
         cudaEventRecord(e1, st);
         ++g_prof.used;
+        // algorithmic HBM bytes per voxel of this launch: read v, write A v (8); the fused
+        // direction update adds read r, x and write p, x (16)
+        g_prof.bytes_per_voxel += mode == LHS_COMBINE ? 24.0 : 8.0;
       }
+      if (rc == UR_ERR_UNSUPPORTED) set_error("fused direction update: streaming kernel n/a");
       return rc;
     }
   }
@@ -490,16 +517,18 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   if (e1) {
     cudaEventRecord(e1, st);
     ++g_prof.used;
+    g_prof.bytes_per_voxel += 8.0;
   }
   UR_LAUNCH_CHECK();
   return UR_OK;
 }
 
-// CG workspace: [CgState | lhs ws | r | p | Ap]
+// CG workspace: [CgState | lhs ws | r | p | Ap | p2]   (p2: second direction buffer of the
+// fused direction update, which cannot run in place because neighbouring CTAs re-read halos)
 struct CgWs {
   CgState *st;
   void *lhs;
-  float *r, *p, *Ap;
+  float *r, *p, *Ap, *p2;
 };
 
 static size_t cg_state_bytes() { return align_up(sizeof(CgState)); }
@@ -516,6 +545,8 @@ static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   w.p = (float *)c;
   c += vol_bytes(lhs);
   w.Ap = (float *)c;
+  c += vol_bytes(lhs);
+  w.p2 = (float *)c;
   return w;
 }
 
@@ -529,6 +560,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_lhs_variant = value;
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
+  } else if (!strcmp(name, "cg_fuse")) {
+    g_cg_fuse = value != 0;
   } else if (!strcmp(name, "stream_pf")) {
     stream_pf = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {
@@ -543,10 +576,12 @@ extern "C" int ur_tune(const char *name, int value) {
 extern "C" int ur_profile_matvec(int enable) {
   g_prof.on = enable != 0;
   g_prof.used = 0;
+  g_prof.bytes_per_voxel = 0.0;
   return UR_OK;
 }
 
-extern "C" int ur_profile_matvec_read(double *total_ms, int32_t *count) {
+extern "C" int ur_profile_matvec_read(double *total_ms, int32_t *count,
+                                      double *bytes_per_voxel_sum) {
   UR_CUDA_CHECK(cudaDeviceSynchronize());
   double tot = 0.0;
   for (int i = 0; i < g_prof.used; ++i) {
@@ -556,7 +591,9 @@ extern "C" int ur_profile_matvec_read(double *total_ms, int32_t *count) {
   }
   if (total_ms) *total_ms = tot;
   if (count) *count = g_prof.used;
+  if (bytes_per_voxel_sum) *bytes_per_voxel_sum = g_prof.bytes_per_voxel;
   g_prof.used = 0;
+  g_prof.bytes_per_voxel = 0.0;
   return UR_OK;
 }
 
@@ -586,7 +623,7 @@ extern "C" int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, d
 extern "C" size_t ur_cg_workspace_bytes(const ur_lhs *lhs) {
   LhsPlan P;
   if (make_plan(lhs, &P)) return 0;
-  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + 3 * vol_bytes(lhs);
+  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + 4 * vol_bytes(lhs);
 }
 
 extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_ws,
@@ -637,15 +674,51 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
     if (rc) return rc;
   }
+  // Residual / no-stop rule with the streaming kernel available: two sweeps per iteration,
+  //   [matvec with p = beta p_old + r and x += alpha_prev p_old folded in]  (24 B/voxel)
+  //   [r -= alpha Ap ; r.r]                                                  (12 B/voxel)
+  // The direction ping-pongs between two buffers; x lags one iteration and is completed by
+  // a final x += alpha p after the loop (which also runs after a device-side early stop).
+  bool fuse = false;
+  if (stop != UR_STOP_ENERGY && g_cg_fuse && opts->variant != 1 && g_lhs_variant != 1 && vec &&
+      aligned16(cw.p2) && P.n_general == 0) {
+    LhsArgs A = P.args;
+    A.v = cw.p;
+    A.out = cw.Ap;
+    A.rres = cw.r;
+    A.p_out = cw.p2;
+    A.xup = d_x;
+    fuse = lhs_stream_launch(LHS_COMBINE, A, -1, st) == UR_OK;
+  }
+  float *pbuf[2] = {cw.p, cw.p2};
+  int cur = 0;
   for (int it = 1; it <= opts->max_iter; ++it) {
-    {  // Ap = A p ; alpha = rz / p.Ap
+    if (fuse && it > 1) {  // p = beta p_old + r ; x += alpha_prev p_old ; Ap = A p ; alpha
+      LhsArgs A = P.args;
+      A.v = pbuf[cur];
+      A.p_out = pbuf[cur ^ 1];
+      A.rres = cw.r;
+      A.xup = d_x;
+      A.out = cw.Ap;
+      A.done = done;
+      A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr, cur ^ 1};
+      rc = launch_lhs(LHS_COMBINE, lhs, P, lw, A, opts->variant, st);
+      if (rc) return rc;
+      cur ^= 1;
+    } else {  // Ap = A p ; alpha = rz / p.Ap
       LhsArgs A = P.args;
       A.v = cw.p;
       A.out = cw.Ap;
       A.done = done;
-      A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr};
+      A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr, 0};
       rc = launch_lhs(LHS_PLAIN, lhs, P, lw, A, opts->variant, st);
       if (rc) return rc;
+    }
+    if (fuse) {  // r -= alpha Ap ; beta = rz'/rz
+      FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
+      cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+      UR_LAUNCH_CHECK();
+      continue;
     }
     if (stop == UR_STOP_ENERGY) {  // x += alpha p ; r -= alpha Ap ; beta = rz'/rz
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
@@ -681,6 +754,10 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
       rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
       if (rc) return rc;
     }
+  }
+  if (fuse) {  // the x update of the last completed iteration: x += alpha p
+    cg_final_x_kernel<<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.p2, n, cw.st);
+    UR_LAUNCH_CHECK();
   }
   return UR_OK;
 }

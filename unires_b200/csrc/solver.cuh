@@ -12,7 +12,7 @@ struct CgState {
   int n_iter;  // completed iterations
   int done;    // set on the device when |gain| < tolerance
   int done_iter;  // iteration whose stop test set `done`
-  int pad_;
+  int p_cur;      // which of the two direction buffers holds the current p (fused update)
   double obj[UR_CG_MAX_ITER + 1];
 };
 
@@ -32,6 +32,7 @@ struct FinalizeArgs {
   double tol;
   CgState *st;
   double *dot_out;
+  int aux;  // FIN_ALPHA: index of the direction buffer this matvec used / produced
 };
 
 __device__ __forceinline__ void record_objective(CgState *st, int n, double o, double tol) {
@@ -71,7 +72,10 @@ struct LatticeTerm {
   float ker[UR_MAX_TAPS];
 };
 
-enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2 };
+// LHS_COMBINE (streaming kernel only): the direction update is folded into the matvec's
+// load stage:  p = beta p_old + r  (tile + halo, on-chip),  x += alpha_prev p_old,
+// out = A p, p.Ap  -- 24 instead of 8 + 20 bytes per voxel for the two sweeps it replaces.
+enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2, LHS_COMBINE = 3 };
 
 struct LhsArgs {
   int nx, ny, nz;
@@ -87,6 +91,11 @@ struct LhsArgs {
   float *r;        // RESID: r = b - A v ; ENERGY (p update): read
   float *p;        // RESID: p = r       ; ENERGY (p update): p = beta p + r
   int update_p;    // ENERGY only
+  // COMBINE: v = p_old (read through TMA), rres = residual, p_out = new direction (a second
+  // buffer: neighbouring CTAs still read p_old halos), xup = x (updated in place)
+  const float *rres;
+  float *p_out;
+  float *xup;
   const int *done;
   GridReduce gr;
   FinalizeArgs fin;
@@ -109,6 +118,7 @@ __device__ __forceinline__ void finalize(const FinalizeArgs &f, double total) {
     case FIN_ALPHA:
       st->pAp = total;
       st->alpha = st->rz / total;
+      st->p_cur = f.aux;
       break;
     case FIN_BETA:
       st->rz0 = st->rz;
