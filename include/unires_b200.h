@@ -208,6 +208,13 @@ int ur_cg_update_p(float *d_p, const float *d_r, size_t n, const double *d_beta,
 int ur_admm_rhs(float *d_b, const float *d_w, const float *d_z,
                 const int32_t dim[3], const float vx[3], float lam, float rho,
                 ur_stream stream);
+/* The whole right-hand side in ONE pass when every observation of the channel
+ * is lattice aligned (else UR_ERR_UNSUPPORTED, nothing launched):
+ *   b = sum_n tau_n An' x_n - lam * div(w_c - rho z_c)
+ * d_x: host array of lhs->n_obs device pointers (the observations x_n).     */
+int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, float *d_b,
+                      const float *d_w, const float *d_z, float lam, float rho,
+                      ur_stream stream);
 /* y += a * x (float32) */
 int ur_axpy(float *d_y, const float *d_x, float a, size_t n, ur_stream stream);
 

@@ -158,3 +158,31 @@ def test_jtv_sharded_equals_fused(cuda):
         assert torch.allclose(z1, z2, rtol=1e-5, atol=1e-6)
         assert torch.allclose(w1, w2, rtol=1e-5, atol=1e-6)
         assert torch.allclose(j1, j2, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['denoise_1ch', 'sr3_thick_xyz', 'thickz2_scl', 'sr2_rigid'])
+def test_rhs_fused_vs_general_and_oracle(cuda, name):
+    """b = sum tau At x - lam div(w - rho z): fused lattice kernel, general path, oracle."""
+    from oracle.nitorch_shim import spatial as OS
+    from unires_b200 import _project, _update
+    _, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    dim, vx = _update._geometry(y)
+    g = torch.Generator().manual_seed(21)
+    for c in range(len(x)):
+        w = torch.rand((3,) + tuple(dim), generator=g) - 0.5
+        z = torch.rand((3,) + tuple(dim), generator=g) - 0.5
+        kw = dict(method=sc.sett.method, do=sc.sett.do_proj)
+        ref = torch.zeros(dim)
+        for n, obs in enumerate(sc.x[c]):
+            ref += obs.tau * P.proj('At', obs.dat, sc.x[c], sc.y[c], n=n, **kw)
+        ref -= sc.y[c].lam * OS.im_divergence(w - sc.rho * z, vx=torch.tensor(vx))
+        lhs = _project.LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj, rho=sc.rho, vx_y=vx)
+        out = {}
+        for key, op in (('fused', lhs), ('general', None)):
+            b = torch.full(dim, 7.0, device=cuda)  # must be fully overwritten
+            _update._rhs(x[c], y[c], z.to(cuda), w.to(cuda), sc.rho, b, sett, dim, vx, lhs=op)
+            out[key] = b
+            assert U.rel_l2(b, ref) < 1e-5, (name, c, key)
+        assert U.rel_l2(out['fused'], out['general']) < 1e-5

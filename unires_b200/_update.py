@@ -108,8 +108,18 @@ def _compute_nll(x, y, sett, rho, sum_dtype=torch.float64):
     return out[1] + out[2], out[1], out[2]
 
 
-def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
-    """tmp = sum_n tau_n An' x_n - lam div(w_c - rho z_c)   (unires/_update.py:124-133)."""
+def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx, lhs=None):
+    """tmp = sum_n tau_n An' x_n - lam div(w_c - rho z_c)   (unires/_update.py:124-133).
+
+    One fused pass when every observation is lattice aligned (`ur_admm_rhs_fused`);
+    otherwise At through the general path, accumulated, then the divergence."""
+    if lhs is not None:
+        dats = [require_cuda_f32(obs.dat, 'x.dat') for obs in xc]
+        rc = lib.ur_admm_rhs_fused(C.byref(lhs.c), _ptr_array(dats), ptr(tmp), ptr(w_c), ptr(z_c),
+                                   _hs(yc.lam), _hs(rho), stream())
+        if rc != _lib.UR_ERR_UNSUPPORTED:
+            check(rc)
+            return
     tmp.zero_()
     n_vox = tmp.numel()
     for n, obs in enumerate(xc):
@@ -125,19 +135,62 @@ def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
                           _hs(rho), stream()))
 
 
+def _solve_channel(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
+    """RHS + device-resident CG of one channel (in place on yc.dat).  Returns its CgInfo."""
+    stop = getattr(sett, 'cgs_stop', 'max_gain')
+    lhs = LhsOperator(xc, yc, method=sett.method, do=sett.do_proj, rho=rho, vx_y=vx,
+                      bound=sett.bound, interpolation=sett.interpolation, diff=sett.diff)
+    _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx, lhs=lhs)
+    yc.dat = require_cuda_f32(yc.dat, 'y.dat')
+    cg(A=lhs, b=tmp, x=yc.dat, verbose=sett.cgs_verbose, max_iter=sett.cgs_max_iter,
+       stop=stop, inplace=True, precond=None, tolerance=sett.cgs_tol)
+    return cg.last
+
+
 def _solve_y(x, y, z, w, rho, tmp, sett, dim, vx):
     """y-update: one device-resident CG per channel.  Returns the CgInfo handles."""
+    return [_solve_channel(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx)
+            for c in range(len(x))]
+
+
+def solve_y_from_host(x, y, z, w, rho, tmp, sett, host_x, host_y, host_out, copy_stream=None):
+    """The y-update with HOST (pinned) observations / initial estimates / results.
+
+    host_x[c][n] -> x[c][n].dat and host_y[c] -> y[c].dat are uploaded, and y[c].dat ->
+    host_out[c] downloaded, on a separate copy stream, per channel, so that the PCIe
+    transfers of channel c+1 (and the download of channel c-1) overlap the CG solve of
+    channel c.  Returns the CgInfo handles; the caller synchronises before reading host_out."""
+    dim, vx = _geometry(y)
+    main = torch.cuda.current_stream()
+    cs = copy_stream if copy_stream is not None else _copy_stream(main.device)
+    cs.wait_stream(main)  # earlier work on the destination buffers is finished
+    ready = []
+    with torch.cuda.stream(cs):
+        for c in range(len(x)):
+            for n, obs in enumerate(x[c]):
+                obs.dat.copy_(host_x[c][n], non_blocking=True)
+            y[c].dat.copy_(host_y[c], non_blocking=True)
+            ready.append(cs.record_event())
     infos = []
-    stop = getattr(sett, 'cgs_stop', 'max_gain')
     for c in range(len(x)):
-        _rhs(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx)
-        lhs = LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj, rho=rho, vx_y=vx,
-                          bound=sett.bound, interpolation=sett.interpolation, diff=sett.diff)
-        y[c].dat = require_cuda_f32(y[c].dat, 'y.dat')
-        cg(A=lhs, b=tmp, x=y[c].dat, verbose=sett.cgs_verbose, max_iter=sett.cgs_max_iter,
-           stop=stop, inplace=True, precond=None, tolerance=sett.cgs_tol)
-        infos.append(cg.last)
+        main.wait_event(ready[c])
+        infos.append(_solve_channel(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx))
+        solved = main.record_event()
+        with torch.cuda.stream(cs):
+            cs.wait_event(solved)
+            host_out[c].copy_(y[c].dat, non_blocking=True)
+    main.wait_stream(cs)
     return infos
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device).index
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
 
 
 def _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett):

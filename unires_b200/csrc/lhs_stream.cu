@@ -55,7 +55,7 @@ struct StreamTerm {
 
 struct StreamArgs {
   int nm, no, nz;
-  long long gs_m, gs_o;  // element strides of the marching / row axis in global memory
+  int gs_m, gs_o;  // element strides of the marching / row axis (volumes < 2^31 voxels)
   int march_y;
   float iv_m, iv_o, iv_z, rl2, w_ident;  // iv_* = 1 / vx^2
   StreamTerm T;
@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     // and is overwritten in place by the new direction.
     float beta_c = 0.f, alpha_c = 0.f;
     uint32_t h_off = 0;
-    size_t h_g = 0;
+    int h_g = 0;
     bool h_has = false, h_in = false;
-    size_t g_own = 0;
+    int g_own = 0;
     if (MODE == LHS_COMBINE) {
       beta_c = (float)a.fin.st->beta;
       alpha_c = (float)a.fin.st->alpha;
@@ -338,28 +338,28 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       h_off = (uint32_t)(h_row * a.sz + 4 * h_c4) * 4u;
       const int h_o = o0 - 1 + h_row, h_z = z0 - a.hz + 4 * h_c4;
       h_in = h_has && h_o >= 0 && h_o < a.no && h_z >= 0 && h_z < a.nz;
-      h_g = h_in ? (size_t)h_o * a.gs_o + h_z : 0;
-      g_own = (size_t)o_first * a.gs_o + z;
+      h_g = h_in ? h_o * a.gs_o + h_z : 0;
+      g_own = o_first * a.gs_o + z;
     }
     float4 cr_own[RPT], cx_own[RPT], cr_h;  // prefetched r / x quads of the plane to combine
-    auto fetch_rx = [&](int q) {
+    // gq = q * gs_m as a signed element offset, advanced incrementally by the callers (it is
+    // only dereferenced for planes inside the volume)
+    auto fetch_rx = [&](int q, int gq) {
       const bool q_in = q >= 0 && q < a.nm;
       const bool q_own = q >= m0 && q < m1;
-      const size_t gq = (size_t)(q_in ? q : 0) * a.gs_m;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const size_t gi = gq + g_own + (size_t)i * a.gs_o;
+        const int gi = gq + g_own + i * a.gs_o;
         cr_own[i] = (q_in && active[i]) ? *reinterpret_cast<const float4 *>(a.rres + gi)
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         cx_own[i] = (q_own && active[i]) ? *reinterpret_cast<const float4 *>(a.xup + gi)
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      cr_h = (q_in && h_in) ? *reinterpret_cast<const float4 *>(a.rres + gq + h_g)
+      cr_h = (q_in && h_in) ? *reinterpret_cast<const float4 *>(a.rres + (gq + h_g))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto combine = [&](int q, uint32_t aq) {
+    auto combine = [&](int q, uint32_t aq, int gq) {
       const bool q_own = q >= m0 && q < m1;
-      const size_t gq = (size_t)(q > 0 ? q : 0) * a.gs_m;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         const uint32_t sa = aq + own_b + i * sz_b;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
         pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), cr_own[i].w);
         sts128(sa, pn);
         if (q_own && active[i]) {
-          const size_t gi = gq + g_own + (size_t)i * a.gs_o;
+          const int gi = gq + g_own + i * a.gs_o;
           *reinterpret_cast<float4 *>(a.p_out + gi) = pn;
           float4 xn;  // the previous iteration's x += alpha p, done now that p_old is at hand
           xn.x = __fadd_rn(cx_own[i].x, __fmul_rn(alpha_c, po.x));
@@ -395,18 +395,20 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     // ---- prime the pipeline: planes first .. u_begin + L - 1 (COMBINE: one more, each
     //      combined as it lands) ----
     const uint32_t a_first = wp.pa;
+    int gq_c = first * a.gs_m;  // COMBINE: element offset of the plane to combine
     for (int n = 0; n < a.L + 1 + (MODE == LHS_COMBINE ? 1 : 0); ++n) {
       const uint32_t aq = wp.pa;
       mbar_wait_a(wp.ba, wp.par);
       wp.inc(R);
       if (MODE == LHS_COMBINE) {
-        fetch_rx(first + n);
-        combine(first + n, aq);
+        fetch_rx(first + n, gq_c);
+        combine(first + n, aq, gq_c);
+        gq_c += a.gs_m;
       }
     }
     if (MODE == LHS_COMBINE) {
       __syncthreads();  // halo quads of the primed planes were written by other threads
-      fetch_rx(u_begin + a.L + 1);
+      fetch_rx(u_begin + a.L + 1, gq_c);
     }
     uint32_t au = a_first + R.plane_b;  // plane u
     if (au == R.end) au = R.base;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     }
     const bool o_is0 = o_first == 0, z_is0 = z == 0;
     // global element offset of this thread's first quad in plane u (advanced per output plane)
-    size_t goff = (size_t)m0 * a.gs_m + (size_t)o_first * a.gs_o + z;
+    int goff = m0 * a.gs_m + o_first * a.gs_o + z;
     int pend = 0;  // planes consumed since the ring was last refilled
 
     for (int u = u_begin; u < m1; ++u) {
@@ -443,8 +445,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
           const uint32_t aq = wp.pa;
           mbar_wait_a(wp.ba, wp.par);
           wp.inc(R);
-          combine(qc, aq);
-          if (qc + 1 <= last) fetch_rx(qc + 1);
+          combine(qc, aq, gq_c);
+          gq_c += a.gs_m;
+          if (qc + 1 <= last) fetch_rx(qc + 1, gq_c);
         }
       } else {
         mbar_wait_a(wp.ba, wp.par);  // plane u + L has landed
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           if (!active[i]) continue;
-          const size_t gi = goff + (size_t)i * a.gs_o;
+          const int gi = goff + i * a.gs_o;
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), rq = bq, pq = bq;
           if (MODE == LHS_RESID || MODE == LHS_ENERGY)
             bq = *reinterpret_cast<const float4 *>(a.b + gi);
@@ -630,7 +633,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       // Refill the ring every kRefill planes (every plane for the z-thick kernel, whose lrz
       // double buffer needs the barrier anyway): after the barrier every warp is done with
       // the planes up to u - 1, so that many slots are free again.
-      constexpr int kRefill = (KIND == SK_THICK_Z || MODE == LHS_COMBINE) ? 1 : 2;
+      // (COMBINE: the quads other warps rewrote in plane u + L + 1 are first read L + 1 >= 2
+      // iterations later, so a barrier every second plane also publishes them in time)
+      constexpr int kRefill = KIND == SK_THICK_Z ? 1 : 2;
       if (++pend == kRefill || u == m1 - 1) {
         __syncthreads();
         if (tid == 0)
@@ -727,6 +732,9 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   const bool dry_run = variant < 0;
   if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
   if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
+  // 32-bit element offsets inside the kernel (incl. the look-ahead planes past the end)
+  if ((long long)A.nx * A.ny * A.nz + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)
+    return UR_ERR_UNSUPPORTED;
   if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
   if (!a16(A.rres) || !a16(A.p_out) || !a16(A.xup)) return UR_ERR_UNSUPPORTED;
   const bool combine = mode == LHS_COMBINE;
@@ -786,8 +794,8 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
   S.nm = march ? A.ny : A.nx;
   S.no = march ? A.nx : A.ny;
   S.nz = A.nz;
-  S.gs_m = march ? (long long)A.nz : (long long)A.ny * A.nz;
-  S.gs_o = march ? (long long)A.ny * A.nz : (long long)A.nz;
+  S.gs_m = march ? A.nz : A.ny * A.nz;
+  S.gs_o = march ? A.ny * A.nz : A.nz;
   S.iv_m = march ? A.ivy * A.ivy : A.ivx * A.ivx;  // 1 / vx^2 per axis
   S.iv_o = march ? A.ivx * A.ivx : A.ivy * A.ivy;
   S.iv_z = A.ivz * A.ivz;
@@ -814,8 +822,8 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
     const int to = NWARP * rpt;
     // window [u-1, u+L] + prefetch + one slot of slack for the every-other-plane refill
     // (COMBINE looks one plane further ahead and refills every plane)
-    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2) + stream_pf +
-           (combine ? 1 : (T.kind == SK_THICK_Z ? 0 : 1));
+    S.ns = S.L + 2 + (rpt == 1 ? 3 : 2) + stream_pf + (combine ? 1 : 0) +
+           (T.kind == SK_THICK_Z ? 0 : 1);
     if (combine && 2 * ((TZ + 2 * hz) / 4) + to * 2 * (hz / 4) > NTHR) return UR_ERR_UNSUPPORTED;
     if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
     S.hz = hz;

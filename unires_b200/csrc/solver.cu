@@ -353,6 +353,86 @@ static bool lattice_term(const ur_proj *po, float tau, LatticeTerm *T) {
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// fused right-hand side of the y-update (unires/_update.py:124-133):
+//   b = sum_n tau_n An' x_n - lam div(w - rho z)
+// for lattice observations An' x is a gather from the low-res volume: at most ceil(K/r)
+// loads per voxel; the pass is bound by reading w and z (24 B/voxel) and writing b.
+// ---------------------------------------------------------------------------
+struct AtTerm {
+  LatticeTerm L;
+  int shift[3];  // y index = low-res index + shift on the non-decimated axes
+  int dimx[3];
+  float a_even, a_odd;  // exp(+scl), exp(-scl): At applies the scaling once
+  const float *x;
+};
+
+struct RhsArgs {
+  int nx, ny, nz;
+  float ivx, ivy, ivz, lam, rho;
+  int nterm;
+  AtTerm term[kMaxFused];
+};
+
+__device__ __forceinline__ float eval_at(const AtTerm &A, int x, int y, int z) {
+  const LatticeTerm &T = A.L;
+  const int i[3] = {x, y, z};
+  int j[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    j[a] = i[a] - A.shift[a];
+    if (a != T.axis && (j[a] < 0 || j[a] >= A.dimx[a])) return 0.f;
+  }
+  float thin = 1.f;
+  if (T.scl_axis >= 0 && T.scl_axis != T.axis) thin = (j[T.scl_axis] & 1) ? A.a_odd : A.a_even;
+  const size_t s1 = A.dimx[2], s0 = (size_t)A.dimx[1] * A.dimx[2];
+  if (T.axis < 0) return T.tau * (thin * __ldg(A.x + j[0] * s0 + j[1] * s1 + j[2]));
+  const int ax = T.axis;
+  const int u = i[ax] - T.off;
+  if (u < 0) return 0.f;
+  int j_hi = u / T.r;
+  if (j_hi > T.nj - 1) j_hi = T.nj - 1;
+  const int a0 = u - T.K + 1;
+  const int j_lo = a0 <= 0 ? 0 : (a0 + T.r - 1) / T.r;
+  const size_t sa = ax == 0 ? s0 : (ax == 1 ? s1 : 1);
+  j[ax] = 0;
+  const float *base = A.x + j[0] * s0 + j[1] * s1 + j[2];
+  float acc = 0.f;
+  for (int jj = j_lo; jj <= j_hi; ++jj) {
+    float v = __ldg(base + (size_t)jj * sa);
+    if (T.scl_axis == ax) v *= (jj & 1) ? A.a_odd : A.a_even;
+    acc = fmaf(T.ker[u - jj * T.r], v, acc);
+  }
+  return T.tau * (thin * acc);
+}
+
+__global__ void __launch_bounds__(256)
+    rhs_fused_kernel(float *__restrict__ b, const float *__restrict__ w,
+                     const float *__restrict__ zz, const RhsArgs a) {
+  __shared__ AtTerm s_term[kMaxFused];
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  {
+    const int nwords = a.nterm * (int)(sizeof(AtTerm) / 4);
+    const int *src = reinterpret_cast<const int *>(a.term);
+    int *dst = reinterpret_cast<int *>(s_term);
+    for (int k = tid; k < nwords; k += blockDim.x * blockDim.y) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (z >= a.nz || y >= a.ny) return;
+  const size_t sy = a.nz, sx = (size_t)a.ny * a.nz, n = sx * a.nx;
+  const size_t i = x * sx + y * sy + z;
+  float val = 0.f;
+  for (int k = 0; k < a.nterm; ++k) val += eval_at(s_term[k], x, y, z);
+  auto q = [&](int c, size_t j) { return w[c * n + j] - a.rho * zz[c * n + j]; };
+  const float t0 = ((x > 0 ? q(0, i - sx) : 0.f) - q(0, i)) * a.ivx;
+  const float t1 = ((y > 0 ? q(1, i - sy) : 0.f) - q(1, i)) * a.ivy;
+  const float t2 = ((z > 0 ? q(2, i - 1) : 0.f) - q(2, i)) * a.ivz;
+  b[i] = val - a.lam * ((t0 + t1) + t2);
+}
+
 static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
   UR_REQUIRE(lhs, "ur_lhs is NULL");
   UR_REQUIRE(lhs->dim_y[0] > 0 && lhs->dim_y[1] > 0 && lhs->dim_y[2] > 0, "ur_lhs: bad dim_y");
@@ -618,6 +698,61 @@ extern "C" int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, d
   A.out = d_out;
   A.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, d_dot};
   return launch_lhs(LHS_PLAIN, lhs, P, w, A, 0, st);
+}
+
+extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, float *d_b,
+                                 const float *d_w, const float *d_z, float lam, float rho,
+                                 ur_stream stream) {
+  UR_REQUIRE(lhs && d_x && d_b && d_w && d_z, "ur_admm_rhs_fused: null pointer");
+  UR_REQUIRE(lhs->n_obs >= 1 && lhs->n_obs <= UR_MAX_OBS, "ur_admm_rhs_fused: bad n_obs");
+  if (lhs->n_obs > kMaxFused) return UR_ERR_UNSUPPORTED;
+  RhsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nx = lhs->dim_y[0];
+  A.ny = lhs->dim_y[1];
+  A.nz = lhs->dim_y[2];
+  A.ivx = 1.f / lhs->vx[0];
+  A.ivy = 1.f / lhs->vx[1];
+  A.ivz = 1.f / lhs->vx[2];
+  A.lam = lam;
+  A.rho = rho;
+  for (int n = 0; n < lhs->n_obs; ++n) {
+    UR_REQUIRE(d_x[n] != nullptr, "ur_admm_rhs_fused: observation %d is NULL", n);
+    AtTerm &T = A.term[A.nterm];
+    T.x = d_x[n];
+    T.a_even = T.a_odd = 1.f;
+    if (!lhs->do_proj) {  // A = identity: tau * x on the recon grid
+      memset(&T.L, 0, sizeof(T.L));
+      T.L.axis = -1;
+      T.L.scl_axis = -1;
+      T.L.tau = lhs->tau[n];
+      for (int a = 0; a < 3; ++a) {
+        T.shift[a] = 0;
+        T.dimx[a] = lhs->dim_y[a];
+      }
+    } else {
+      const ur_proj *po = &lhs->obs[n];
+      int rc = validate_proj(po);
+      if (rc) return rc;
+      if (!lattice_term(po, lhs->tau[n], &T.L)) return UR_ERR_UNSUPPORTED;
+      float wgt = lhs->tau[n];  // At applies each thin-axis coefficient once (AtA: twice)
+      for (int a = 0; a < 3; ++a) {
+        T.shift[a] = (int)lrintf(po->mat[4 * a + 3]);
+        T.dimx[a] = po->dim_x[a];
+        if (a != T.L.axis && po->method == UR_SUPERRES) wgt *= po->ker[a][0];
+      }
+      T.L.tau = wgt;
+      if (T.L.scl_axis >= 0) {
+        T.a_even = expf(po->scl);
+        T.a_odd = expf(-po->scl);
+      }
+    }
+    ++A.nterm;
+  }
+  dim3 block(64, 4, 1), grid(div_up(A.nz, 64), div_up(A.ny, 4), A.nx);
+  rhs_fused_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_b, d_w, d_z, A);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
 }
 
 extern "C" size_t ur_cg_workspace_bytes(const ur_lhs *lhs) {
