@@ -132,5 +132,61 @@ def main():
               '%.0f KB' % (os.path.getsize(path) / 1024))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and '--fit' not in sys.argv:
     main()
+    main_fit()
+
+
+# ---------------------------------------------------------------------------
+# outer loop (unires/run.py::fit) fixture
+# ---------------------------------------------------------------------------
+FIT_RECIPE = dict(base='sr3_256', dim_y=(16, 18, 16), n_channels=2, sd=25.0, scl=0.0, rigid=None,
+                  max_iter=70)
+
+
+def prepare_fit(sc, reference=False):
+    """Settings of the fit fixture (and the fields only the reference's fit touches)."""
+    s = sc.sett
+    s.max_iter, s.tolerance, s.reg_scl, s.sched_num = FIT_RECIPE['max_iter'], 1e-4, 4.0, 3
+    s.clean_fov, s.scaling, s.unified_rigid, s.rigid_mod = True, False, False, 1
+    if reference:
+        from oracle.nitorch_shim.spatial import affine_basis
+        s.rigid_basis = affine_basis(group='SE', dtype=torch.float64)
+        s.write_out, s.write_jtv, s.show_jtv, s.plot_conv, s.mat, s.do_print = \
+            False, False, False, False, None, 0
+        for xc in sc.x:
+            for o in xc:
+                o.rigid_q = torch.zeros(6, dtype=torch.float64)
+                o.direc = o.nam = None
+    return sc
+
+
+def main_fit():
+    from oracle.adapters import reference_namespaces
+    from oracle.load_reference import load_reference
+    ref = load_reference()
+    ops, structs = reference_namespaces()
+    sc = prepare_fit(build(FIT_RECIPE, ops, structs), reference=True)
+    obj_rows = []
+    orig = ref.run._update_admm
+
+    def spy(x, y, z, w, rho, tmp, obj, n_iter, sett):
+        out = orig(x, y, z, w, rho, tmp, obj, n_iter, sett)
+        obj_rows.append(out[4][n_iter].clone())
+        return out
+
+    ref.run._update_admm = spy
+    try:
+        dat_y = ref.run.fit(sc.x, sc.y, sc.sett)[0]
+    finally:
+        ref.run._update_admm = orig
+    out = {'recipe': json.dumps(FIT_RECIPE), 'dat_y': dat_y.numpy(),
+           'obj': torch.stack(obj_rows).numpy(), 'n_iter': np.int32(len(obj_rows))}
+    path = os.path.join(GOLDEN_DIR, 'fit_sr2.npz')
+    np.savez_compressed(path, **out)
+    print('fit_sr2 n_iter', len(obj_rows), 'obj', obj_rows[0][0].item(), '->', obj_rows[-1][0].item(),
+          '%.0f KB' % (os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__' and '--fit' in sys.argv:
+    main_fit()

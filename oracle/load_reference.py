@@ -32,6 +32,13 @@ def install_shim():
         'nitorch.core.optim': shim.core.optim,
         'nitorch.core.math': shim.core.math,
         'nitorch.core._linalg_expm': shim.core._linalg_expm,
+        'nitorch.core.constants': shim.core.constants,
+        'nitorch.core.utils': shim.core.utils,
+        'nitorch.tools': shim.tools,
+        'nitorch.tools.preproc': shim.tools.preproc,
+        'nitorch.tools.img_statistics': shim.tools.img_statistics,
+        'nitorch.tools._preproc_fov': shim.tools._preproc_fov,
+        'nitorch.tools._preproc_utils': shim.tools._preproc_utils,
         'nitorch.io': shim.io,
         'nitorch.plot': shim.plot,
         'nitorch.plot.volumes': shim.plot.volumes,
@@ -56,7 +63,7 @@ def load_reference():
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, 'unires')]
     sys.modules[pkg_name] = pkg
     ns = types.SimpleNamespace()
-    for mod in ('struct', '_util', '_project', '_update'):
+    for mod in ('struct', '_util', '_project', '_update', '_core', 'run'):
         full = pkg_name + '.' + mod
         spec = importlib.util.spec_from_file_location(
             full, os.path.join(REFERENCE_ROOT, 'unires', mod + '.py'))

@@ -188,3 +188,24 @@ def im_divergence(dat, vx=None, which='forward', bound='zero'):
         t = (p.narrow(ax, 0, n) - p.narrow(ax, 1, n)) / vx[a]
         out = t if out is None else out + t
     return out
+
+
+def affine_basis(group='SE', dim=3, dtype=None, device=None):
+    """Lie-algebra basis of SE(3): 3 translations then 3 rotations (unires/_core.py:317)."""
+    if group != 'SE' or dim != 3:
+        raise NotImplementedError
+    B = torch.zeros(6, 4, 4, dtype=dtype or torch.float64, device=device)
+    for i in range(3):
+        B[i, i, 3] = 1
+    for k, (i, j) in enumerate(((0, 1), (0, 2), (1, 2))):
+        B[3 + k, i, j] = 1
+        B[3 + k, j, i] = -1
+    return B
+
+
+def affine_matrix_classic(*args, **kwargs):  # pragma: no cover
+    raise NotImplementedError('affine_matrix_classic is only used by pre-processing')
+
+
+def max_bb(*args, **kwargs):  # pragma: no cover
+    raise NotImplementedError('max_bb is only used by pre-processing')

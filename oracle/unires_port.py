@@ -51,7 +51,9 @@ def Settings(**kw):
                               interpolation='linear',
                               method='super-resolution', rho=None, rho_scl=1.0,
                               tolerance=1e-4, profile_ip=2, profile_tp=0,
-                              gap=0.0)
+                              gap=0.0, max_iter=512, reg_scl=4.0, sched_num=3,
+                              rigid_mod=1, clean_fov=False, scaling=False,
+                              unified_rigid=False)
     for k, v in kw.items():
         setattr(s, k, v)
     return s
@@ -256,3 +258,68 @@ def update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett, cg_stop='max_gain',
     for c in range(C):
         w[c] += rho * (scaled_grad(c) - z[c])
     return y, z, w, jtv, obj, cg_iters
+
+
+# ----------------------------------------------------------------------------
+# outer loop  (unires/run.py:24-207, default path: no scaling / rigid updates;
+# schedule from unires/_core.py:288-307, output clamp from unires/_core.py:619-627)
+# ----------------------------------------------------------------------------
+def get_sched(N, sett):
+    """Coarse-to-fine regularisation scaling, e.g. reg_scl=4, sched_num=3 -> [32, 16, 8, 4]."""
+    sched_num = 0 if (sett.sched_num < 0 or N == 1) else sett.sched_num
+    scl = torch.as_tensor(sett.reg_scl, dtype=torch.float32).reshape(1)
+    powers = 2.0 ** torch.arange(0, 32, dtype=torch.float32).flip(0)
+    ix = int(torch.min((powers - scl).abs(), dim=0)[1])
+    return torch.cat((powers[ix - sched_num:ix], scl))
+
+
+def fit(x, y, sett):
+    """Returns (dat_y (X,Y,Z,C), obj[:n_done], n_done, jtv)."""
+    N = sum(len(xc) for xc in x)
+    reg = get_sched(N, sett)
+    cnt_scl = 0
+    for yc in y:
+        yc.lam = reg[cnt_scl] * yc.lam0
+    rho = step_size(x, y, sett)
+    z, w = admm_aux(y)
+    obj = torch.zeros(sett.max_iter, 3, dtype=F64)
+    tmp = torch.zeros_like(y[0].dat)
+    cnt_scl_iter, countdown0, countdown1, n_done = 0, 6, 6, 0
+    for n_iter in range(sett.max_iter):
+        y, z, w, tmp, obj, _ = update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett)
+        n_done = n_iter + 1
+        gain = O.get_gain(obj[:n_iter + 1, 0], monotonicity='decreasing')
+        if cnt_scl >= reg.numel() - 1 and cnt_scl_iter > 20 and \
+                (gain.abs() < sett.tolerance or n_iter >= sett.max_iter - 1):
+            countdown0 -= 1
+            if countdown0 == 0:
+                break
+        else:
+            countdown0 = 6
+        if cnt_scl + 1 < len(reg) and cnt_scl_iter > 16 and gain.abs() < 1e-3:
+            countdown1 -= 1
+            if countdown1 == 0:
+                cnt_scl_iter = 0
+                cnt_scl += 1
+                for yc in y:
+                    yc.lam = reg[cnt_scl] * yc.lam0
+                rho = step_size(x, y, sett)
+        else:
+            countdown1 = 6
+        cnt_scl_iter += 1
+    if getattr(sett, 'clean_fov', False):
+        for xc, yc in zip(x, y):
+            msk = torch.ones(yc.dim, dtype=torch.bool)
+            for obs in xc:
+                M = torch.linalg.solve(yc.mat, obs.po.rigid @ obs.mat).inverse()
+                grid = S.affine_grid(M.to(obs.dat.dtype), yc.dim)
+                for d in range(3):
+                    msk &= (grid[..., d] >= 0) & (grid[..., d] < obs.dim[d])
+            yc.dat[~msk] = 0.0
+    out = []
+    for xc, yc in zip(x, y):
+        mn = min(float(obs.dat.min()) for obs in xc)
+        mx = max(float(obs.dat.max()) for obs in xc)
+        yc.dat.clamp_(mn, mx)
+        out.append(yc.dat[..., None].clone())
+    return torch.cat(out, dim=3), obj[:n_done], n_done, tmp

@@ -1,0 +1,45 @@
+"""Outer loop `fit` (unires/run.py:24-207) on the GPU against the reference's fit fixture."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gen_golden
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fit_matches_reference_fixture(cuda):
+    from unires_b200 import run
+    g = np.load(U.GOLDEN_DIR + '/fit_sr2.npz', allow_pickle=False)
+    recipe = json.loads(str(g['recipe']))
+    sc = gen_golden.prepare_fit(U.build(recipe, *U.port_namespaces()))
+    x, y, sett = U.to_device(sc, cuda)
+    for k in ('max_iter', 'tolerance', 'reg_scl', 'sched_num', 'clean_fov', 'scaling',
+              'unified_rigid', 'rigid_mod'):
+        setattr(sett, k, getattr(sc.sett, k))
+    for c in range(len(y)):
+        y[c].lam0 = torch.tensor(float(sc.y[c].lam0), device=cuda)
+        for n, o in enumerate(x[c]):
+            o.dim = tuple(sc.x[c][n].dat.shape)
+            o.tau = torch.tensor(float(sc.x[c][n].tau), device=cuda)
+    dat_y, mat, pth, R, label, pth_label = run.fit(x, y, sett)
+    last = run.fit.last
+    assert last['reg_scl'].tolist() == [32.0, 16.0, 8.0, 4.0]
+    assert last['n_iter'] == int(g['n_iter'])
+    obj = last['obj'].cpu().numpy()
+    # the objective trajectory through three schedule changes
+    assert np.allclose(obj, g['obj'], rtol=2e-4)
+    assert tuple(dat_y.shape) == tuple(g['dat_y'].shape)
+    assert U.rel_l2(dat_y, g['dat_y']) < 1e-3
+    assert R.shape == (2, 4, 4) and pth == [] and label is None
+
+
+def test_fit_rejects_out_of_scope_updates(cuda):
+    from unires_b200 import run, struct
+    s = struct.settings()
+    s.scaling = True
+    with pytest.raises(NotImplementedError):
+        run.fit([], [], s)
