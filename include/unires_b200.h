@@ -58,12 +58,19 @@ uint64_t ur_launch_count(void);
 int ur_profile_matvec(int enable);
 int ur_profile_matvec_read(double *total_ms, int32_t *count,
                            double *bytes_per_voxel_sum);
-/* Tuning / test knobs (process-wide).  "lhs_variant": 0 automatic, 1 force the
- * direct (non-TMA) lhs kernel; "stream_mc": planes per CTA chunk of the TMA
- * streaming kernel (0 automatic); "stream_rpt": rows per thread of that
- * kernel (0 automatic, 1 = 8-row tiles, 2 = 16-row tiles).  Unknown names
- * return UR_ERR_ARG.                                                        */
+/* Tuning / test knobs (process-wide).  "lhs_variant": 0 automatic (lean
+ * specialised TMA kernel -> generic TMA streaming kernel -> direct kernel),
+ * 1 force the direct (non-TMA) lhs kernel, 2 skip the lean kernel;
+ * "stream_mc" / "stream_rpt" / "stream_pf": planes per CTA chunk, rows per
+ * thread (0 automatic, 1 = 8-row tiles, 2 = 16-row tiles) and extra prefetch
+ * slots of the generic streaming kernel; "fast_q" / "fast_rpt" / "fast_depth":
+ * work units per CTA, rows per thread and ring prefetch depth (plane pairs)
+ * of the lean kernel; "cg_fuse": fold the direction update into the matvec.
+ * Unknown names return UR_ERR_ARG.                                          */
 int ur_tune(const char *name, int value);
+/* Which kernel served the most recent lhs launch of this process:
+ * 0 direct, 1 generic TMA streaming kernel, 2 lean specialised TMA kernel.  */
+int ur_last_lhs_path(void);
 
 /* ---------------------------------------------------------------- finite
  * differences: nitorch.spatial.im_gradient / im_divergence, 'forward',

@@ -1,6 +1,6 @@
 #!/bin/bash
-# quick iteration: stream-kernel tests, then microbench
+# quick iteration: lhs kernel tests, then the CG microbenchmark
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_stream_kernel.py tests/test_gpu_ops.py -m gpu -x -q > gpurun_out/pytest_iter.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_iter.log
-tail -12 gpurun_out/pytest_iter.log
-timeout 300 python scripts/microbench_lhs.py sr3_256 "$@" 2>&1 | tee gpurun_out/microbench.log
+timeout 900 python -m pytest tests/test_gpu_stream_kernel.py -m gpu -x -q > gpurun_out/pytest_iter.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_iter.log
+tail -15 gpurun_out/pytest_iter.log
+timeout 300 python scripts/microbench_cg.py sr3_256 20 5 "$@" 2>&1 | tee gpurun_out/microbench_cg.log

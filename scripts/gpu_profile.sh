@@ -1,7 +1,8 @@
 #!/bin/bash
-# ncu: full capture of the streaming kernel (thick-x channel) + launch list of one bench step
+# ncu: full capture of the fused (COMBINE) streaming matvec, thick-x channel and thick-z channel
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:lhs_stream -s 2 -c 1 -o gpurun_out/prof_stream python scripts/microbench_lhs.py sr3_256 0 > gpurun_out/ncu_run.log 2>&1
+python scripts/microbench_cg.py sr3_256 2>&1 | tee gpurun_out/microbench_cg.log
+ncu --set full --clock-control none --import-source on -k regex:lhs_stream_kernel -s 8 -c 1 -o gpurun_out/prof_combine_m python scripts/microbench_cg.py sr3_256 20 1 > gpurun_out/ncu_run.log 2>&1
 tail -3 gpurun_out/ncu_run.log
-ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-tail -2 gpurun_out/bench_ncu.log | cut -c1-300
+ncu --set full --clock-control none --import-source on -k regex:lhs_stream_kernel -s 140 -c 1 -o gpurun_out/prof_combine_z python scripts/microbench_cg.py sr3_256 20 1 > gpurun_out/ncu_run2.log 2>&1
+tail -3 gpurun_out/ncu_run2.log

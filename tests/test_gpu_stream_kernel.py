@@ -1,5 +1,6 @@
-"""The TMA streaming lhs kernel against the direct kernel and the oracle: tile / chunk
-boundaries, FOV crops, every thick axis, even/odd scaling, volume edges, all CG epilogues."""
+"""The TMA streaming lhs kernels (generic `lhs_stream`, lean specialised `lhs_fast`) against the
+direct kernel and the oracle: tile / chunk boundaries, FOV crops, every thick axis, even/odd
+scaling, volume edges, all CG epilogues."""
 import pytest
 import torch
 
@@ -12,6 +13,33 @@ pytestmark = pytest.mark.gpu
 def _tune(name, value):
     from unires_b200 import _lib
     _lib.check(_lib.lib.ur_tune(name.encode(), int(value)))
+
+
+def _last_path():
+    from unires_b200 import _lib
+    return _lib.lib.ur_last_lhs_path()
+
+
+KERNELS = ['stream', 'fast']
+
+
+def _select(kern, chunk=0, rpt=0):
+    """Route the lhs through the generic streaming kernel or (when eligible) the lean one."""
+    _tune('lhs_variant', 2 if kern == 'stream' else 0)
+    _tune('stream_mc', chunk)
+    _tune('stream_rpt', rpt)
+    _tune('fast_q', chunk)
+    _tune('fast_rpt', rpt)
+
+
+def _reset():
+    for k in ('lhs_variant', 'stream_mc', 'stream_rpt', 'fast_q', 'fast_rpt'):
+        _tune(k, 0)
+    _tune('cg_fuse', 1)
+
+
+def _fast_eligible(factor, scl_on_thick=True):
+    return factor in (2, 4)
 
 
 def _make(dim_y, fov, thick_axis, factor, scl, cuda, denoise=False):
@@ -43,9 +71,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('kern', KERNELS)
 @pytest.mark.parametrize('rpt', [1, 2])
 @pytest.mark.parametrize('case', CASES)
-def test_stream_equals_direct_and_oracle(cuda, case, rpt):
+def test_stream_equals_direct_and_oracle(cuda, case, rpt, kern):
     from unires_b200 import _project
     dim_y, fov, axis, factor, scl, mc = case
     obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
@@ -57,15 +86,13 @@ def test_stream_equals_direct_and_oracle(cuda, case, rpt):
     try:
         _tune('lhs_variant', 1)
         direct = op(v.to(cuda))
-        _tune('lhs_variant', 0)
-        _tune('stream_mc', mc)
-        _tune('stream_rpt', rpt)
+        _select(kern, mc, rpt)
         dot = torch.zeros(1, dtype=torch.float64, device=cuda)
         stream = op(v.to(cuda), dot=dot)
+        path = _last_path()
     finally:
-        _tune('lhs_variant', 0)
-        _tune('stream_mc', 0)
-        _tune('stream_rpt', 0)
+        _reset()
+    assert path == (2 if kern == 'fast' and _fast_eligible(factor) else 1)
     assert U.rel_l2(direct, ref) < 1e-5
     assert U.rel_l2(stream, ref) < 1e-5
     assert U.rel_l2(stream, direct) < 1e-6
@@ -73,8 +100,9 @@ def test_stream_equals_direct_and_oracle(cuda, case, rpt):
     assert abs(dot.item() - want) < 1e-5 * abs(want)
 
 
+@pytest.mark.parametrize('kern', KERNELS)
 @pytest.mark.parametrize('dim', [(18, 20, 128), (9, 11, 12), (40, 8, 256)])
-def test_stream_denoise_lhs(cuda, dim):
+def test_stream_denoise_lhs(cuda, dim, kern):
     """do_proj = False: tau * v + rho lam^2 DtD v (configs[0] path)."""
     from unires_b200 import _project, struct
     g = torch.Generator().manual_seed(5)
@@ -86,15 +114,18 @@ def test_stream_denoise_lhs(cuda, dim):
     op = _project.LhsOperator([struct._input(tau=0.02)], struct._output(dim=dim, lam=0.3), do=False,
                               rho=0.9, vx_y=vx)
     try:
-        _tune('stream_mc', 5)
+        _select(kern, 5)
         out = op(v.to(cuda))
+        path = _last_path()
     finally:
-        _tune('stream_mc', 0)
+        _reset()
+    assert path == (2 if kern == 'fast' else 1)
     assert U.rel_l2(out, ref) < 1e-6
 
 
+@pytest.mark.parametrize('kern', KERNELS)
 @pytest.mark.parametrize('stop', ['max_gain', 'residual'])
-def test_cg_stream_vs_direct(cuda, stop):
+def test_cg_stream_vs_direct(cuda, stop, kern):
     """Whole CG solves (all epilogues: residual init, energy + p update) agree between kernels."""
     from unires_b200 import _project, optim
     obs_o, rec_o, obs_g, rec_g = _make((24, 28, 132), (20, 22, 120), 1, 4, 0.1, cuda)
@@ -105,14 +136,16 @@ def test_cg_stream_vs_direct(cuda, stop):
     res = {}
     try:
         for variant in (1, 0):
-            _tune('lhs_variant', variant)
-            _tune('stream_mc', 0 if variant else 11)
+            if variant:
+                _reset()
+                _tune('lhs_variant', 1)
+            else:
+                _select(kern, 11)
             x = x0.clone()
             optim.cg(A=op, b=b, x=x, max_iter=20, tolerance=1e-3, stop=stop)
             res[variant] = (x, optim.cg.last.n_iter, optim.cg.last.obj)
     finally:
-        _tune('lhs_variant', 0)
-        _tune('stream_mc', 0)
+        _reset()
     assert res[0][1] == res[1][1]
     assert U.rel_l2(res[0][0], res[1][0]) < 1e-5
     # the two kernels round D'D differently; sqrt(r.r) of the recursively updated residual
@@ -131,9 +164,10 @@ FUSE_CASES = [
 ]
 
 
+@pytest.mark.parametrize('kern', KERNELS)
 @pytest.mark.parametrize('case', FUSE_CASES)
 @pytest.mark.parametrize('stop,tol', [('residual', 1e-3), ('max_gain', 0.0)])
-def test_cg_fused_direction_update(cuda, case, stop, tol):
+def test_cg_fused_direction_update(cuda, case, stop, tol, kern):
     """Matvec with p = beta p + r and x += alpha p folded in (two sweeps per iteration) against
     the unfused three-sweep iteration and the oracle: same trip count, same iterate."""
     from oracle.nitorch_shim.core import optim as OO
@@ -156,17 +190,16 @@ def test_cg_fused_direction_update(cuda, case, stop, tol):
     OO.cg(A=lhs_o, b=b, x=xo, max_iter=12, tolerance=tol, stop=stop)
     res = {}
     try:
-        _tune('stream_rpt', rpt)
-        _tune('stream_mc', 13)
+        _select(kern, 13, rpt)
         for fuse in (0, 1):
             _tune('cg_fuse', fuse)
             x = x0.clone().to(cuda)
             optim.cg(A=op, b=b.to(cuda), x=x, max_iter=12, tolerance=tol, stop=stop)
             res[fuse] = (x, optim.cg.last.n_iter)
+        path = _last_path()
     finally:
-        _tune('cg_fuse', 1)
-        _tune('stream_rpt', 0)
-        _tune('stream_mc', 0)
+        _reset()
+    assert path == (2 if kern == 'fast' else 1)
     assert res[0][1] == res[1][1] == OO.cg.last_n_iter
     assert U.rel_l2(res[1][0], res[0][0]) < 1e-6
     assert U.rel_l2(res[1][0], xo) < U.REL_TOL

@@ -83,6 +83,7 @@ _SIGNATURES = {
     'ur_profile_matvec_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_double)]),
     'ur_tune': (C.c_int, [C.c_char_p, C.c_int]),
+    'ur_last_lhs_path': (C.c_int, []),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_dtd': (C.c_int, [_p, _p, _i3, _f3, _p]),

@@ -1,0 +1,187 @@
+// Host side of the lean streaming lhs kernel (lhs_fast.cuh): eligibility, specialisation
+// lookup, ring sizing, balanced one-wave work split in row-aligned units, launch.
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "lhs_fast.cuh"
+
+namespace ur {
+
+// lhs_stream.cu: cached cuTensorMapEncodeTiled of an (X, Y, Z) float volume with a box of one
+// plane tile (sz floats along z, `rows` rows, 1 plane along the march axis)
+bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
+                       CUtensorMap *out);
+
+int fast_rpt = 0;     // rows per thread: 0 automatic, 1 | 2
+int fast_depth = 1;   // prefetch depth of the ring in plane pairs (>= 1)
+int fast_q_units = 0; // units per CTA override (0 automatic)
+
+static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
+
+// dry_run: eligibility check only, nothing is launched
+int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
+  using namespace fast;
+  if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
+  if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
+  if ((long long)A.nx * A.ny * A.nz + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)
+    return UR_ERR_UNSUPPORTED;
+  if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
+  if (!a16(A.rres) || !a16(A.p_out) || !a16(A.xup)) return UR_ERR_UNSUPPORTED;
+  const bool combine = mode == LHS_COMBINE;
+
+  FastArgs S;
+  memset(&S, 0, sizeof(S));
+  int kind = FK_NONE, kp = 1, r = 1, e = 0, march = 0;
+  S.lo_m = S.lo_o = S.lo_z = 0;
+  S.s_even = S.s_odd = 1.f;
+  if (A.nterm == 1) {
+    const LatticeTerm &T = A.term[0];
+    if (T.axis == 1) march = 1;
+    const int ax_m = march, ax_o = 1 - march;
+    if (T.scl_axis >= 0 && T.scl_axis != T.axis) return UR_ERR_UNSUPPORTED;  // thin-axis scaling
+    S.tau = T.tau;
+    S.off = T.off;
+    S.nj = T.nj;
+    S.lo_m = T.lo[ax_m];
+    S.hi_m = T.hi[ax_m];
+    S.lo_o = T.lo[ax_o];
+    S.hi_o = T.hi[ax_o];
+    S.lo_z = T.lo[2];
+    S.hi_z = T.hi[2];
+    S.scl_conv = T.scl_axis >= 0;
+    S.s_even = T.s_even;
+    S.s_odd = T.s_odd;
+    if (T.axis < 0) {
+      kind = FK_POINT;
+    } else {
+      kp = T.K;
+      r = T.r;
+      if (kp > kTaps) return UR_ERR_UNSUPPORTED;
+      for (int t = 0; t < kp; ++t) {
+        S.ker[t] = T.ker[t];
+        S.kerT[t] = T.tau * T.ker[t];
+      }
+      e = ((T.off % r) + r) % r;
+      if (T.axis == 2) {
+        kind = FK_THICK_Z;
+        S.lo_z = 0;
+        S.hi_z = A.nz;
+      } else {
+        kind = FK_THICK_M;
+        S.lo_m = 0;
+        S.hi_m = march ? A.ny : A.nx;
+      }
+    }
+  }
+  S.march_y = march;
+  S.nm = march ? A.ny : A.nx;
+  S.no = march ? A.nx : A.ny;
+  S.nz = A.nz;
+  S.gs_m = march ? A.nz : A.ny * A.nz;
+  S.gs_o = march ? A.ny * A.nz : A.nz;
+  const float iv_m = march ? A.ivy * A.ivy : A.ivx * A.ivx;
+  const float iv_o = march ? A.ivx * A.ivx : A.ivy * A.ivy;
+  const float iv_z = A.ivz * A.ivz;
+  S.a_m = A.rl2 * iv_m;
+  S.a_o = A.rl2 * iv_o;
+  S.a_z = A.rl2 * iv_z;
+  S.d0 = A.w_ident + 2.f * ((S.a_m + S.a_o) + S.a_z);
+
+  int rpt = kind == FK_THICK_M ? 1 : 2;
+  if (fast_rpt == 1 || fast_rpt == 2) rpt = fast_rpt;
+  if (S.no <= NWARP) rpt = 1;
+
+  FastKernel kernel = nullptr;
+  const int ez = kind == FK_THICK_Z ? e : 0;
+  switch (mode) {
+    case LHS_PLAIN:
+      kernel = fast_lookup_plain(kind, kp, r, ez, rpt);
+      break;
+    case LHS_RESID:
+      kernel = fast_lookup_resid(kind, kp, r, ez, rpt);
+      break;
+    case LHS_ENERGY:
+      kernel = fast_lookup_energy(kind, kp, r, ez, rpt);
+      break;
+    default:
+      kernel = fast_lookup_combine(kind, kp, r, ez, rpt);
+      break;
+  }
+  if (!kernel) return UR_ERR_UNSUPPORTED;
+
+  const int to = NWARP * rpt;
+  const int L = kind == FK_THICK_M ? kp - 1 : 1;
+  const int B = kind == FK_THICK_M ? kp - 1 : 0;
+  const int depth = fast_depth < 1 ? 1 : fast_depth;
+  S.ns = L + 3 + 2 * depth;
+  S.nrs = combine ? S.ns - L - 1 : 0;
+  if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
+  const size_t plane_b = ((size_t)(to + 2) * SZ * 4 + 127) / 128 * 128;
+  const size_t smem = (size_t)(S.ns + S.nrs) * plane_b + 128;
+  if (smem > 200u * 1024u) return UR_ERR_UNSUPPORTED;
+
+  CUtensorMap map_v, map_r;
+  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_v))
+    return UR_ERR_UNSUPPORTED;
+  map_r = map_v;
+  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r))
+    return UR_ERR_UNSUPPORTED;
+  if (dry_run) return UR_OK;
+
+  int resident = 0;
+  {
+    static std::unordered_map<size_t, int> occ_cache;
+    static std::mutex occ_mu;
+    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull);
+    std::lock_guard<std::mutex> lock(occ_mu);
+    auto it = occ_cache.find(key);
+    if (it != occ_cache.end()) {
+      resident = it->second;
+    } else {
+      UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident,
+                                                                     (const void *)kernel, NTHR,
+                                                                     smem);
+      if (oe != cudaSuccess || resident < 1) resident = 1;
+      occ_cache[key] = resident;
+    }
+  }
+
+  // work units: groups of unit_r planes of one column, cut at low-res row starts
+  S.unit_r = kind == FK_THICK_M ? r : 1;
+  S.unit_e2 = kind == FK_THICK_M ? (e > 0 ? e : r) : 1;
+  S.units_per_col = 1 + (S.nm > S.unit_e2 ? (S.nm - S.unit_e2 + S.unit_r - 1) / S.unit_r : 0);
+  const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, to);
+  S.gx = (int)gx;
+  S.ncol = (int)(gx * gy);
+  const long long total = (long long)S.ncol * S.units_per_col;
+  const long long slots = (long long)resident * sm_count();
+  long long q = (total + slots - 1) / slots;
+  const long long q_min = (4 * (B + L + 1) + S.unit_r - 1) / S.unit_r;
+  if (q < q_min) q = q_min;
+  if (fast_q_units > 0) q = fast_q_units;
+  if (q > total) q = total;
+  S.q_units = (int)q;
+  const unsigned n_cta = (unsigned)((total + q - 1) / q);
+
+  S.v = A.v;
+  S.out = A.out;
+  S.b = A.b;
+  S.r = A.r;
+  S.p = A.p;
+  S.update_p = A.update_p;
+  S.p_out = A.p_out;
+  S.xup = A.xup;
+  S.done = A.done;
+  S.gr = A.gr;
+  S.fin = A.fin;
+
+  kernel<<<dim3(n_cta), dim3(NTHR), smem, st>>>(map_v, map_r, S);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+}  // namespace ur

@@ -720,6 +720,11 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
   return true;
 }
 
+bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
+                       CUtensorMap *out) {
+  return get_tensor_map(v, nx, ny, nz, sz, march_y, rows, out);
+}
+
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
 int stream_mc_override = 0;  // test / tuning hook (plane-tiles per CTA), 0 = automatic

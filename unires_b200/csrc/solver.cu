@@ -25,6 +25,7 @@ int scratch_reduce(GridReduce *gr);  // vecops.cu
 // lhs_stream.cu: TMA-staged streaming kernel.  Returns UR_ERR_UNSUPPORTED (without
 // setting an error) when the problem does not fit it, so the caller falls back.
 int lhs_stream_launch(int mode, const LhsArgs &a, int variant, cudaStream_t st);
+int lhs_fast_launch(int mode, const LhsArgs &a, bool dry_run, cudaStream_t st);  // lhs_fast.cu
 
 __device__ __forceinline__ float eval_term(const LatticeTerm &T, const float *__restrict__ v,
                                            const int (&i)[3], size_t lin, const int (&n)[3],
@@ -524,8 +525,10 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
+extern int fast_rpt, fast_depth, fast_q_units;  // lhs_fast.cu
 static int g_lhs_variant = 0;
-static int g_cg_fuse = 1;  // fold the direction / x updates into the matvec when possible
+static int g_cg_fuse = 1;
+static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
 
 struct MatvecProfile {
   bool on = false;
@@ -567,10 +570,17 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
   cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
   if (e0) cudaEventRecord(e0, st);
-  // variant 0 = automatic (TMA streaming kernel when it applies), 1 = force the direct kernel
+  // variant 0 = automatic (lean TMA kernel, then the generic TMA streaming kernel, then the
+  // direct kernel), 1 = force the direct kernel, 2 = skip the lean kernel
   if (variant == 0) variant = g_lhs_variant;
   if (variant != 1 || mode == LHS_COMBINE) {
-    const int rc = lhs_stream_launch(mode, A, variant == 1 ? 0 : variant, st);
+    int rc = UR_ERR_UNSUPPORTED;
+    if (variant != 2) rc = lhs_fast_launch(mode, A, false, st);
+    g_last_path = 2;
+    if (rc == UR_ERR_UNSUPPORTED) {
+      rc = lhs_stream_launch(mode, A, 0, st);
+      g_last_path = 1;
+    }
     if (rc != UR_ERR_UNSUPPORTED || mode == LHS_COMBINE) {
       if (e1 && rc == UR_OK) {
         cudaEventRecord(e1, st);
@@ -583,6 +593,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
       return rc;
     }
   }
+  g_last_path = 0;
   switch (mode) {
     case LHS_PLAIN:
       lhs_direct_kernel<LHS_PLAIN><<<P.grid, P.block, 0, st>>>(A);
@@ -644,6 +655,12 @@ extern "C" int ur_tune(const char *name, int value) {
     g_cg_fuse = value != 0;
   } else if (!strcmp(name, "stream_pf")) {
     stream_pf = value < 0 ? 0 : value;
+  } else if (!strcmp(name, "fast_rpt")) {
+    fast_rpt = (value == 1 || value == 2) ? value : 0;
+  } else if (!strcmp(name, "fast_depth")) {
+    fast_depth = value < 1 ? 1 : value;
+  } else if (!strcmp(name, "fast_q")) {
+    fast_q_units = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {
     stream_rpt = (value == 1 || value == 2) ? value : 0;
   } else {
@@ -652,6 +669,8 @@ extern "C" int ur_tune(const char *name, int value) {
   }
   return UR_OK;
 }
+
+extern "C" int ur_last_lhs_path(void) { return g_last_path; }
 
 extern "C" int ur_profile_matvec(int enable) {
   g_prof.on = enable != 0;
@@ -823,7 +842,9 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     A.rres = cw.r;
     A.p_out = cw.p2;
     A.xup = d_x;
-    fuse = lhs_stream_launch(LHS_COMBINE, A, -1, st) == UR_OK;
+    fuse = (g_lhs_variant != 2 && opts->variant != 2 &&
+            lhs_fast_launch(LHS_COMBINE, A, true, st) == UR_OK) ||
+           lhs_stream_launch(LHS_COMBINE, A, -1, st) == UR_OK;
   }
   float *pbuf[2] = {cw.p, cw.p2};
   int cur = 0;
