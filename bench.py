@@ -53,6 +53,16 @@ def peaks():
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return float(json.load(f)[workload]['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -145,7 +155,6 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    _lib.lib.ur_profile_matvec(1)
     l0 = _lib.lib.ur_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -159,11 +168,23 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.ur_launch_count() - l0
+    clocks = sampler.result()
+
+    # ---- roofline pass: the same K steps again with every matvec launch bracketed by CUDA
+    # events on its stream (library instrumentation).  Channels run back to back on one stream
+    # here so that a bracket holds exactly one kernel; the event records cost ~4 % of a step,
+    # which is why `value` is timed without them. ----
     import ctypes as C_
+    streams_cfg = getattr(sett, 'channel_streams', 1)
+    sett.channel_streams = 1
+    _lib.lib.ur_profile_matvec(1)
+    for _ in range(args.steps):
+        reset()
+        y_update(sc.x, sc.y, z, w, rho, tmp, sett, vx, dim)
     tot, cnt, bpv = C_.c_double(0), C_.c_int32(0), C_.c_double(0)
     _lib.check(_lib.lib.ur_profile_matvec_read(C_.byref(tot), C_.byref(cnt), C_.byref(bpv)))
     _lib.lib.ur_profile_matvec(0)
-    clocks = sampler.result()
+    sett.channel_streams = streams_cfg
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step ----
     hx = [[o.dat.cpu().pin_memory() for o in xc] for xc in sc.x]
@@ -213,6 +234,7 @@ def run_ours(args):
                                'one subject per GPU' % (args.workload, C, 'x'.join(map(str, dim)),
                                                         args.cg_iters),
                    'channels': C, 'recon_grid': list(dim), 'cg_iters_per_channel': args.cg_iters,
+                   'channel_streams': int(getattr(sett, 'channel_streams', 1)),
                    'l2': 'inputs larger than L2: CG working set per channel 5 volumes = %.0f MB '
                          '(L2 126 MB); no explicit flush' % (5 * n_vox * 4 / 1e6)},
         'e2e': {'value': total_its / (ms_e2e * 1e-3), 'unit': UNIT,
@@ -220,11 +242,14 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'host_enqueue_ms_per_step': host_ms / args.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'lhs_stream_kernel: CG matvec A p = sum tau AtA p + rho lam^2 '
+        'roofline': {'bound': 'hbm', 'kernel': 'lhs_fast_kernel: CG matvec A p = sum tau AtA p + rho lam^2 '
                                                'DtD p with p = beta p + r, x += alpha p and p.Ap '
                                                'fused in (first iteration of a solve: plain matvec)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                     'frac': (achieved / peak) if achieved else None,
+                     'traffic': ncu_traffic(args.workload),
+                     'timing': 'CUDA events around every matvec launch in a second pass over the '
+                               'same K steps (channels serialised on one stream)',
                      'algorithmic_bytes_per_launch': mv_bpv * n_vox,
                      'algorithmic_bytes_per_voxel': mv_bpv,
                      'avg_launch_ms': mv_ms, 'launches_timed': cnt.value, 'peak_source': peak_src},

@@ -36,7 +36,7 @@ def main():
         x = x0.clone()
         optim.cg_fused(op, b, x, iters, 0.0, _lib.UR_STOP_NONE)
         torch.cuda.synchronize()
-        _lib.lib.ur_profile_matvec(1)
+        _lib.lib.ur_profile_matvec(0 if os.environ.get('NOPROF') else 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -48,7 +48,7 @@ def main():
         _lib.check(_lib.lib.ur_profile_matvec_read(C.byref(tot), C.byref(cnt), C.byref(bpv)))
         _lib.lib.ur_profile_matvec(0)
         us_it = e0.elapsed_time(e1) * 1e3 / reps / iters
-        mv_us = tot.value * 1e3 / max(cnt.value, 1)
+        mv_us = max(tot.value * 1e3 / max(cnt.value, 1), 1e-9)
         mv_b = bpv.value / max(cnt.value, 1) * n
         print('channel %d: %7.1f us/CG-it (%6.0f it/s)  matvec %6.1f us  %6.0f GB/s  frac %.3f  '
               '[36 B/voxel iteration: %5.0f GB/s frac %.3f]'

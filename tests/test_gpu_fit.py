@@ -35,7 +35,9 @@ def test_fit_matches_reference_fixture(cuda):
     # float32 summation noise; one CG iteration more or less in a single solve then moves the
     # objective by O(1e-4) relative (measured on B200: <= 3.3e-4 over 70 iterations, identical
     # ADMM trip count and schedule switches, final image 3e-5 relative L2)
-    assert np.allclose(obj[:6], g['obj'][:6], rtol=1e-6)
+    # (the lean lhs kernel evaluates D'D as diag*c - sum(neighbours), the reference as
+    # differences of differences: the data term agrees to ~1e-6 relative from the first row)
+    assert np.allclose(obj[:6], g['obj'][:6], rtol=1e-5)
     assert np.allclose(obj, g['obj'], rtol=1e-3)
     assert tuple(dat_y.shape) == tuple(g['dat_y'].shape)
     assert U.rel_l2(dat_y, g['dat_y']) < 1e-3

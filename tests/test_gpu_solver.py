@@ -96,6 +96,30 @@ def test_update_admm_vs_golden_and_oracle(cuda, name):
     assert np.allclose(obj.cpu().numpy(), g['obj'], rtol=1e-4)
 
 
+def test_channel_streams_do_not_change_results(cuda):
+    """The per-channel CG solves spread over several CUDA streams (sett.channel_streams) give
+    bit-identical iterates and trip counts to the sequential loop of unires/_update.py:122."""
+    from unires_b200 import _update
+    _, recipe = U.load_golden('sr3_thick_xyz')
+    res = {}
+    for ns in (1, 3):
+        sc = U.build(recipe, *U.port_namespaces())
+        x, y, sett = U.to_device(sc, cuda)
+        sett.channel_streams = ns
+        z, w = _update._admm_aux(y, sett)
+        tmp = torch.zeros(y[0].dim, device=cuda)
+        obj = torch.zeros(2, 3, dtype=torch.float64, device=cuda)
+        for it in range(2):
+            y, z, w, tmp, obj = _update._update_admm(x, y, z, w, sc.rho.to(cuda), tmp, obj, it, sett)
+        res[ns] = ([yc.dat.clone() for yc in y], z.clone(), w.clone(), obj.clone(),
+                   [i.n_iter for i in _update._update_admm.last_cg])
+    assert res[1][4] == res[3][4]
+    for a, b in zip(res[1][0], res[3][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[1][1], res[3][1]) and torch.equal(res[1][2], res[3][2])
+    assert torch.equal(res[1][3], res[3][3])
+
+
 def test_compute_nll_vs_oracle(cuda):
     from unires_b200 import _update
     _, recipe = U.load_golden('sr2_rigid')

@@ -147,10 +147,51 @@ def _solve_channel(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
     return cg.last
 
 
+def _side_streams(device, n):
+    key = torch.device(device).index
+    pool = _channel_streams.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+_channel_streams = {}
+
+
+def _n_streams(sett, n_channels):
+    return max(1, min(int(getattr(sett, 'channel_streams', 1) or 1), n_channels))
+
+
+def _rhs_buffer(dim, device):
+    n_vox = dim[0] * dim[1] * dim[2]
+    return _lib.workspace(4 * n_vox, device, 'rhs').view(torch.float32)[:n_vox].view(dim)
+
+
 def _solve_y(x, y, z, w, rho, tmp, sett, dim, vx):
-    """y-update: one device-resident CG per channel.  Returns the CgInfo handles."""
-    return [_solve_channel(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx)
-            for c in range(len(x))]
+    """y-update: one device-resident CG per channel.  Returns the CgInfo handles.
+
+    The channels are independent linear systems (unires/_update.py:122-150 loops over them
+    sequentially); with `sett.channel_streams` > 1 they are enqueued round-robin on that many
+    CUDA streams, so that the launch gaps and the ramp-down of one channel's kernels are
+    filled by another channel's.  Each stream owns its right-hand side and CG workspace."""
+    ns = _n_streams(sett, len(x))
+    if ns == 1:
+        return [_solve_channel(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx)
+                for c in range(len(x))]
+    main = torch.cuda.current_stream()
+    streams = _side_streams(tmp.device, ns)
+    start = main.record_event()
+    infos = []
+    for c in range(len(x)):
+        s = streams[c % ns]
+        if c < ns:
+            s.wait_event(start)
+        with torch.cuda.stream(s):
+            infos.append(_solve_channel(x[c], y[c], z[c], w[c], rho, _rhs_buffer(dim, tmp.device),
+                                        sett, dim, vx))
+    for s in streams:
+        main.wait_stream(s)
+    return infos
 
 
 def solve_y_from_host(x, y, z, w, rho, tmp, sett, host_x, host_y, host_out, copy_stream=None):
@@ -171,14 +212,25 @@ def solve_y_from_host(x, y, z, w, rho, tmp, sett, host_x, host_y, host_out, copy
                 obs.dat.copy_(host_x[c][n], non_blocking=True)
             y[c].dat.copy_(host_y[c], non_blocking=True)
             ready.append(cs.record_event())
+    ns = _n_streams(sett, len(x))
+    streams = _side_streams(main.device, ns) if ns > 1 else [main]
+    start = main.record_event()
     infos = []
     for c in range(len(x)):
-        main.wait_event(ready[c])
-        infos.append(_solve_channel(x[c], y[c], z[c], w[c], rho, tmp, sett, dim, vx))
-        solved = main.record_event()
+        s = streams[c % ns]
+        if ns > 1 and c < ns:
+            s.wait_event(start)
+        s.wait_event(ready[c])
+        with torch.cuda.stream(s):
+            b = _rhs_buffer(dim, main.device) if ns > 1 else tmp
+            infos.append(_solve_channel(x[c], y[c], z[c], w[c], rho, b, sett, dim, vx))
+            solved = s.record_event()
         with torch.cuda.stream(cs):
             cs.wait_event(solved)
             host_out[c].copy_(y[c].dat, non_blocking=True)
+    for s in streams:
+        if s is not main:
+            main.wait_stream(s)
     main.wait_stream(cs)
     return infos
 

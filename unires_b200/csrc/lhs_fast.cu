@@ -17,6 +17,8 @@ bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march
 int fast_rpt = 0;     // rows per thread: 0 automatic, 1 | 2
 int fast_depth = 1;   // prefetch depth of the ring in plane pairs (>= 1)
 int fast_q_units = 0; // units per CTA override (0 automatic)
+int fast_pfd = 0;     // planes prefetched into L2 ahead of the ring
+int fast_lock = 1;    // cut every column into the same segments (neighbours march in step)
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
@@ -122,11 +124,14 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   const size_t smem = (size_t)(S.ns + S.nrs) * plane_b + 128;
   if (smem > 200u * 1024u) return UR_ERR_UNSUPPORTED;
 
-  CUtensorMap map_v, map_r;
+  CUtensorMap map_v, map_r, map_x;
   if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_v))
     return UR_ERR_UNSUPPORTED;
   map_r = map_v;
   if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r))
+    return UR_ERR_UNSUPPORTED;
+  map_x = map_v;
+  if (combine && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x))
     return UR_ERR_UNSUPPORTED;
   if (dry_run) return UR_OK;
 
@@ -165,7 +170,20 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   if (fast_q_units > 0) q = fast_q_units;
   if (q > total) q = total;
   S.q_units = (int)q;
-  const unsigned n_cta = (unsigned)((total + q - 1) / q);
+  unsigned n_cta = (unsigned)((total + q - 1) / q);
+  // Lock-step split: the same cuts in every column, one CTA per segment.  Neighbouring tiles
+  // are then read at (nearly) the same time and the halo re-reads hit L2 instead of HBM.
+  S.segs = 0;
+  if (fast_lock && fast_q_units == 0 && S.ncol <= slots) {
+    long long segs = slots / S.ncol;
+    const long long max_segs = S.units_per_col / q_min > 0 ? S.units_per_col / q_min : 1;
+    if (segs > max_segs) segs = max_segs;
+    if (segs * S.ncol * 4 >= slots * 3) {  // keep >= 75 % of the CTA slots busy
+      S.segs = (int)segs;
+      n_cta = (unsigned)(segs * S.ncol);
+    }
+  }
+  S.pfd = fast_pfd < 0 ? 0 : fast_pfd;
 
   S.v = A.v;
   S.out = A.out;
@@ -179,7 +197,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.gr = A.gr;
   S.fin = A.fin;
 
-  kernel<<<dim3(n_cta), dim3(NTHR), smem, st>>>(map_v, map_r, S);
+  kernel<<<dim3(n_cta), dim3(NTHR), smem, st>>>(map_v, map_r, map_x, S);
   UR_LAUNCH_CHECK();
   return UR_OK;
 }

@@ -59,6 +59,10 @@ struct FastArgs {
   // work split: a unit is a group of unit_r planes of one column starting at unit_e (mod unit_r)
   int unit_r, unit_e2, units_per_col, q_units, ncol, gx;
   int ns, nrs;  // ring slots: planes of v / planes of the residual (COMBINE)
+  int segs;     // > 0: every column is cut into `segs` equal segments, one CTA each (neighbouring
+                // columns then march in step and share their halos through L2); 0: contiguous
+                // ranges of q_units units in (column, unit) order
+  int pfd;      // planes prefetched into L2 ahead of the ring's issue front
   const float *v;
   float *out;
   const float *b;
@@ -72,7 +76,8 @@ struct FastArgs {
   FinalizeArgs fin;
 };
 
-typedef void (*FastKernel)(const CUtensorMap, const CUtensorMap, const FastArgs);
+typedef void (*FastKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const FastArgs);
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -124,6 +129,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 __device__ __forceinline__ float &cmp(float4 &q, int k) {
   return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
 }
@@ -142,6 +154,7 @@ template <int MODE, int KIND, int KP, int R, int E, int RPT>
 __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     lhs_fast_kernel(const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_r,
+                    const __grid_constant__ CUtensorMap tmap_x,
                     const __grid_constant__ FastArgs a) {
   constexpr int TO = NWARP * RPT;
   constexpr uint32_t ROWB = SZ * 4u;
@@ -220,7 +233,12 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 
   const long long total_units = (long long)a.ncol * a.units_per_col;
   long long t = (long long)blockIdx.x * a.q_units;
-  const long long t_end = t + a.q_units < total_units ? t + a.q_units : total_units;
+  long long t_end = t + a.q_units < total_units ? t + a.q_units : total_units;
+  if (a.segs > 0) {  // one segment of one column
+    const int c = blockIdx.x / a.segs, sg = blockIdx.x - c * a.segs;
+    t = (long long)c * a.units_per_col + (long long)sg * a.units_per_col / a.segs;
+    t_end = (long long)c * a.units_per_col + (long long)(sg + 1) * a.units_per_col / a.segs;
+  }
 
   // ring positions persist across the column segments of this CTA
   uint32_t arr_pa = ring_base, arr_ba = bar_base, arr_par = 0u, arr_ra = rring_base;
@@ -279,7 +297,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 
     // ---- producer ----
     __syncthreads();  // every thread is done with the previous segment's slots
-    int iq = first;
+    int iq = first, pq = first;
     auto issue = [&](int limit) {
       while (iq <= last && iq < limit) {
         if (COMBINE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -302,6 +320,18 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
           if (ip_ra == rring_end) ip_ra = rring_base;
         }
         ++iq;
+      }
+      // L2 prefetch of the planes the ring cannot hold yet
+      if (pq < iq) pq = iq;
+      while (pq <= last && pq < iq + a.pfd) {
+        const int c1 = a.march_y ? pq : o0 - 1, c2 = a.march_y ? o0 - 1 : pq;
+        tma_prefetch_3d(&tmap_v, z0 - HZ, c1, c2);
+        if (COMBINE) {
+          tma_prefetch_3d(&tmap_r, z0 - HZ, c1, c2);
+          if (pq >= m0 && pq < m1)
+            tma_prefetch_3d(&tmap_x, z0, a.march_y ? pq : o0, a.march_y ? o0 : pq);
+        }
+        ++pq;
       }
     };
     if (tid == 0) issue(u_start + a.ns);

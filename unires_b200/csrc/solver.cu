@@ -525,7 +525,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
-extern int fast_rpt, fast_depth, fast_q_units;  // lhs_fast.cu
+extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock;  // lhs_fast.cu
 static int g_lhs_variant = 0;
 static int g_cg_fuse = 1;
 static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
@@ -659,6 +659,10 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_rpt = (value == 1 || value == 2) ? value : 0;
   } else if (!strcmp(name, "fast_depth")) {
     fast_depth = value < 1 ? 1 : value;
+  } else if (!strcmp(name, "fast_pfd")) {
+    fast_pfd = value < 0 ? 0 : value;
+  } else if (!strcmp(name, "fast_lock")) {
+    fast_lock = value != 0;
   } else if (!strcmp(name, "fast_q")) {
     fast_q_units = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {

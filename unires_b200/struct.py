@@ -62,4 +62,8 @@ class settings(_bag):
         write_jtv=False, write_out=True,
         # extension: which objective nitorch's cg uses for stop='max_gain'
         # (SURVEY.md Appendix A, Q1): 'energy' (nitorch's fall-through) or 'residual'
-        cgs_stop='max_gain')
+        cgs_stop='max_gain',
+        # extension: number of CUDA streams the per-channel CG solves of one ADMM iteration
+        # are spread over (the reference loops over channels sequentially; the systems are
+        # independent, so this only changes scheduling, not results)
+        channel_streams=3)
