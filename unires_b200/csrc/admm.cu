@@ -112,6 +112,142 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Vector variant: one thread owns V (4 or 2) consecutive z voxels of one row, all channels.
+// Every access to w / z / jtv is a 128- / 64-bit load or store and all loads of the first
+// sweep are in flight together; the arithmetic per voxel is the scalar kernel's, in the same
+// order (bit-identical results).  V is chosen so that at least two blocks stay resident per
+// SM (loads of one block overlap the stores of another).  Needs nz % V == 0 and aligned volumes.
+// ---------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void ldv(float (&o)[V], const float *p) {
+  if (V == 4) {
+    const float4 q = *reinterpret_cast<const float4 *>(p);
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[V - 1] = q.w;
+  } else {
+    const float2 q = *reinterpret_cast<const float2 *>(p);
+    o[0] = q.x; o[V - 1] = q.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void ldgv(float (&o)[V], const float *p) {
+  if (V == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[V - 1] = q.w;
+  } else {
+    const float2 q = __ldg(reinterpret_cast<const float2 *>(p));
+    o[0] = q.x; o[V - 1] = q.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(float *p, const float (&o)[V]) {
+  if (V == 4)
+    *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[V - 1]);
+  else
+    *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[V - 1]);
+}
+
+template <int MODE, int CT, int V>
+__global__ void __launch_bounds__(256, 2)
+    jtv_kernel_vec(ChannelPtrs ch, float *__restrict__ zz, float *__restrict__ w,
+                   float *__restrict__ nrm2, float *__restrict__ jtv, JtvGeom g, int accumulate) {
+  const int z = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (z >= g.nz || y >= g.ny) return;
+  const size_t sy = g.nz, sx = (size_t)g.ny * g.nz, n = sx * g.nx;
+  const size_t i = x * sx + y * sy + z;
+  float gk[CT][3][V], wk[CT][3][V];  // u = w / rho + g is re-formed in the second sweep
+  float s2[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s2[k] = 0.f;
+  {
+    // issue every load of the sweep first
+    float yc[CT][V], yx[CT][V], yy[CT][V], yz[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const float *yp = ch.y[c] + i;
+      ldgv<V>(yc[c], yp);
+#pragma unroll
+      for (int k = 0; k < V; ++k) yx[c][k] = yy[c][k] = 0.f;
+      if (x + 1 < g.nx) ldgv<V>(yx[c], yp + sx);
+      if (y + 1 < g.ny) ldgv<V>(yy[c], yp + sy);
+      yz[c] = z + V < g.nz ? __ldg(yp + V) : 0.f;
+      if (MODE != JTV_PRIOR) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ldv<V>(wk[c][d], w + ((size_t)c * 3 + d) * n + i);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const float lam = ch.lam[c];
+      float zo[3][V];
+      if (MODE != JTV_PRIOR && g.alpha != 1.f) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ldv<V>(zo[d], zz + ((size_t)c * 3 + d) * n + i);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float cv = yc[c][k];
+        const float zp = k < V - 1 ? yc[c][k < V - 1 ? k + 1 : k] : yz[c];
+        float gr[3];
+        gr[0] = lam * ((yx[c][k] - cv) * g.ivx);
+        gr[1] = lam * ((yy[c][k] - cv) * g.ivy);
+        gr[2] = lam * ((zp - cv) * g.ivz);
+        float e = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (MODE != JTV_PRIOR && g.alpha != 1.f)
+            gr[d] = __fadd_rn(__fmul_rn(g.alpha, gr[d]),
+                              __fmul_rn(__fsub_rn(1.f, g.alpha), zo[d][k]));
+          float u = gr[d];
+          if (MODE != JTV_PRIOR) u = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), u);
+          gk[c][d][k] = gr[d];
+          e = d == 0 ? __fmul_rn(u, u) : __fadd_rn(e, __fmul_rn(u, u));
+        }
+        s2[k] = __fadd_rn(s2[k], e);
+      }
+    }
+  }
+  if (MODE == JTV_NORM2 || MODE == JTV_PRIOR) {
+    if (accumulate) {
+      float o[V];
+      ldv<V>(o, nrm2 + i);
+#pragma unroll
+      for (int k = 0; k < V; ++k) s2[k] = __fadd_rn(o[k], s2[k]);
+    }
+    stv<V>(nrm2 + i, s2);
+    return;
+  }
+  if (MODE == JTV_APPLY) ldv<V>(s2, nrm2 + i);
+  float f[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float s = sqrtf(s2[k]);
+    f[k] = __fdiv_rn(fmaxf(__fsub_rn(s, __fdiv_rn(1.f, g.rho)), 0.f), __fadd_rn(s, 1e-7f));
+  }
+  if (jtv) stv<V>(jtv + i, f);
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t q = ((size_t)c * 3 + d) * n + i;
+      float zv[V], wn[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float uu = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), gk[c][d][k]);
+        zv[k] = __fmul_rn(f[k], uu);
+        wn[k] = __fadd_rn(wk[c][d][k], __fmul_rn(g.rho, __fsub_rn(gk[c][d][k], zv[k])));
+      }
+      stv<V>(zz + q, zv);
+      stv<V>(w + q, wn);
+    }
+  }
+}
+
+static bool ptr16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
+
 static int fill(ChannelPtrs *ch, const float *const *y, const float *lam, int C) {
   UR_REQUIRE(C >= 1 && C <= UR_MAX_CHANNELS, "channel count %d not in [1,%d]", C, UR_MAX_CHANNELS);
   UR_REQUIRE(y && lam, "null channel array");
@@ -136,6 +272,26 @@ static int launch(const float *const *y, float *z, float *w, float *nrm2, float 
   int rc = fill(&ch, y, lam, C);
   if (rc) return rc;
   JtvGeom g = geom(dim, vx, rho, alpha);
+  // vector path: whole quads (pairs for 3-4 channels: register budget for two resident
+  // blocks), aligned volumes, channel count known at compile time
+  bool vec = g.nz % 4 == 0 && C <= 4 && ptr16(z) && ptr16(w) && ptr16(nrm2) && ptr16(jtv);
+  for (int c = 0; c < C; ++c) vec = vec && ptr16(y[c]);
+  if (vec) {
+    const bool wide = C <= 2 || MODE == JTV_PRIOR;
+    const int V = wide ? 4 : 2;
+    dim3 vblock(32, 8, 1), vgrid(div_up(g.nz, 32 * V), div_up(g.ny, 8), g.nx);
+#define UR_JTV_V(CT, VV)                                                                    \
+  jtv_kernel_vec<MODE, CT, VV><<<vgrid, vblock, 0, st>>>(ch, z, w, nrm2, jtv, g, accumulate)
+    switch (C) {
+      case 1: UR_JTV_V(1, 4); break;
+      case 2: UR_JTV_V(2, 4); break;
+      case 3: if (wide) UR_JTV_V(3, 4); else UR_JTV_V(3, 2); break;
+      default: if (wide) UR_JTV_V(4, 4); else UR_JTV_V(4, 2); break;
+    }
+#undef UR_JTV_V
+    UR_LAUNCH_CHECK();
+    return UR_OK;
+  }
   dim3 block(64, 4, 1), grid(div_up(g.nz, 64), div_up(g.ny, 4), g.nx);
 #define UR_JTV_CASE(CT)                                                                     \
   jtv_kernel<MODE, CT><<<grid, block, 0, st>>>(ch, z, w, nrm2, jtv, C, g, accumulate)

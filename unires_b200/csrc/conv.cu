@@ -40,6 +40,45 @@ __global__ void conv_axis_kernel(const float *__restrict__ in, float *__restrict
   out[((size_t)x * odim.y + y) * odim.z + z] = acc;
 }
 
+// Same arithmetic for a conv axis other than z, marching: a thread owns one (z, other-axis)
+// line and produces a chunk of consecutive outputs along the conv axis, so the K (or ~K/stride)
+// inputs an output needs are re-read by the SAME thread from L1 instead of by K different
+// blocks from L2; z stays the coalesced direction.
+constexpr int kConvChunk = 32;
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+    conv_march_kernel(const float *__restrict__ in, float *__restrict__ out, Dim3i idim,
+                      Dim3i odim, int axis, Taps taps, int K, int stride) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oth = blockIdx.y * blockDim.y + threadIdx.y;  // y (axis 0) or x (axis 1)
+  const int n_oth = axis == 0 ? odim.y : odim.x;
+  if (z >= odim.z || oth >= n_oth) return;
+  const int n_out = axis == 0 ? odim.x : odim.y;
+  const int n_in = axis == 0 ? idim.x : idim.y;
+  const size_t istep = axis == 0 ? (size_t)idim.y * idim.z : (size_t)idim.z;
+  const size_t ostep = axis == 0 ? (size_t)odim.y * odim.z : (size_t)odim.z;
+  const size_t ibase = (axis == 0 ? (size_t)oth * idim.z : (size_t)oth * idim.y * idim.z) + z;
+  const size_t obase = (axis == 0 ? (size_t)oth * odim.z : (size_t)oth * odim.y * odim.z) + z;
+  const int p0 = blockIdx.z * kConvChunk;
+  const int p1 = p0 + kConvChunk < n_out ? p0 + kConvChunk : n_out;
+  for (int pos = p0; pos < p1; ++pos) {
+    float acc = 0.f;
+    if (!TRANSPOSE) {
+      const float *p = in + ibase + (size_t)pos * stride * istep;
+      for (int t = 0; t < K; ++t) acc = fmaf(taps.k[t], __ldg(p + t * istep), acc);
+    } else {
+      int j_hi = pos / stride;
+      if (j_hi > n_in - 1) j_hi = n_in - 1;
+      int j_lo = (pos - K + stride) / stride;
+      if (pos - K + 1 <= 0) j_lo = 0;
+      for (int j = j_lo; j <= j_hi; ++j)
+        acc = fmaf(taps.k[pos - j * stride], __ldg(in + ibase + (size_t)j * istep), acc);
+    }
+    out[obase + (size_t)pos * ostep] = acc;
+  }
+}
+
 __global__ void scaling_kernel(const float *__restrict__ in, float *__restrict__ out, Dim3i d,
                                float even, float odd, int axis) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,6 +106,16 @@ int conv_axis(const float *in, Dim3i idim, float *out, int axis, const float *ke
   if (odim_out) *odim_out = od;
   Taps taps;
   for (int t = 0; t < UR_MAX_TAPS; ++t) taps.k[t] = t < K ? ker[t] : 0.f;
+  if (axis != 2) {
+    const int n_oth = axis == 0 ? od.y : od.x, n_out = axis == 0 ? od.x : od.y;
+    dim3 block(64, 4, 1), grid(div_up(od.z, 64), div_up(n_oth, 4), div_up(n_out, kConvChunk));
+    if (transpose)
+      conv_march_kernel<true><<<grid, block, 0, st>>>(in, out, idim, od, axis, taps, K, stride);
+    else
+      conv_march_kernel<false><<<grid, block, 0, st>>>(in, out, idim, od, axis, taps, K, stride);
+    UR_LAUNCH_CHECK();
+    return UR_OK;
+  }
   dim3 block(64, 4, 1), grid(div_up(od.z, 64), div_up(od.y, 4), od.x);
   if (transpose)
     conv_axis_kernel<true><<<grid, block, 0, st>>>(in, out, idim, od, axis, taps, K, stride);

@@ -14,6 +14,8 @@ namespace ur {
 int affine_pull(const float *, Dim3i, const float[12], float *, Dim3i, int, int, cudaStream_t);
 int affine_push(const float *, Dim3i, const float[12], float *, Dim3i, int, int, float,
                 cudaStream_t);
+int lattice_pull(const float *, Dim3i, const float[12], float *, Dim3i, cudaStream_t);
+int lattice_push(const float *, Dim3i, const float[12], float *, Dim3i, float, cudaStream_t);
 int conv_axis(const float *, Dim3i, float *, int, const float *, int, int, bool, cudaStream_t,
               Dim3i *);
 int apply_scaling(const float *, float *, Dim3i, float, int, cudaStream_t);
@@ -83,17 +85,23 @@ static int conv_down(const ur_proj *po, const float *in, Dim3i d, float *bufs[2]
   return UR_OK;
 }
 
-// C': transpose passes in the reverse order.
+// C': transpose passes in exactly the reverse order of conv_down (the z pass, whose accesses
+// are strided along the contiguous axis, then runs on the smallest volume in both directions).
 static int conv_up(const ur_proj *po, const float *in, Dim3i d, float *bufs[2],
                    cudaStream_t st, const float **result, Dim3i *rdim) {
   int order[3] = {0, 1, 2};
   for (int i = 0; i < 3; ++i)
     for (int j = i + 1; j < 3; ++j)
-      if (po->ratio[order[j]] < po->ratio[order[i]]) {
+      if (po->ratio[order[j]] > po->ratio[order[i]]) {
         int t = order[i];
         order[i] = order[j];
         order[j] = t;
       }
+  {
+    const int t = order[0];
+    order[0] = order[2];
+    order[2] = t;
+  }
   const float *cur = in;
   int flip = (in == bufs[0]) ? 1 : 0;
   for (int i = 0; i < 3; ++i) {
@@ -128,14 +136,19 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
   const Dim3i dsrc = sr ? make_dim(po->dim_yx) : dx;
   const float *cur;
   Dim3i d;
+  // identity rotation + integer shift: crop / zero-pad embed instead of gather / atomic scatter
+  const bool lat = ur_proj_is_lattice(po) != 0;
+  auto pull = [&](const float *src, float *dst) {
+    return lat ? lattice_pull(src, dy, po->mat, dst, dsrc, st)
+               : affine_pull(src, dy, po->mat, dst, dsrc, 1, 0, st);
+  };
 
   if (op == UR_OP_A) {
     bool any_pass = false;
     for (int a = 0; a < 3 && sr; ++a) any_pass |= !identity_pass(po, a);
     const bool need_scale = sr && po->scl != 0.f;
-    if (!any_pass && !need_scale)
-      return affine_pull(d_in, dy, po->mat, d_out, dsrc, 1, 0, st);
-    rc = affine_pull(d_in, dy, po->mat, bufs[0], dsrc, 1, 0, st);
+    if (!any_pass && !need_scale) return pull(d_in, d_out);
+    rc = pull(d_in, bufs[0]);
     if (rc) return rc;
     cur = bufs[0];
     d = dsrc;
@@ -156,7 +169,7 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
       cur = bufs[0];
     }
   } else {  // AtA
-    rc = affine_pull(d_in, dy, po->mat, bufs[0], dsrc, 1, 0, st);
+    rc = pull(d_in, bufs[0]);
     if (rc) return rc;
     cur = bufs[0];
     d = dsrc;
@@ -175,6 +188,7 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
     rc = conv_up(po, cur, d, bufs, st, &cur, &d);
     if (rc) return rc;
   }
+  if (lat) return lattice_push(cur, dsrc, po->mat, d_out, dy, scale, st);
   return affine_push(cur, dsrc, po->mat, d_out, dy, 1, 0, scale, st);
 }
 

@@ -104,6 +104,27 @@ __global__ void affine_grid_kernel(float *__restrict__ grid, Dim3i o, CoordAffin
   grid[3 * lin + 2] = cz;
 }
 
+// Lattice-aligned operators (identity rotation, integer translation): pull is a shifted crop,
+// push a shifted zero-pad embed -- one corner of weight exactly 1, a one-to-one mapping, so
+// the push needs no atomics.  o = grid of the coordinates, s = the volume they point into.
+template <bool PUSH>
+__global__ void lattice_shift_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                     Dim3i s, Dim3i o, int tx, int ty, int tz, float scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= o.z || j >= o.y) return;
+  const size_t lin = ((size_t)i * o.y + j) * o.z + k;
+  const int px = i + tx, py = j + ty, pz = k + tz;
+  const bool inside = px >= 0 && px < s.x && py >= 0 && py < s.y && pz >= 0 && pz < s.z;
+  const size_t q = ((size_t)px * s.y + py) * s.z + pz;
+  if (PUSH) {
+    if (inside) out[q] += scale * in[lin];
+  } else {
+    out[lin] = inside ? __ldg(in + q) : 0.f;
+  }
+}
+
 static inline void shape_for(const Dim3i &o, dim3 &grid, dim3 &block) {
   block = dim3(64, 4, 1);
   grid = dim3(div_up(o.z, 64), div_up(o.y, 4), o.x);
@@ -131,6 +152,28 @@ int affine_push(const float *in, Dim3i o, const float mat[12], float *out, Dim3i
   shape_for(o, grid, block);
   resample_kernel<CoordAffine, true>
       <<<grid, block, 0, st>>>(in, out, s, o, make_affine(mat), order, extrapolate, scale);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+int lattice_pull(const float *src, Dim3i s, const float mat[12], float *out, Dim3i o,
+                 cudaStream_t st) {
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  lattice_shift_kernel<false><<<grid, block, 0, st>>>(src, out, s, o, (int)lrintf(mat[3]),
+                                                      (int)lrintf(mat[7]), (int)lrintf(mat[11]),
+                                                      1.f);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+int lattice_push(const float *in, Dim3i o, const float mat[12], float *out, Dim3i s, float scale,
+                 cudaStream_t st) {
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  lattice_shift_kernel<true><<<grid, block, 0, st>>>(in, out, s, o, (int)lrintf(mat[3]),
+                                                     (int)lrintf(mat[7]), (int)lrintf(mat[11]),
+                                                     scale);
   UR_LAUNCH_CHECK();
   return UR_OK;
 }

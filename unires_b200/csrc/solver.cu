@@ -72,11 +72,16 @@ __global__ void __launch_bounds__(256) lhs_direct_kernel(const LhsArgs a) {
     for (int w = tid; w < nwords; w += blockDim.x * blockDim.y) dst[w] = src[w];
   }
   __syncthreads();
+  // a block owns one (64 z x 4 y) column tile and a contiguous range of x planes: the float64
+  // grid reduction (one same-address atomic per block) is paid O(SM count) times, not once
+  // per tile
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int x = blockIdx.z;
+  const int xc = (a.nx + gridDim.z - 1) / gridDim.z;
+  const int x_begin = blockIdx.z * xc, x_end = min(a.nx, x_begin + xc);
   double part = 0.0;
-  if (z < a.nz && y < a.ny) {
+  for (int x = x_begin; x < x_end; ++x) {
+    if (z >= a.nz || y >= a.ny) break;
     const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
     const size_t i = x * sx + y * sy + z;
     const float *__restrict__ v = a.v;
@@ -99,15 +104,15 @@ __global__ void __launch_bounds__(256) lhs_direct_kernel(const LhsArgs a) {
     const float val = data + a.rl2 * dtd;
     if (MODE == LHS_PLAIN) {
       a.out[i] = val;
-      part = (double)__fmul_rn(c, val);
+      part += (double)__fmul_rn(c, val);
     } else if (MODE == LHS_RESID) {
       const float rr = __fsub_rn(a.b[i], val);
       a.r[i] = rr;
       a.p[i] = rr;
-      part = (double)__fmul_rn(rr, rr);
+      part += (double)__fmul_rn(rr, rr);
     } else {
       const float e = __fmul_rn(__fsub_rn(val, 2.f * a.b[i]), c);
-      part = (double)e;
+      part += (double)e;
       if (a.update_p) {
         const float beta = (float)a.fin.st->beta;
         a.p[i] = __fadd_rn(__fmul_rn(beta, a.p[i]), a.r[i]);
@@ -468,7 +473,13 @@ static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
     }
   }
   P->block = dim3(64, 4, 1);
-  P->grid = dim3(div_up(A.nz, 64), div_up(A.ny, 4), A.nx);
+  {
+    const unsigned gx = div_up(A.nz, 64), gy = div_up(A.ny, 4);
+    const unsigned cap = (unsigned)sm_count() * 8;
+    unsigned xs = gx * gy >= cap ? 1 : (cap + gx * gy - 1) / (gx * gy);
+    if (xs > (unsigned)A.nx) xs = (unsigned)A.nx;
+    P->grid = dim3(gx, gy, xs);
+  }
   return UR_OK;
 }
 
