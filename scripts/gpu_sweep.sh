@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-(echo "== iso2_512"; timeout 600 python scripts/microbench_admm.py iso2_512 2>&1 | tail -5) 2>&1 | tee gpurun_out/admm_iso2.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_iso2.csv python scripts/lhs_once.py iso2_512 > gpurun_out/lhs_once.log 2>&1
-tail -1 gpurun_out/lhs_once.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12
+(for wl in denoise_181; do timeout 300 python scripts/microbench_admm.py $wl 2>&1 | tail -5; done
+echo "== cg denoise_181"; timeout 200 python scripts/microbench_cg.py denoise_181 20 5 2>&1 | tail -1
+) 2>&1 | tee gpurun_out/admm_pieces2.log

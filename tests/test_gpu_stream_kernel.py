@@ -203,3 +203,48 @@ def test_cg_fused_direction_update(cuda, case, stop, tol, kern):
     assert res[0][1] == res[1][1] == OO.cg.last_n_iter
     assert U.rel_l2(res[1][0], res[0][0]) < 1e-6
     assert U.rel_l2(res[1][0], xo) < U.REL_TOL
+
+
+@pytest.mark.parametrize('stop,tol', [('max_gain', 1e-3), ('residual', 1e-3), ('max_gain', 0.0)])
+@pytest.mark.parametrize('case', [
+    # dim_y (nz % 4 != 0), fov, thick axis (None = denoising), factor, scl
+    ((22, 26, 133), (18, 21, 121), 0, 4, 0.0),
+    ((19, 23, 131), (15, 18, 122), 2, 4, 0.1),
+    ((17, 21, 61), None, None, 1, 0.0),
+    ((13, 9, 181), None, 1, 2, 0.0),
+])
+def test_cg_padded_rows_for_odd_nz(cuda, case, stop, tol):
+    """nz not a multiple of 4 (BrainWeb: 181): the solve runs through the lean TMA kernel on
+    zero-padded rows; same trip count and iterate as the direct kernel and the oracle."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim, struct
+    dim_y, fov, axis, factor, scl = case
+    g = torch.Generator().manual_seed(21)
+    b = torch.rand(dim_y, generator=g) * 0.1
+    x0 = torch.rand(dim_y, generator=g)
+    if axis is None:
+        obs_o = P.Observation(torch.zeros(dim_y), torch.eye(4), tau=0.02, po=None)
+        rec_o = P.Recon(torch.zeros(dim_y), torch.eye(4), lam=0.3)
+        op = _project.LhsOperator([struct._input(tau=0.02)], struct._output(dim=dim_y, lam=0.3),
+                                  do=False, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+        lhs_o = lambda v: P.proj('AtA', v, [obs_o], rec_o, do=False, rho=1.3, vx_y=torch.ones(3))
+    else:
+        obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
+        op = _project.LhsOperator([obs_g], rec_g, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+        lhs_o = lambda v: P.proj('AtA', v, [obs_o], rec_o, rho=1.3, vx_y=torch.ones(3))
+    xo = x0.clone()
+    OO.cg(A=lhs_o, b=b, x=xo, max_iter=12, tolerance=tol, stop=stop)
+    res = {}
+    try:
+        for variant in (1, 0):
+            _reset()
+            _tune('lhs_variant', variant)
+            x = x0.clone().to(cuda)
+            optim.cg(A=op, b=b.to(cuda), x=x, max_iter=12, tolerance=tol, stop=stop)
+            res[variant] = (x, optim.cg.last.n_iter, _last_path())
+    finally:
+        _reset()
+    assert res[0][2] == 2 and res[1][2] == 0  # padded lean kernel vs direct kernel
+    assert res[0][1] == res[1][1] == OO.cg.last_n_iter
+    assert U.rel_l2(res[0][0], res[1][0]) < 1e-5
+    assert U.rel_l2(res[0][0], xo) < U.REL_TOL

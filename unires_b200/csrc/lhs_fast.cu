@@ -12,7 +12,7 @@ namespace ur {
 // lhs_stream.cu: cached cuTensorMapEncodeTiled of an (X, Y, Z) float volume with a box of one
 // plane tile (sz floats along z, `rows` rows, 1 plane along the march axis)
 bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
-                       CUtensorMap *out);
+                       CUtensorMap *out, int pitch);
 
 int fast_rpt = 0;     // rows per thread: 0 automatic, 1 | 2
 int fast_depth = 1;   // prefetch depth of the ring in plane pairs (>= 1)
@@ -26,8 +26,9 @@ static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 
 int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   using namespace fast;
   if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
-  if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
-  if ((long long)A.nx * A.ny * A.nz + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)
+  const int pitch = A.pitch > 0 ? A.pitch : A.nz;
+  if (pitch % 4 != 0 || pitch < A.nz || pitch - A.nz >= 4 || A.nz < 4) return UR_ERR_UNSUPPORTED;
+  if ((long long)A.nx * A.ny * pitch + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)
     return UR_ERR_UNSUPPORTED;
   if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
   if (!a16(A.rres) || !a16(A.p_out) || !a16(A.xup)) return UR_ERR_UNSUPPORTED;
@@ -81,8 +82,8 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.nm = march ? A.ny : A.nx;
   S.no = march ? A.nx : A.ny;
   S.nz = A.nz;
-  S.gs_m = march ? A.nz : A.ny * A.nz;
-  S.gs_o = march ? A.ny * A.nz : A.nz;
+  S.gs_m = march ? pitch : A.ny * pitch;
+  S.gs_o = march ? A.ny * pitch : pitch;
   const float iv_m = march ? A.ivy * A.ivy : A.ivx * A.ivx;
   const float iv_o = march ? A.ivx * A.ivx : A.ivy * A.ivy;
   const float iv_z = A.ivz * A.ivz;
@@ -125,13 +126,13 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   if (smem > 200u * 1024u) return UR_ERR_UNSUPPORTED;
 
   CUtensorMap map_v, map_r, map_x;
-  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_v))
+  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_v, pitch))
     return UR_ERR_UNSUPPORTED;
   map_r = map_v;
-  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r))
+  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r, pitch))
     return UR_ERR_UNSUPPORTED;
   map_x = map_v;
-  if (combine && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x))
+  if (combine && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))
     return UR_ERR_UNSUPPORTED;
   if (dry_run) return UR_OK;
 

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 
     // ---- per-thread constants of this column ----
     bool act[RPT];
+    const bool ztail = z + 4 > a.nz;  // padded rows (nz % 4 != 0): keep the pad voxels zero
     float4 Dq[RPT];
     float4 tm[RPT];        // POINT: tau x FOV mask per voxel; THICK_M: FOV mask of the row quad
     float czr[RPT][NRZ];   // THICK_Z: validity x scaling of the candidate low-res rows
@@ -562,6 +563,11 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               const float s_z = lft + rgt;
               const float S = fmaf(a.a_z, s_z, fmaf(a.a_o, s_o, a.a_m * s_m));
               val[k] = fmaf(cmpv(Dk, k), c, cmpv(dat, k)) - S;
+            }
+            if (ztail) {
+#pragma unroll
+              for (int k = 1; k < 4; ++k)
+                if (z + k >= a.nz) val[k] = 0.f;
             }
             if (act[i]) {
               const int gi = goff_u + i * a.gs_o;

@@ -671,10 +671,10 @@ static EncodeTiledFn encode_fn() {
 
 struct MapKey {
   const void *ptr;
-  int nx, ny, nz, sz, march_y, rows;
+  int nx, ny, nz, sz, march_y, rows, pitch;
   bool operator==(const MapKey &o) const {
     return ptr == o.ptr && nx == o.nx && ny == o.ny && nz == o.nz && sz == o.sz &&
-           march_y == o.march_y && rows == o.rows;
+           march_y == o.march_y && rows == o.rows && pitch == o.pitch;
   }
 };
 struct MapKeyHash {
@@ -685,17 +685,20 @@ struct MapKeyHash {
     h = h * 1315423911u + k.nz;
     h = h * 1315423911u + k.sz * 2 + k.march_y;
     h = h * 1315423911u + k.rows;
+    h = h * 1315423911u + k.pitch;
     return h;
   }
 };
 
 // 3-D tensor map over the (X, Y, Z) float volume with a box of one plane tile:
 // sz floats along z, `rows` rows along the non-marching axis, 1 plane along the march.
+// `pitch`: elements between consecutive z rows in memory (>= nz, multiple of 4).
 static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
-                           CUtensorMap *out) {
+                           CUtensorMap *out, int pitch = 0) {
+  if (pitch <= 0) pitch = nz;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{v, nx, ny, nz, sz, march_y, rows};
+  MapKey key{v, nx, ny, nz, sz, march_y, rows, pitch};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -705,7 +708,7 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
-  cuuint64_t gstr[2] = {(cuuint64_t)nz * 4, (cuuint64_t)nz * ny * 4};
+  cuuint64_t gstr[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * ny * 4};
   cuuint32_t box[3] = {(cuuint32_t)sz, march_y ? 1u : (cuuint32_t)rows,
                        march_y ? (cuuint32_t)rows : 1u};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -721,8 +724,8 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
 }
 
 bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
-                       CUtensorMap *out) {
-  return get_tensor_map(v, nx, ny, nz, sz, march_y, rows, out);
+                       CUtensorMap *out, int pitch) {
+  return get_tensor_map(v, nx, ny, nz, sz, march_y, rows, out, pitch);
 }
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }

@@ -485,8 +485,11 @@ static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
 
 static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
 
+static int pitch4(const ur_lhs *lhs) { return (lhs->dim_y[2] + 3) / 4 * 4; }
+
+// one volume with its z rows padded to a multiple of 4 elements (>= the dense volume)
 static size_t vol_bytes(const ur_lhs *lhs) {
-  return align_up((size_t)lhs->dim_y[0] * lhs->dim_y[1] * lhs->dim_y[2] * sizeof(float));
+  return align_up((size_t)lhs->dim_y[0] * lhs->dim_y[1] * pitch4(lhs) * sizeof(float));
 }
 
 // lhs workspace: [counter 256B | partials | acc volume (general) | proj ws]
@@ -588,6 +591,10 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     int rc = UR_ERR_UNSUPPORTED;
     if (variant != 2) rc = lhs_fast_launch(mode, A, false, st);
     g_last_path = 2;
+    if (rc == UR_ERR_UNSUPPORTED && A.pitch > 0 && A.pitch != A.nz) {
+      set_error("padded volume: only the lean TMA kernel understands a row pitch");
+      return UR_ERR_CUDA;
+    }
     if (rc == UR_ERR_UNSUPPORTED) {
       rc = lhs_stream_launch(mode, A, 0, st);
       g_last_path = 1;
@@ -603,6 +610,10 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
       if (rc == UR_ERR_UNSUPPORTED) set_error("fused direction update: streaming kernel n/a");
       return rc;
     }
+  }
+  if (A.pitch > 0 && A.pitch != A.nz) {
+    set_error("padded volume: only the lean TMA kernel understands a row pitch");
+    return UR_ERR_CUDA;
   }
   g_last_path = 0;
   switch (mode) {
@@ -625,12 +636,13 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   return UR_OK;
 }
 
-// CG workspace: [CgState | lhs ws | r | p | Ap | p2]   (p2: second direction buffer of the
-// fused direction update, which cannot run in place because neighbouring CTAs re-read halos)
+// CG workspace: [CgState | lhs ws | r | p | Ap | p2 | b_pad | x_pad]   (p2: second direction
+// buffer of the fused direction update, which cannot run in place because neighbouring CTAs
+// re-read halos; b_pad / x_pad: zero-padded copies of b and x when nz is not a multiple of 4)
 struct CgWs {
   CgState *st;
   void *lhs;
-  float *r, *p, *Ap, *p2;
+  float *r, *p, *Ap, *p2, *b_pad, *x_pad;
 };
 
 static size_t cg_state_bytes() { return align_up(sizeof(CgState)); }
@@ -649,6 +661,10 @@ static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   w.Ap = (float *)c;
   c += vol_bytes(lhs);
   w.p2 = (float *)c;
+  c += vol_bytes(lhs);
+  w.b_pad = (float *)c;
+  c += vol_bytes(lhs);
+  w.x_pad = (float *)c;
   return w;
 }
 
@@ -792,7 +808,8 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
 extern "C" size_t ur_cg_workspace_bytes(const ur_lhs *lhs) {
   LhsPlan P;
   if (make_plan(lhs, &P)) return 0;
-  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + 4 * vol_bytes(lhs);
+  const int extra = lhs->dim_y[2] % 4 != 0 ? 2 : 0;  // padded copies of b and x
+  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + (4 + extra) * vol_bytes(lhs);
 }
 
 extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_ws,
@@ -810,10 +827,41 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
   cudaStream_t st = (cudaStream_t)stream;
   const int stop = opts->tolerance > 0 ? opts->stop_rule : UR_STOP_NONE;
   const double tol = opts->tolerance;
-  const size_t n = (size_t)lhs->dim_y[0] * lhs->dim_y[1] * lhs->dim_y[2];
+  size_t n = (size_t)lhs->dim_y[0] * lhs->dim_y[1] * lhs->dim_y[2];
 
   CgWs cw = carve_cg_ws(lhs, P, d_ws);
   LhsWs lw = carve_lhs_ws(lhs, P, cw.lhs);
+  // nz not a multiple of 4 (most real scans): the TMA kernels need 16-byte row pitches, so the
+  // solve runs on zero-padded copies of b and x (pads stay exactly zero through every kernel:
+  // the loads are zero-filled past nz by the tensor map, the matvec masks its pad outputs)
+  // and x is copied back at the end -- 3 strided copies per solve instead of the direct kernel.
+  float *const d_x_user = d_x;
+  bool padded = false;
+  const int nz = lhs->dim_y[2], pitch = pitch4(lhs);
+  const size_t rows = (size_t)lhs->dim_y[0] * lhs->dim_y[1];
+  if (nz % 4 != 0 && nz >= 4 && P.n_general == 0 && g_lhs_variant == 0 && opts->variant == 0) {
+    LhsArgs T = P.args;
+    T.pitch = pitch;
+    T.v = cw.x_pad;
+    T.b = cw.b_pad;
+    T.r = cw.r;
+    T.p = cw.p;
+    T.out = cw.Ap;
+    padded = lhs_fast_launch(LHS_RESID, T, true, st) == UR_OK &&
+             lhs_fast_launch(LHS_PLAIN, T, true, st) == UR_OK &&
+             lhs_fast_launch(LHS_ENERGY, T, true, st) == UR_OK;
+  }
+  if (padded) {
+    UR_CUDA_CHECK(cudaMemsetAsync(cw.b_pad, 0, 2 * vol_bytes(lhs), st));  // b_pad and x_pad
+    UR_CUDA_CHECK(cudaMemcpy2DAsync(cw.b_pad, (size_t)pitch * 4, d_b, (size_t)nz * 4,
+                                    (size_t)nz * 4, rows, cudaMemcpyDeviceToDevice, st));
+    UR_CUDA_CHECK(cudaMemcpy2DAsync(cw.x_pad, (size_t)pitch * 4, d_x, (size_t)nz * 4,
+                                    (size_t)nz * 4, rows, cudaMemcpyDeviceToDevice, st));
+    P.args.pitch = pitch;
+    d_b = cw.b_pad;
+    d_x = cw.x_pad;
+    n = rows * pitch;
+  }
   UR_CUDA_CHECK(cudaMemsetAsync(cw.st, 0, cg_state_bytes() + 256, st));  // state + ticket
   const int *done = &cw.st->done;
   const GridReduce gr{lw.partials, lw.counter};
@@ -930,6 +978,9 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     cg_final_x_kernel<<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.p2, n, cw.st);
     UR_LAUNCH_CHECK();
   }
+  if (padded)
+    UR_CUDA_CHECK(cudaMemcpy2DAsync(d_x_user, (size_t)nz * 4, d_x, (size_t)pitch * 4,
+                                    (size_t)nz * 4, rows, cudaMemcpyDeviceToDevice, st));
   return UR_OK;
 }
 

@@ -79,6 +79,8 @@ enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2, LHS_COMBINE = 3 };
 
 struct LhsArgs {
   int nx, ny, nz;
+  int pitch;  // elements between z rows (0 / nz: dense).  > nz only with the lean TMA kernel:
+              // volumes whose nz is not a multiple of 4 are solved in a zero-padded copy
   float ivx, ivy, ivz;
   float rl2;      // rho * lam^2
   float w_ident;  // sum of tau over identity observations (do_proj = 0)
