@@ -204,10 +204,13 @@ __global__ void __launch_bounds__(256)
 // per-element arithmetic and its order are unchanged, hence bitwise identical iterates):
 //   cg_update_r_kernel : r -= alpha Ap ; sum r*r                      (12 B/voxel)
 //   cg_update_xp_kernel: x += alpha p ; p = beta p + r                (20 B/voxel)
+// `reverse`: sweep the volume from its end to its start.  The matvec that precedes this kernel
+// leaves the most recently written part of Ap in L2; which end that is depends on its march.
 template <int VEC>
 __global__ void __launch_bounds__(256)
     cg_update_r_kernel(float *__restrict__ r, const float *__restrict__ Ap, size_t n,
-                       const double *alpha_ptr, const int *done, GridReduce gr, FinalizeArgs fin) {
+                       const double *alpha_ptr, const int *done, GridReduce gr, FinalizeArgs fin,
+                       int reverse) {
   __shared__ double s_red[kMaxWarps];
   if (done && *done) return;
   const float alpha = (float)(*alpha_ptr);
@@ -217,16 +220,31 @@ __global__ void __launch_bounds__(256)
     const size_t n4 = n / 4;
     float4 *r4 = reinterpret_cast<float4 *>(r);
     const float4 *A4 = reinterpret_cast<const float4 *>(Ap);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-      float4 rv = r4[i];
-      const float4 av = A4[i];
-      rv.x = __fsub_rn(rv.x, __fmul_rn(alpha, av.x));
-      rv.y = __fsub_rn(rv.y, __fmul_rn(alpha, av.y));
-      rv.z = __fsub_rn(rv.z, __fmul_rn(alpha, av.z));
-      rv.w = __fsub_rn(rv.w, __fmul_rn(alpha, av.w));
-      r4[i] = rv;
-      part += (double)__fmul_rn(rv.x, rv.x) + (double)__fmul_rn(rv.y, rv.y) +
-              (double)__fmul_rn(rv.z, rv.z) + (double)__fmul_rn(rv.w, rv.w);
+    constexpr int U = 4;  // independent quads per thread and trip: 2 U loads in flight
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+      float4 rv[U], av[U];
+      size_t idx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = i0 + u * stride;
+        idx[u] = reverse ? n4 - 1 - i : i;
+        if (i < n4) {
+          rv[u] = r4[idx[u]];
+          av[u] = A4[idx[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u * stride >= n4) break;
+        float4 q = rv[u];
+        q.x = __fsub_rn(q.x, __fmul_rn(alpha, av[u].x));
+        q.y = __fsub_rn(q.y, __fmul_rn(alpha, av[u].y));
+        q.z = __fsub_rn(q.z, __fmul_rn(alpha, av[u].z));
+        q.w = __fsub_rn(q.w, __fmul_rn(alpha, av[u].w));
+        r4[idx[u]] = q;
+        part += (double)__fmul_rn(q.x, q.x) + (double)__fmul_rn(q.y, q.y) +
+                (double)__fmul_rn(q.z, q.z) + (double)__fmul_rn(q.w, q.w);
+      }
     }
   } else {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -542,6 +560,7 @@ extern int stream_pf;           // lhs_stream.cu
 extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock;  // lhs_fast.cu
 static int g_lhs_variant = 0;
 static int g_cg_fuse = 1;
+static int g_r_reverse = 0;   // residual update sweeps the volume end -> start
 static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
 
 struct MatvecProfile {
@@ -686,6 +705,8 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_rpt = (value == 1 || value == 2) ? value : 0;
   } else if (!strcmp(name, "fast_depth")) {
     fast_depth = value < 1 ? 1 : value;
+  } else if (!strcmp(name, "r_reverse")) {
+    g_r_reverse = value != 0;
   } else if (!strcmp(name, "fast_pfd")) {
     fast_pfd = value < 0 ? 0 : value;
   } else if (!strcmp(name, "fast_lock")) {
@@ -935,7 +956,8 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     }
     if (fuse) {  // r -= alpha Ap ; beta = rz'/rz
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
-      cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+      cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
+                                                     g_r_reverse);
       UR_LAUNCH_CHECK();
       continue;
     }
@@ -951,11 +973,13 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     } else {  // r -= alpha Ap ; beta = rz'/rz   then   x += alpha p ; p = beta p + r
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
       if (vec) {
-        cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+        cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
+                                                     g_r_reverse);
         UR_LAUNCH_CHECK();
         cg_update_xp_kernel<4><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
       } else {
-        cg_update_r_kernel<1><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin);
+        cg_update_r_kernel<1><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
+                                                       0);
         UR_LAUNCH_CHECK();
         cg_update_xp_kernel<1><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
       }
