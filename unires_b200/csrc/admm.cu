@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, 2)
   if (z >= g.nz || y >= g.ny) return;
   const size_t sy = g.nz, sx = (size_t)g.ny * g.nz, n = sx * g.nx;
   const size_t i = x * sx + y * sy + z;
-  float gk[CT][3][V], wk[CT][3][V];  // u = w / rho + g is re-formed in the second sweep
+  float gk[CT][3][V], wk[CT][3][V], uk[CT][3][V];
   float s2[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) s2[k] = 0.f;
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256, 2)
           float u = gr[d];
           if (MODE != JTV_PRIOR) u = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), u);
           gk[c][d][k] = gr[d];
+          uk[c][d][k] = u;
           e = d == 0 ? __fmul_rn(u, u) : __fadd_rn(e, __fmul_rn(u, u));
         }
         s2[k] = __fadd_rn(s2[k], e);
@@ -236,7 +237,8 @@ __global__ void __launch_bounds__(256, 2)
       float zv[V], wn[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float uu = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), gk[c][d][k]);
+        float uu = uk[c][d][k];
+        if (MODE == JTV_APPLY) uu = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), gk[c][d][k]);
         zv[k] = __fmul_rn(f[k], uu);
         wn[k] = __fadd_rn(wk[c][d][k], __fmul_rn(g.rho, __fsub_rn(gk[c][d][k], zv[k])));
       }
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(256, 2)
     }
   }
 }
+
 
 static bool ptr16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
