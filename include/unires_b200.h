@@ -256,6 +256,21 @@ int ur_nll_prior_energy(const float *const *d_y, float *d_e, int n_channels,
                         int accumulate, ur_stream stream);
 int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream);
 
+/* ---------------------------------------------------------------- even/odd slice
+ * scaling update, _update_scaling (unires/_update.py:270-393).
+ * ur_scaling_sums: the five masked float64 sums of one Gauss-Newton step over
+ * the voxels with x != 0 (d_x observed, d_y = A y with the current scaling;
+ * p = parity of the slice index along `axis`):
+ *   d_out[0] = sum (x-y)^2   d_out[1+p] = sum y (x-y)   d_out[3+p] = sum y^2
+ * (unires/_update.py:321 log-likelihood, :334-339 gradient and Hessian; the
+ * reference's "odd" slices are ::2, i.e. p = 0).  ur_scale_slices: out = f_even
+ * * in on slices ::2 and f_odd * in on slices 1::2 (_apply_scaling with the
+ * factors exp(+-s) formed by the caller, unires/_update.py:361); in place ok. */
+int ur_scaling_sums(const float *d_x, const float *d_y, const int32_t dim[3], int axis,
+                    double *d_out, ur_stream stream);
+int ur_scale_slices(const float *d_in, float *d_out, const int32_t dim[3], float f_even,
+                    float f_odd, int axis, ur_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

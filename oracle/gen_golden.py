@@ -132,9 +132,11 @@ def main():
               '%.0f KB' % (os.path.getsize(path) / 1024))
 
 
-if __name__ == '__main__' and '--fit' not in sys.argv:
+if __name__ == '__main__' and '--fit' not in sys.argv and '--scaling' not in sys.argv:
     main()
     main_fit()
+    main_fit(scaling=True)
+    main_scaling()
 
 
 # ---------------------------------------------------------------------------
@@ -144,11 +146,18 @@ FIT_RECIPE = dict(base='sr3_256', dim_y=(16, 18, 16), n_channels=2, sd=25.0, scl
                   max_iter=70)
 
 
-def prepare_fit(sc, reference=False):
+FIT_SCALING_RECIPE = dict(base='thickz2_256', dim_y=(16, 14, 20), n_channels=2, sd=15.0, scl=0.1,
+                          rigid=None, max_iter=40)
+
+
+def prepare_fit(sc, reference=False, scaling=False):
     """Settings of the fit fixture (and the fields only the reference's fit touches)."""
     s = sc.sett
-    s.max_iter, s.tolerance, s.reg_scl, s.sched_num = FIT_RECIPE['max_iter'], 1e-4, 4.0, 3
-    s.clean_fov, s.scaling, s.unified_rigid, s.rigid_mod = True, False, False, 1
+    recipe = FIT_SCALING_RECIPE if scaling else FIT_RECIPE
+    s.max_iter, s.tolerance, s.reg_scl, s.sched_num = recipe['max_iter'], 1e-4, 4.0, 3
+    s.clean_fov, s.scaling, s.unified_rigid, s.rigid_mod = True, scaling, False, 1
+    if scaling:  # the data carry exp(+-0.1); the fit starts from 0 and has to find it
+        prepare_scaling(sc, 0.0)
     if reference:
         from oracle.nitorch_shim.spatial import affine_basis
         s.rigid_basis = affine_basis(group='SE', dtype=torch.float64)
@@ -161,12 +170,13 @@ def prepare_fit(sc, reference=False):
     return sc
 
 
-def main_fit():
+def main_fit(scaling=False):
     from oracle.adapters import reference_namespaces
     from oracle.load_reference import load_reference
     ref = load_reference()
     ops, structs = reference_namespaces()
-    sc = prepare_fit(build(FIT_RECIPE, ops, structs), reference=True)
+    recipe = FIT_SCALING_RECIPE if scaling else FIT_RECIPE
+    sc = prepare_fit(build(recipe, ops, structs), reference=True, scaling=scaling)
     obj_rows = []
     orig = ref.run._update_admm
 
@@ -180,13 +190,58 @@ def main_fit():
         dat_y = ref.run.fit(sc.x, sc.y, sc.sett)[0]
     finally:
         ref.run._update_admm = orig
-    out = {'recipe': json.dumps(FIT_RECIPE), 'dat_y': dat_y.numpy(),
-           'obj': torch.stack(obj_rows).numpy(), 'n_iter': np.int32(len(obj_rows))}
-    path = os.path.join(GOLDEN_DIR, 'fit_sr2.npz')
+    out = {'recipe': json.dumps(recipe), 'dat_y': dat_y.numpy(),
+           'obj': torch.stack(obj_rows).numpy(), 'n_iter': np.int32(len(obj_rows)),
+           'scl': np.array([float(o.po.scl) for xc in sc.x for o in xc])}
+    path = os.path.join(GOLDEN_DIR, 'fit_scaling.npz' if scaling else 'fit_sr2.npz')
     np.savez_compressed(path, **out)
-    print('fit_sr2 n_iter', len(obj_rows), 'obj', obj_rows[0][0].item(), '->', obj_rows[-1][0].item(),
+    print(os.path.basename(path), 'scl', out['scl'].tolist(), 'n_iter', len(obj_rows), 'obj', obj_rows[0][0].item(), '->', obj_rows[-1][0].item(),
           '%.0f KB' % (os.path.getsize(path) / 1024))
+
+
+# ---------------------------------------------------------------------------
+# even/odd slice-scaling update (unires/_update.py::_update_scaling) fixture
+# ---------------------------------------------------------------------------
+SCALING_CASES = {
+    # recipe name -> initial po.scl handed to the update (the data were simulated with recipe scl)
+    'thickz2_scl': 0.0,
+    'sr3_thick_xyz': 0.03,
+}
+SCALING_STEPS = 3
+
+
+def prepare_scaling(sc, scl0):
+    for xc in sc.x:
+        for o in xc:
+            o.po.scl = torch.tensor(scl0, dtype=torch.float32)
+    return sc
+
+
+def main_scaling():
+    from oracle.adapters import reference_namespaces
+    from oracle.load_reference import load_reference
+    ref = load_reference()
+    ops, structs = reference_namespaces()
+    out = {}
+    for name, scl0 in SCALING_CASES.items():
+        torch.manual_seed(0)
+        sc = prepare_fit(build(RECIPES[name], ops, structs), reference=True)
+        sc.sett.max_iter = 512
+        prepare_scaling(sc, scl0)
+        scl, sll = [], []
+        for _ in range(SCALING_STEPS):
+            _, s = ref._update._update_scaling(sc.x, sc.y, sc.sett, max_niter_gn=1,
+                                               num_linesearch=6, verbose=0)
+            scl.append([float(o.po.scl) for xc in sc.x for o in xc])
+            sll.append(float(s))
+        out[name + '_scl'] = np.array(scl, dtype=np.float64)
+        out[name + '_sll'] = np.array(sll, dtype=np.float64)
+        print('scaling', name, scl, sll)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'scaling_update.npz'), **out)
 
 
 if __name__ == '__main__' and '--fit' in sys.argv:
     main_fit()
+    main_fit(scaling=True)
+if __name__ == '__main__' and '--scaling' in sys.argv:
+    main_scaling()

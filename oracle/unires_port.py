@@ -15,6 +15,7 @@ Reference lines restated (relative to /root/reference):
   admm_aux / step_size       unires/_update.py:17-64
   compute_nll                unires/_update.py:396-427
   update_admm                unires/_update.py:105-195
+  even_odd / update_scaling  unires/_update.py:430-445, 270-393
 """
 import math
 import types
@@ -103,13 +104,16 @@ def proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0,
 
 
 def apply_scaling(dat, scl, dim):
-    """exp(+scl) on even, exp(-scl) on odd slices along spatial axis dim (:9-24)."""
+    """exp(+scl) on even, exp(-scl) on odd slices along spatial axis dim (:9-24).
+    The factors are formed in scl's own dtype (float64 once _update_scaling has run) and only
+    then rounded to the data type, like torch's `0-dim tensor * volume`."""
+    scl = torch.as_tensor(scl)
     n = dat.shape[dat.dim() - 3 + dim]
-    sign = torch.ones(n, dtype=dat.dtype)
-    sign[1::2] = -1
+    factor = torch.exp(scl).to(dat.dtype).repeat(n)
+    factor[1::2] = torch.exp(-scl).to(dat.dtype)
     shape = [1] * dat.dim()
     shape[dat.dim() - 3 + dim] = n
-    return dat * torch.exp(scl * sign).reshape(shape)
+    return dat * factor.reshape(shape)
 
 
 def proj_apply(operator, dat, po, method='super-resolution', bound='zero',
@@ -296,6 +300,8 @@ def fit(x, y, sett):
                 break
         else:
             countdown0 = 6
+        if getattr(sett, 'scaling', False):  # unires/run.py:115-122
+            x, _ = update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=6)
         if cnt_scl + 1 < len(reg) and cnt_scl_iter > 16 and gain.abs() < 1e-3:
             countdown1 -= 1
             if countdown1 == 0:
@@ -323,3 +329,65 @@ def fit(x, y, sett):
         yc.dat.clamp_(mn, mx)
         out.append(yc.dat[..., None].clone())
     return torch.cat(out, dim=3), obj[:n_done], n_done, tmp
+
+
+# ----------------------------------------------------------------------------
+# even/odd slice-scaling update  (unires/_update.py:270-393, 430-445)
+# ----------------------------------------------------------------------------
+def even_odd(dat, which, dim):
+    """Upstream's naming: 'odd' = slices 0, 2, 4, ...; 'even' = slices 1, 3, 5, ... (:430-445)."""
+    start = 0 if which == 'odd' else 1
+    index = [slice(None)] * 3
+    index[dim] = slice(start, None, 2)
+    return dat[tuple(index)]
+
+
+def update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=4):
+    """One Gauss-Newton update (with backtracking) of every observation's po.scl.
+    Returns (x, sll).  The operator's rigid matrix is po.rigid (upstream rebuilds it from
+    rigid_q, which is what _proj_info stored there)."""
+    sll = torch.tensor(0, dtype=F64)
+    for c in range(len(x)):
+        for obs in x[c]:
+            if obs.ct:
+                continue
+            po = obs.po
+            thick, tau, scl = int(po.dim_thick), obs.tau, po.scl
+            dat_x = obs.dat
+            msk = dat_x != 0
+            m_odd, m_even = even_odd(msk, 'odd', thick), even_odd(msk, 'even', thick)
+            x_odd, x_even = even_odd(dat_x, 'odd', thick)[m_odd], even_odd(dat_x, 'even', thick)[m_even]
+            # reconstruction in observation space: pull -> slice profile -> scaling (:312-318)
+            vox = torch.linalg.solve(po.mat_y, po.rigid @ po.mat_yx)
+            grid = S.affine_grid(vox.to(torch.float32), po.dim_yx)[None]
+            dat_y = S.grid_pull(y[c].dat[None, None], grid, bound=sett.bound, extrapolate=False,
+                                interpolation=sett.interpolation)
+            dat_y = F.conv3d(dat_y, po.smo_ker, stride=po.ratio)[0, 0]
+            dat_y = apply_scaling(dat_y, scl, thick)
+
+            def loglik(d):
+                return 0.5 * tau * torch.sum((dat_x[msk] - d[msk]) ** 2, dtype=F64)
+
+            ll = torch.tensor(0, dtype=F64)
+            for _ in range(max_niter_gn):
+                ll = loglik(dat_y)
+                y_odd, y_even = even_odd(dat_y, 'odd', thick)[m_odd], even_odd(dat_y, 'even', thick)[m_even]
+                grad = tau * (torch.sum(y_even * (x_even - y_even), dtype=F64)
+                              - torch.sum(y_odd * (x_odd - y_odd), dtype=F64))
+                hess = tau * (torch.sum(y_even ** 2, dtype=F64) + torch.sum(y_odd ** 2, dtype=F64))
+                step = grad / hess
+                old_scl, old_ll = scl.clone(), ll.clone()
+                armijo = torch.tensor(1.0, dtype=old_scl.dtype)
+                if num_linesearch == 0:
+                    scl = old_scl - armijo * step
+                for _ls in range(num_linesearch):
+                    scl = old_scl - armijo * step
+                    dat_y = apply_scaling(dat_y, scl - old_scl, thick)  # cumulative, as upstream
+                    ll = loglik(dat_y)
+                    if ll < old_ll:
+                        break
+                    scl, ll = old_scl, old_ll
+                    armijo = armijo * 0.5
+            po.scl = scl
+            sll = sll + ll
+    return x, sll

@@ -44,9 +44,35 @@ def test_fit_matches_reference_fixture(cuda):
     assert R.shape == (2, 4, 4) and pth == [] and label is None
 
 
+def test_fit_with_scaling_matches_reference_fixture(cuda):
+    """sett.scaling: the even/odd slice scaling exp(+-0.1) of the simulated data is recovered
+    from 0 by the Gauss-Newton update interleaved with the ADMM iterations (unires/run.py:
+    115-122); trajectory against the reference's own fit."""
+    from unires_b200 import run
+    g = np.load(U.GOLDEN_DIR + '/fit_scaling.npz', allow_pickle=False)
+    recipe = json.loads(str(g['recipe']))
+    sc = gen_golden.prepare_fit(U.build(recipe, *U.port_namespaces()), scaling=True)
+    x, y, sett = U.to_device(sc, cuda)
+    for k in ('max_iter', 'tolerance', 'reg_scl', 'sched_num', 'clean_fov', 'scaling',
+              'unified_rigid', 'rigid_mod'):
+        setattr(sett, k, getattr(sc.sett, k))
+    for c in range(len(y)):
+        y[c].lam0 = torch.tensor(float(sc.y[c].lam0), device=cuda)
+        for n, o in enumerate(x[c]):
+            o.dim = tuple(sc.x[c][n].dat.shape)
+            o.tau = torch.tensor(float(sc.x[c][n].tau), device=cuda)
+    dat_y = run.fit(x, y, sett)[0]
+    last = run.fit.last
+    assert last['n_iter'] == int(g['n_iter'])
+    scl = [float(o.po.scl) for xc in x for o in xc]
+    assert np.allclose(scl, g['scl'], rtol=2e-3), (scl, g['scl'].tolist())
+    assert np.allclose(last['obj'].cpu().numpy(), g['obj'], rtol=1e-3)
+    assert U.rel_l2(dat_y, g['dat_y']) < 1e-3
+
+
 def test_fit_rejects_out_of_scope_updates(cuda):
     from unires_b200 import run, struct
     s = struct.settings()
-    s.scaling = True
+    s.unified_rigid = True
     with pytest.raises(NotImplementedError):
         run.fit([], [], s)

@@ -213,3 +213,42 @@ def test_rhs_fused_vs_general_and_oracle(cuda, name):
             out[key] = b
             assert U.rel_l2(b, ref) < 1e-5, (name, c, key)
         assert U.rel_l2(out['fused'], out['general']) < 1e-5
+
+
+@pytest.mark.parametrize('name', ['thickz2_scl', 'sr3_thick_xyz'])
+def test_update_scaling_vs_golden_and_oracle(cuda, name):
+    """_update_scaling on the GPU (ur_scaling_sums + ur_scale_slices) against the reference's
+    fixture and the oracle port: same line-search decisions, scl and log-likelihood."""
+    from unires_b200 import _update
+    g = np.load(U.GOLDEN_DIR + '/scaling_update.npz', allow_pickle=False)
+    scl0 = gen_golden.SCALING_CASES[name]
+    sc = gen_golden.prepare_scaling(U.build(gen_golden.RECIPES[name], *U.port_namespaces()), scl0)
+    x, y, sett = U.to_device(sc, cuda)
+    for k in range(gen_golden.SCALING_STEPS):
+        x, sll = _update._update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=6)
+        got = [float(o.po.scl) for xc in x for o in xc]
+        want = g[name + '_scl'][k].tolist()
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-6), (k, got, want)
+        assert abs(float(sll) - float(g[name + '_sll'][k])) < 1e-5 * float(g[name + '_sll'][k])
+
+
+def test_scaling_sums_kernel(cuda):
+    """The five masked even/odd sums against torch float64 on every axis."""
+    from unires_b200 import _lib
+    from unires_b200._lib import lib, check, ptr, i3, stream
+    g = torch.Generator().manual_seed(4)
+    dim = (9, 14, 11)
+    xx = torch.rand(dim, generator=g)
+    xx[xx < 0.2] = 0.0
+    yy = torch.rand(dim, generator=g)
+    out = torch.zeros(5, dtype=torch.float64, device=cuda)
+    xg, yg = xx.to(cuda), yy.to(cuda)
+    for axis in range(3):
+        check(lib.ur_scaling_sums(ptr(xg), ptr(yg), i3(dim), axis, ptr(out), stream()))
+        m = xx != 0
+        want = [torch.sum(((xx - yy) ** 2)[m], dtype=torch.float64).item()]
+        for fn in (lambda a, b: b * (a - b), lambda a, b: b * b):
+            for which in ('odd', 'even'):
+                xs, ys, ms = (P.even_odd(t, which, axis) for t in (xx, yy, m))
+                want.append(torch.sum(fn(xs, ys)[ms], dtype=torch.float64).item())
+        assert np.allclose(out.cpu().numpy(), want, rtol=1e-12)

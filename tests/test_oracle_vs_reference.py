@@ -46,3 +46,22 @@ def test_step_size_matches_reference():
     sr = U.build(recipe, *reference_namespaces())
     sr.sett.rho = None
     assert torch.equal(P.step_size(sr.x, sr.y, sr.sett), ref._update._step_size(sr.x, sr.y, sr.sett))
+
+
+@pytest.mark.parametrize('name', ['thickz2_scl', 'sr3_thick_xyz'])
+def test_port_update_scaling_matches_reference_bitwise(name):
+    """Even/odd slice-scaling Gauss-Newton update (unires/_update.py:270-393)."""
+    from oracle import gen_golden
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    scl0 = gen_golden.SCALING_CASES[name]
+    sp = gen_golden.prepare_scaling(U.build(gen_golden.RECIPES[name], *U.port_namespaces()), scl0)
+    sr = gen_golden.prepare_scaling(gen_golden.prepare_fit(
+        U.build(gen_golden.RECIPES[name], *reference_namespaces()), reference=True), scl0)
+    for _ in range(2):
+        _, sll_p = P.update_scaling(sp.x, sp.y, sp.sett, max_niter_gn=1, num_linesearch=6)
+        _, sll_r = ref._update._update_scaling(sr.x, sr.y, sr.sett, max_niter_gn=1, num_linesearch=6,
+                                               verbose=0)
+        assert float(sll_p) == float(sll_r)
+        for xp, xr in zip(sp.x, sr.x):
+            assert float(xp[0].po.scl) == float(xr[0].po.scl)

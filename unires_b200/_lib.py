@@ -84,6 +84,10 @@ _SIGNATURES = {
                                       C.POINTER(C.c_double)]),
     'ur_tune': (C.c_int, [C.c_char_p, C.c_int]),
     'ur_last_lhs_path': (C.c_int, []),
+    'ur_scaling_sums': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    'ur_scale_slices': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_float,
+                                  C.c_float, C.c_int, C.c_void_p]),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_dtd': (C.c_int, [_p, _p, _i3, _f3, _p]),

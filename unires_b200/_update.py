@@ -2,6 +2,7 @@
 arguments, in-place behaviour and return values as unires/_update.py:
 
     _admm_aux      unires/_update.py:17-32
+    _update_scaling unires/_update.py:270-393 (even/odd slice scaling, Gauss-Newton)
     _step_size     unires/_update.py:35-64
     _compute_nll   unires/_update.py:396-427
     _update_admm   unires/_update.py:105-195
@@ -310,3 +311,68 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
                                          lam, i3(dim), f3(vx), rho_f, alpha, stream())),
         group)
     return y, z, w, tmp, obj
+
+
+def _update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=4, verbose=0):
+    """Gauss-Newton update of the even/odd slice scaling `po.scl` of every observation
+    (unires/_update.py:270-393; derivation in derivations/scaling.m).  Returns (x, sll).
+
+    Per observation: dat_y = A y with the current scaling (pull -> slice profile -> exp(+-s)),
+    then over the voxels with x != 0 the five float64 sums of `ur_scaling_sums` give the
+    log-likelihood 0.5 tau sum (x - y)^2, the gradient tau (sum_e y (x-y) - sum_o y (x-y)) and
+    the Fisher Hessian tau (sum_e y^2 + sum_o y^2), where -- as upstream -- "odd" are the slices
+    ::2 and "even" the slices 1::2 along the thick axis.  The line search rescales dat_y in
+    place by exp(+-(s - s_old)) at every trial, cumulatively, exactly like the reference.
+    One host synchronisation per trial (the reference's `if ll < old_ll`)."""
+    import math
+    from ._project import _proj_apply
+    dev = y[0].dat.device
+    sums = torch.zeros(5, dtype=torch.float64, device=dev)
+    sll = 0.0
+    for c in range(len(x)):
+        for obs in x[c]:
+            if getattr(obs, 'ct', False):
+                continue
+            po = obs.po
+            thick = int(po.dim_thick)
+            tau = float(np.float32(_hs(obs.tau)))
+            scl = _hs(po.scl) if po.scl is not None else 0.0
+            dat_x = require_cuda_f32(obs.dat, 'x.dat')
+            dim_x = i3(tuple(dat_x.shape))
+            dat_y = _proj_apply('A', y[c].dat[None, None, ...], po, method='super-resolution',
+                                bound=sett.bound, interpolation=sett.interpolation)[0, 0]
+            dat_y = require_cuda_f32(dat_y, 'A y')
+            if scl == 0.0:
+                dat_y = dat_y.clone()  # rescaled in place below; A may have returned a view
+
+            def measure():
+                check(lib.ur_scaling_sums(ptr(dat_x), ptr(dat_y), dim_x, thick, ptr(sums),
+                                          stream()))
+                return sums.tolist()
+
+            ll = 0.0
+            for _ in range(max_niter_gn):
+                s = measure()
+                ll = float(np.float32(0.5 * tau)) * s[0]
+                gr = tau * (s[2] - s[1])
+                hes = tau * (s[4] + s[3])
+                update = gr / hes
+                old_scl, old_ll, armijo = scl, ll, 1.0
+                if num_linesearch == 0:
+                    scl = old_scl - armijo * update
+                else:
+                    for _ls in range(num_linesearch):
+                        scl = old_scl - armijo * update
+                        # torch: exp(float64 0-dim) * float32 volume -> the factor rounded to float32
+                        f0 = float(np.float32(math.exp(scl - old_scl)))
+                        f1 = float(np.float32(math.exp(-(scl - old_scl))))
+                        check(lib.ur_scale_slices(ptr(dat_y), ptr(dat_y), dim_x, f0, f1, thick,
+                                                  stream()))
+                        ll = float(np.float32(0.5 * tau)) * measure()[0]
+                        if ll < old_ll:
+                            break
+                        scl, ll = old_scl, old_ll
+                        armijo *= 0.5
+            po.scl = torch.tensor(scl, dtype=torch.float64, device=dev)
+            sll += ll
+    return x, torch.tensor(sll, dtype=torch.float64, device=dev)

@@ -148,6 +148,17 @@ extern "C" int ur_conv_axis(const float *d_in, const int32_t idim[3], float *d_o
                    (cudaStream_t)stream, nullptr);
 }
 
+extern "C" int ur_scale_slices(const float *d_in, float *d_out, const int32_t dim[3], float f_even,
+                               float f_odd, int axis, ur_stream stream) {
+  UR_REQUIRE(d_in && d_out && dim, "ur_scale_slices: null argument");
+  UR_REQUIRE(axis >= 0 && axis < 3, "ur_scale_slices: axis must be 0, 1 or 2");
+  const Dim3i d = make_dim(dim);
+  dim3 block(64, 4, 1), grid(div_up(d.z, 64), div_up(d.y, 4), d.x);
+  scaling_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_in, d_out, d, f_even, f_odd, axis);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
 extern "C" int ur_apply_scaling(const float *d_in, float *d_out, const int32_t dim[3], float scl,
                                 int axis, ur_stream stream) {
   UR_REQUIRE(d_in && d_out && dim, "ur_apply_scaling: null argument");

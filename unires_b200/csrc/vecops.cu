@@ -136,6 +136,70 @@ extern "C" int ur_nll_data(const float *d_x, const float *d_Ay, size_t n, float 
   return UR_OK;
 }
 
+// Masked even/odd sums of the slice-scaling update (unires/_update.py:303-335): over the
+// voxels with x != 0, with p = parity of the index along `axis`,
+//   out[0] = sum (x - y)^2, out[1 + p] = sum y (x - y), out[3 + p] = sum y^2
+// float32 products accumulated in float64 like torch.sum(..., dtype=float64); deterministic
+// two-stage reduction (per-block partials, the last block sums them in index order).
+__global__ void __launch_bounds__(256)
+    scaling_sums_kernel(const float *__restrict__ x, const float *__restrict__ y, Dim3i d,
+                        int axis, GridReduce gr, double *out) {
+  __shared__ double s_red[5][kMaxWarps];
+  __shared__ bool s_last;
+  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const size_t n = d.numel(), stride = (size_t)gridDim.x * blockDim.x;
+  const size_t sx = (size_t)d.y * d.z;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float xv = x[i];
+    if (xv == 0.f) continue;
+    const float yv = y[i], df = __fsub_rn(xv, yv);
+    const int pos = axis == 0 ? (int)(i / sx) : (axis == 1 ? (int)((i / d.z) % d.y) : (int)(i % d.z));
+    const int p = pos & 1;
+    part[0] += (double)__fmul_rn(df, df);
+    part[1 + p] += (double)__fmul_rn(yv, df);
+    part[3 + p] += (double)__fmul_rn(yv, yv);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double v = warp_sum(part[k]);
+    if (lane == 0) s_red[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_red[threadIdx.x][w];
+    gr.partials[blockIdx.x * 5 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(gr.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(gr.partials + b * 5 + threadIdx.x);
+    out[threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) *gr.counter = 0u;
+}
+
+extern "C" int ur_scaling_sums(const float *d_x, const float *d_y, const int32_t dim[3], int axis,
+                               double *d_out, ur_stream stream) {
+  UR_REQUIRE(d_x && d_y && d_out && dim && dim[0] > 0 && dim[1] > 0 && dim[2] > 0,
+             "ur_scaling_sums: bad args");
+  UR_REQUIRE(axis >= 0 && axis < 3, "ur_scaling_sums: axis must be 0, 1 or 2");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  const Dim3i d = make_dim(dim);
+  scaling_sums_kernel<<<red_blocks(d.numel()), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, d, axis,
+                                                                               gr, d_out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
 extern "C" int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream) {
   UR_REQUIRE(d_e && d_out && n > 0, "ur_sqrt_sum: bad args");
   GridReduce gr;

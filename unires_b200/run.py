@@ -3,15 +3,16 @@ unires/run.py:24-207 -- coarse-to-fine regularisation schedule (unires/_core.py:
 ADMM iterations, convergence test on the objective, clean-FOV mask and output clamp
 (unires/_core.py:619-627).
 
-Scope: the default path of the reference (`sett.scaling` / `sett.unified_rigid` False); the
-even/odd-scaling and rigid Gauss-Newton updates raise NotImplementedError, nothing is written
-to disk.  `init` / `preproc` (I/O, hyper-parameter estimation, co-registration) are out of
+Scope: the reference's path without `sett.unified_rigid` (the rigid Gauss-Newton update raises
+NotImplementedError); `sett.scaling` runs the even/odd slice-scaling update
+(`_update._update_scaling`) after every ADMM iteration like unires/run.py:115-122; nothing is
+written to disk.  `init` / `preproc` (I/O, hyper-parameter estimation, co-registration) are out of
 scope: the caller supplies x (observations with tau, mu, po) and y (recon with lam0, mat).
 """
 import torch
 
 from . import _lib
-from ._update import _admm_aux, _step_size, _update_admm
+from ._update import _admm_aux, _step_size, _update_admm, _update_scaling
 from .optim import get_gain
 from .spatial import affine_grid
 
@@ -50,8 +51,8 @@ def fit(x, y, sett):
     reconstruction as float32 (X, Y, Z, C); pth_y is empty and label None (nothing is
     written); R holds one identity matrix per observation (no rigid update).
     `fit.last` keeps {'n_iter', 'obj', 'jtv', 'reg_scl'} of the run."""
-    if getattr(sett, 'scaling', False) or getattr(sett, 'unified_rigid', False):
-        raise NotImplementedError('even/odd scaling and rigid updates are out of scope '
+    if getattr(sett, 'unified_rigid', False):
+        raise NotImplementedError('the rigid Gauss-Newton update is out of scope '
                                   '(SURVEY.md section 8f)')
     with torch.no_grad():
         N = sum(len(xc) for xc in x)
@@ -80,6 +81,9 @@ def fit(x, y, sett):
                     break
             else:
                 countdown0 = 6
+            # even/odd slice scaling (unires/run.py:115-122)
+            if getattr(sett, 'scaling', False):
+                x, _ = _update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=6)
             # coarse-to-fine: next regularisation level, new ADMM step size
             if cnt_scl + 1 < len(sett.reg_scl) and cnt_scl_iter > 16 and bool(gain.abs() < 1e-3):
                 countdown1 -= 1
