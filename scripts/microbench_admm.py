@@ -25,8 +25,11 @@ def timed(fn, n=10):
 
 def main():
     dev = torch.device('cuda:0')
-    workload = sys.argv[1] if len(sys.argv) > 1 else 'sr3_256'
-    tol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-3
+    args = [a for a in sys.argv[1:] if '=' not in a]
+    for k, v in (a.split('=') for a in sys.argv[1:] if '=' in a):
+        check(lib.ur_tune(k.encode(), int(v)))
+    workload = args[0] if args else 'sr3_256'
+    tol = float(args[1]) if len(args) > 1 else 1e-3
     sc = synth.make_scenario(synth.CONFIGS[workload], _project, struct, device=dev, seed=0)
     sett = sc.sett
     sett.cgs_tol = tol

@@ -166,10 +166,11 @@ FUSE_CASES = [
 
 @pytest.mark.parametrize('kern', KERNELS)
 @pytest.mark.parametrize('case', FUSE_CASES)
-@pytest.mark.parametrize('stop,tol', [('residual', 1e-3), ('max_gain', 0.0)])
+@pytest.mark.parametrize('stop,tol', [('residual', 1e-3), ('max_gain', 0.0), ('max_gain', 1e-3)])
 def test_cg_fused_direction_update(cuda, case, stop, tol, kern):
-    """Matvec with p = beta p + r and x += alpha p folded in (two sweeps per iteration) against
-    the unfused three-sweep iteration and the oracle: same trip count, same iterate."""
+    """Matvec with p = beta p + r and x += alpha p folded in (two sweeps per iteration; energy
+    rule: p and x updates folded into the two matvecs, 44 B/voxel) against the unfused
+    iteration and the oracle: same trip count, same iterate."""
     from oracle.nitorch_shim.core import optim as OO
     from unires_b200 import _project, optim, struct
     dim_y, fov, axis, factor, scl, rpt = case

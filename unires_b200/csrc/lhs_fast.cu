@@ -32,7 +32,8 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
     return UR_ERR_UNSUPPORTED;
   if (!a16(A.v) || !a16(A.out) || !a16(A.b) || !a16(A.r) || !a16(A.p)) return UR_ERR_UNSUPPORTED;
   if (!a16(A.rres) || !a16(A.p_out) || !a16(A.xup)) return UR_ERR_UNSUPPORTED;
-  const bool combine = mode == LHS_COMBINE;
+  const bool combine = mode == LHS_COMBINE || mode == LHS_ECOMBINE;
+  const bool x_fused = mode == LHS_COMBINE && A.xup != nullptr;
 
   FastArgs S;
   memset(&S, 0, sizeof(S));
@@ -108,6 +109,9 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
     case LHS_ENERGY:
       kernel = fast_lookup_energy(kind, kp, r, ez, rpt);
       break;
+    case LHS_ECOMBINE:
+      kernel = fast_lookup_ecombine(kind, kp, r, ez, rpt);
+      break;
     default:
       kernel = fast_lookup_combine(kind, kp, r, ez, rpt);
       break;
@@ -132,7 +136,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r, pitch))
     return UR_ERR_UNSUPPORTED;
   map_x = map_v;
-  if (combine && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))
+  if (x_fused && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))
     return UR_ERR_UNSUPPORTED;
   if (dry_run) return UR_OK;
 

@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   constexpr int L = THICK_M ? KP - 1 : 1;    // look-ahead planes of the march
   constexpr int B = THICK_M ? KP - 1 : 0;    // pre-roll planes before the first output plane
   constexpr int PRE = THICK_M ? 0 : 1;       // plane u_begin - 1 needed (D'D of the first plane)
-  constexpr bool COMBINE = MODE == LHS_COMBINE;
+  // COMBINE: both fused modes (an in-place update of the tile + halo from a second TMA ring)
+  constexpr bool COMBINE = MODE == LHS_COMBINE || MODE == LHS_ECOMBINE;
+  constexpr bool ECOMB = MODE == LHS_ECOMBINE;
   static_assert(!THICK_M || (KP - 1 <= R && KP <= 2 * R), "thick-m: two live rows, aligned cuts");
   static_assert(!THICK_Z || (4 % R == 0 && KP - 1 <= HZ), "thick-z: ratio divides the quad");
   constexpr int NRZ = THICK_Z ? 8 / R : 1;  // candidate low-res rows per quad (thick along z)
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     beta_c = (float)a.fin.st->beta;
     alpha_c = (float)a.fin.st->alpha;
   }
+  const bool x_fused = MODE == LHS_COMBINE && a.xup != nullptr;  // x += alpha p_old rides along
   float beta_e = 0.f;
   if (MODE == LHS_ENERGY && a.update_p) beta_e = (float)a.fin.st->beta;
 
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
         tma_prefetch_3d(&tmap_v, z0 - HZ, c1, c2);
         if (COMBINE) {
           tma_prefetch_3d(&tmap_r, z0 - HZ, c1, c2);
-          if (pq >= m0 && pq < m1)
+          if (x_fused && pq >= m0 && pq < m1)
             tma_prefetch_3d(&tmap_x, z0, a.march_y ? pq : o0, a.march_y ? o0 : pq);
         }
         ++pq;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       prev[i] = cur[i] = lrc[i] = lro[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       xr[0][i] = xr[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (COMBINE) {
+    if (x_fused) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int q = first + h;
@@ -393,17 +396,27 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               const uint32_t sa = arr_pa + own_b + i * ROWB;
               const float4 po = lds128(sa);
               const float4 rr = lds128(arr_ra + own_b + i * ROWB);
-              float4 pn;  // torch: p *= beta; p += r  (two roundings)
-              pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), rr.x);
-              pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), rr.y);
-              pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), rr.z);
-              pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), rr.w);
+              float4 pn;
+              if (ECOMB) {  // torch: x += alpha * p  (two roundings)
+                pn.x = __fadd_rn(po.x, __fmul_rn(alpha_c, rr.x));
+                pn.y = __fadd_rn(po.y, __fmul_rn(alpha_c, rr.y));
+                pn.z = __fadd_rn(po.z, __fmul_rn(alpha_c, rr.z));
+                pn.w = __fadd_rn(po.w, __fmul_rn(alpha_c, rr.w));
+              } else {  // torch: p *= beta; p += r  (two roundings)
+                pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), rr.x);
+                pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), rr.y);
+                pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), rr.z);
+                pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), rr.w);
+              }
               sts128(sa, pn);
               if (cap_prev) prev[i] = pn;
               if (cap_cur) cur[i] = pn;
               if (c_own && act[i]) {
                 const int gi = goff_c + i * a.gs_o;
                 *reinterpret_cast<float4 *>(a.p_out + gi) = pn;
+              }
+              if (x_fused && c_own && act[i]) {
+                const int gi = goff_c + i * a.gs_o;
                 float4 xn;  // the previous iteration's x += alpha p
                 xn.x = __fadd_rn(xr[h][i].x, __fmul_rn(alpha_c, po.x));
                 xn.y = __fadd_rn(xr[h][i].y, __fmul_rn(alpha_c, po.y));
@@ -416,10 +429,17 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               const float4 po = lds128(arr_pa + h_off);
               const float4 rr = lds128(arr_ra + h_off);
               float4 pn;
-              pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), rr.x);
-              pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), rr.y);
-              pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), rr.z);
-              pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), rr.w);
+              if (ECOMB) {
+                pn.x = __fadd_rn(po.x, __fmul_rn(alpha_c, rr.x));
+                pn.y = __fadd_rn(po.y, __fmul_rn(alpha_c, rr.y));
+                pn.z = __fadd_rn(po.z, __fmul_rn(alpha_c, rr.z));
+                pn.w = __fadd_rn(po.w, __fmul_rn(alpha_c, rr.w));
+              } else {
+                pn.x = __fadd_rn(__fmul_rn(beta_c, po.x), rr.x);
+                pn.y = __fadd_rn(__fmul_rn(beta_c, po.y), rr.y);
+                pn.z = __fadd_rn(__fmul_rn(beta_c, po.z), rr.z);
+                pn.w = __fadd_rn(__fmul_rn(beta_c, po.w), rr.w);
+              }
               sts128(arr_pa + h_off, pn);
             }
             // x quads of plane c + 2 (combined by the next trip)
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
               xr[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (q_own && act[i])
+              if (x_fused && q_own && act[i])
                 xr[h][i] = *reinterpret_cast<const float4 *>(a.xup + (goff_c + 2 * a.gs_m +
                                                                         i * a.gs_o));
             }
@@ -588,13 +608,13 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 *reinterpret_cast<float4 *>(a.p + gi) = rr;
                 part += (double)__fmul_rn(rr.x, rr.x) + (double)__fmul_rn(rr.y, rr.y) +
                         (double)__fmul_rn(rr.z, rr.z) + (double)__fmul_rn(rr.w, rr.w);
-              } else {  // LHS_ENERGY
+              } else {  // LHS_ENERGY / LHS_ECOMBINE
                 const float4 bq = *reinterpret_cast<const float4 *>(a.b + gi);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * cmpv(bq, k)),
                                             cmpv(cur[i], k));
-                if (a.update_p) {
+                if (MODE == LHS_ENERGY && a.update_p) {
                   const float4 rq = *reinterpret_cast<const float4 *>(a.r + gi);
                   const float4 pq = *reinterpret_cast<const float4 *>(a.p + gi);
                   float4 pn;
@@ -634,6 +654,7 @@ FastKernel fast_lookup_plain(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_resid(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_energy(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_combine(int kind, int kp, int r, int e, int rpt);
+FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
 
 #define UR_FAST_LOOKUP_BODY(MODE)                                                          \
   {                                                                                        \

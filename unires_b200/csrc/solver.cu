@@ -293,6 +293,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fused energy rule: the iterate ping-pongs between the caller's x and a workspace buffer;
+// bring it home if the solve ended (device-side stop included) in the workspace copy.
+__global__ void __launch_bounds__(256)
+    cg_select_x_kernel(float *__restrict__ x, const float *__restrict__ x_alt, size_t n,
+                       const CgState *st) {
+  if (!st->x_cur) return;
+  const float4 *s4 = reinterpret_cast<const float4 *>(x_alt);
+  float4 *x4 = reinterpret_cast<float4 *>(x);
+  const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) x4[i] = s4[i];
+}
+
 // Fused direction update: x lags by one iteration; complete it with the last alpha and the
 // direction buffer the device state points at (valid after an early stop as well).
 __global__ void __launch_bounds__(256)
@@ -600,6 +612,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   }
   A.gr = GridReduce{w.partials, w.counter};
   const bool is_matvec = mode == LHS_PLAIN || mode == LHS_COMBINE;
+  const bool lean_only = mode == LHS_ECOMBINE || (mode == LHS_COMBINE && A.xup == nullptr);
   cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
   cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
   if (e0) cudaEventRecord(e0, st);
@@ -608,8 +621,12 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   if (variant == 0) variant = g_lhs_variant;
   if (variant != 1 || mode == LHS_COMBINE) {
     int rc = UR_ERR_UNSUPPORTED;
-    if (variant != 2) rc = lhs_fast_launch(mode, A, false, st);
+    if (variant != 2 || lean_only) rc = lhs_fast_launch(mode, A, false, st);
     g_last_path = 2;
+    if (rc == UR_ERR_UNSUPPORTED && lean_only) {
+      set_error("fused energy-rule sweeps need the lean TMA kernel");
+      return UR_ERR_CUDA;
+    }
     if (rc == UR_ERR_UNSUPPORTED && A.pitch > 0 && A.pitch != A.nz) {
       set_error("padded volume: only the lean TMA kernel understands a row pitch");
       return UR_ERR_CUDA;
@@ -624,7 +641,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
         ++g_prof.used;
         // algorithmic HBM bytes per voxel of this launch: read v, write A v (8); the fused
         // direction update adds read r, x and write p, x (16)
-        g_prof.bytes_per_voxel += mode == LHS_COMBINE ? 24.0 : 8.0;
+        g_prof.bytes_per_voxel += mode == LHS_COMBINE ? (A.xup ? 24.0 : 16.0) : 8.0;
       }
       if (rc == UR_ERR_UNSUPPORTED) set_error("fused direction update: streaming kernel n/a");
       return rc;
@@ -655,13 +672,13 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   return UR_OK;
 }
 
-// CG workspace: [CgState | lhs ws | r | p | Ap | p2 | b_pad | x_pad]   (p2: second direction
+// CG workspace: [CgState | lhs ws | r | p | Ap | p2 | b_pad | x_pad | x2]   (p2: second direction
 // buffer of the fused direction update, which cannot run in place because neighbouring CTAs
 // re-read halos; b_pad / x_pad: zero-padded copies of b and x when nz is not a multiple of 4)
 struct CgWs {
   CgState *st;
   void *lhs;
-  float *r, *p, *Ap, *p2, *b_pad, *x_pad;
+  float *r, *p, *Ap, *p2, *b_pad, *x_pad, *x2;
 };
 
 static size_t cg_state_bytes() { return align_up(sizeof(CgState)); }
@@ -684,6 +701,8 @@ static CgWs carve_cg_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   w.b_pad = (float *)c;
   c += vol_bytes(lhs);
   w.x_pad = (float *)c;
+  c += vol_bytes(lhs);
+  w.x2 = (float *)c;
   return w;
 }
 
@@ -829,8 +848,8 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
 extern "C" size_t ur_cg_workspace_bytes(const ur_lhs *lhs) {
   LhsPlan P;
   if (make_plan(lhs, &P)) return 0;
-  const int extra = lhs->dim_y[2] % 4 != 0 ? 2 : 0;  // padded copies of b and x
-  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + (4 + extra) * vol_bytes(lhs);
+  // r, p, Ap, p2 | padded copies of b and x (nz % 4 != 0) | second x buffer (fused energy rule)
+  return cg_state_bytes() + align_up(lhs_ws_bytes(lhs, P)) + 7 * vol_bytes(lhs);
 }
 
 extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_ws,
@@ -908,7 +927,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     A.b = d_b;
     A.update_p = 0;
     A.done = done;
-    A.fin = FinalizeArgs{FIN_ENERGY, 0, stop, tol, cw.st, nullptr};
+    A.fin = FinalizeArgs{FIN_ENERGY, 0, stop, tol, cw.st, nullptr, -1};
     rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
     if (rc) return rc;
   }
@@ -930,9 +949,71 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
             lhs_fast_launch(LHS_COMBINE, A, true, st) == UR_OK) ||
            lhs_stream_launch(LHS_COMBINE, A, -1, st) == UR_OK;
   }
+  // Energy rule with the lean kernel: three sweeps per iteration, 44 instead of 52 B/voxel,
+  //   [matvec with p = beta p_old + r folded in ; p.Ap]                       (16 B/voxel)
+  //   [r -= alpha Ap ; r.r]                                                   (12 B/voxel)
+  //   [energy matvec with x = x_old + alpha p folded in ; 0.5 (Ax - 2b).x]    (16 B/voxel)
+  // p and x each ping-pong between two buffers (neighbouring CTAs still read the old halos).
+  bool efuse = false;
+  if (stop == UR_STOP_ENERGY && g_cg_fuse && opts->variant == 0 && g_lhs_variant == 0 && vec &&
+      aligned16(cw.p2) && aligned16(cw.x2) && P.n_general == 0) {
+    LhsArgs A = P.args;
+    A.v = cw.p;
+    A.out = cw.Ap;
+    A.rres = cw.r;
+    A.p_out = cw.p2;
+    A.xup = nullptr;
+    A.b = d_b;
+    efuse = lhs_fast_launch(LHS_COMBINE, A, true, st) == UR_OK &&
+            lhs_fast_launch(LHS_ECOMBINE, A, true, st) == UR_OK;
+  }
   float *pbuf[2] = {cw.p, cw.p2};
-  int cur = 0;
-  for (int it = 1; it <= opts->max_iter; ++it) {
+  float *xbuf[2] = {d_x, cw.x2};
+  int cur = 0, xcur = 0;
+  for (int it = 1; efuse && it <= opts->max_iter; ++it) {
+    {
+      LhsArgs A = P.args;
+      A.out = cw.Ap;
+      A.done = done;
+      if (it > 1) {  // p = beta p_old + r ; Ap = A p ; alpha
+        A.v = pbuf[cur];
+        A.p_out = pbuf[cur ^ 1];
+        A.rres = cw.r;
+        A.xup = nullptr;
+        A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr, cur ^ 1};
+        rc = launch_lhs(LHS_COMBINE, lhs, P, lw, A, opts->variant, st);
+        cur ^= 1;
+      } else {  // Ap = A p ; alpha
+        A.v = pbuf[cur];
+        A.fin = FinalizeArgs{FIN_ALPHA, it, stop, tol, cw.st, nullptr, cur};
+        rc = launch_lhs(LHS_PLAIN, lhs, P, lw, A, opts->variant, st);
+      }
+      if (rc) return rc;
+    }
+    {  // r -= alpha Ap ; beta = rz'/rz
+      FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
+      cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
+                                                     g_r_reverse);
+      UR_LAUNCH_CHECK();
+    }
+    {  // x = x_old + alpha p ; obj = 0.5 (A x - 2 b).x ; stop test
+      LhsArgs A = P.args;
+      A.v = xbuf[xcur];
+      A.rres = pbuf[cur];
+      A.p_out = xbuf[xcur ^ 1];
+      A.b = d_b;
+      A.done = done;
+      A.fin = FinalizeArgs{FIN_ENERGY, it, stop, tol, cw.st, nullptr, xcur ^ 1};
+      rc = launch_lhs(LHS_ECOMBINE, lhs, P, lw, A, opts->variant, st);
+      if (rc) return rc;
+      xcur ^= 1;
+    }
+  }
+  if (efuse) {
+    cg_select_x_kernel<<<vblocks, 256, 0, st>>>(d_x, cw.x2, n, cw.st);
+    UR_LAUNCH_CHECK();
+  }
+  for (int it = 1; !efuse && it <= opts->max_iter; ++it) {
     if (fuse && it > 1) {  // p = beta p_old + r ; x += alpha_prev p_old ; Ap = A p ; alpha
       LhsArgs A = P.args;
       A.v = pbuf[cur];
@@ -993,7 +1074,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
       A.p = cw.p;
       A.update_p = 1;
       A.done = done;
-      A.fin = FinalizeArgs{FIN_ENERGY, it, stop, tol, cw.st, nullptr};
+      A.fin = FinalizeArgs{FIN_ENERGY, it, stop, tol, cw.st, nullptr, -1};
       rc = launch_lhs(LHS_ENERGY, lhs, P, lw, A, opts->variant, st);
       if (rc) return rc;
     }

@@ -13,6 +13,7 @@ struct CgState {
   int done;    // set on the device when |gain| < tolerance
   int done_iter;  // iteration whose stop test set `done`
   int p_cur;      // which of the two direction buffers holds the current p (fused update)
+  int x_cur;      // which of the two x buffers holds the current iterate (fused energy rule)
   double obj[UR_CG_MAX_ITER + 1];
 };
 
@@ -32,7 +33,8 @@ struct FinalizeArgs {
   double tol;
   CgState *st;
   double *dot_out;
-  int aux;  // FIN_ALPHA: index of the direction buffer this matvec used / produced
+  int aux;  // FIN_ALPHA: index of the direction buffer this matvec produced; FIN_ENERGY: index
+            // of the x buffer it produced (-1: x was not moved)
 };
 
 __device__ __forceinline__ void record_objective(CgState *st, int n, double o, double tol) {
@@ -75,7 +77,11 @@ struct LatticeTerm {
 // LHS_COMBINE (streaming kernel only): the direction update is folded into the matvec's
 // load stage:  p = beta p_old + r  (tile + halo, on-chip),  x += alpha_prev p_old,
 // out = A p, p.Ap  -- 24 instead of 8 + 20 bytes per voxel for the two sweeps it replaces.
-enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2, LHS_COMBINE = 3 };
+// LHS_ECOMBINE (lean kernel only): the x update is folded into the energy matvec's load stage:
+//   x_new = x_old + alpha p (tile + halo, on-chip; written to a second buffer),
+//   0.5 (A x_new - 2 b).x_new  -- with LHS_COMBINE (without its x update) and the residual
+// update this is the energy-rule iteration in 44 instead of 52 bytes per voxel.
+enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2, LHS_COMBINE = 3, LHS_ECOMBINE = 4 };
 
 struct LhsArgs {
   int nx, ny, nz;
@@ -131,6 +137,7 @@ __device__ __forceinline__ void finalize(const FinalizeArgs &f, double total) {
       break;
     case FIN_ENERGY:
       record_objective(st, f.iter, 0.5 * total, f.tol);
+      if (f.aux >= 0) st->x_cur = f.aux;
       break;
   }
 }
