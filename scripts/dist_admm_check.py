@@ -16,7 +16,7 @@ def main():
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
     cfg = synth.scaled(synth.CONFIGS['sr3_256'], (64, 72, 128))
-    cfg['thick'] = [(0, 4), (1, 4), (2, 4), (2, 2)]
+    cfg['thick'] = ([(0, 4), (1, 4), (2, 4), (2, 2)] * ((world + 3) // 4))[:max(4, world)]
     full = synth.make_scenario(cfg, _project, struct, device=dev, seed=0)
     C = len(full.x)
     mine = parallel.channel_shard(C, world, rank)

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15
-(for f in 1 0; do echo "== cg_fuse $f"; timeout 300 python scripts/microbench_admm.py sr3_256 1e-3 cg_fuse=$f 2>&1 | grep _update_admm; done) 2>&1 | tee gpurun_out/efuse.log
+(for i in 1 2; do timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-120; done
+) | tee gpurun_out/variance2.log

@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(256)
     const size_t n4 = n / 4;
     float4 *r4 = reinterpret_cast<float4 *>(r);
     const float4 *A4 = reinterpret_cast<const float4 *>(Ap);
-    constexpr int U = 4;  // independent quads per thread and trip: 2 U loads in flight
+    constexpr int U = 1;  // quads per thread and trip (more did not help and costs registers
+                          // that co-resident kernels of other channels' streams could use)
     for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
       float4 rv[U], av[U];
       size_t idx[U];
