@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(for i in 1 2; do timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-120; done
-) | tee gpurun_out/variance2.log
+timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_solver.py -m gpu -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_pipe.log | cut -c1-900

@@ -236,6 +236,64 @@ def solve_y_from_host(x, y, z, w, rho, tmp, sett, host_x, host_y, host_out, copy
     return infos
 
 
+class HostPipeline:
+    """y-updates of a STREAM of subjects whose observations / initial estimates live in host
+    (pinned) memory and whose reconstructions are wanted back on the host.
+
+    `sets` are two or more device-side container sets [(x, y), ...] of identical geometry; subject
+    k uses set k % len(sets).  Per subject and channel: upload on the H2D stream, CG solve on
+    that channel's stream (`_solve_channel`), download on the D2H stream -- so the PCIe
+    transfers of subject k+1 and k-1 overlap the solves of subject k in both directions.  A
+    set is reused only after its previous download has completed (event, no host sync).
+    Every byte of every subject crosses PCIe; `drain()` waits for the last result."""
+
+    def __init__(self, sets, z, w, rho, sett):
+        self.sets, self.z, self.w, self.rho, self.sett = sets, z, w, rho, sett
+        y0 = sets[0][1]
+        self.dim, self.vx = _geometry(y0)
+        dev = y0[0].dat.device
+        self.dev = dev
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.ns = max(2, _n_streams(sett, len(y0)))
+        self.free = [None] * len(sets)
+        self.k = 0
+        self.h2d.wait_stream(torch.cuda.current_stream(dev))
+
+    def submit(self, host_x, host_y, host_out):
+        x, y = self.sets[self.k % len(self.sets)]
+        slot = self.k % len(self.sets)
+        self.k += 1
+        streams = _side_streams(self.dev, self.ns)
+        ready = []
+        with torch.cuda.stream(self.h2d):
+            if self.free[slot] is not None:
+                self.h2d.wait_event(self.free[slot])
+            for c in range(len(x)):
+                for n, obs in enumerate(x[c]):
+                    obs.dat.copy_(host_x[c][n], non_blocking=True)
+                y[c].dat.copy_(host_y[c], non_blocking=True)
+                ready.append(self.h2d.record_event())
+        infos = []
+        for c in range(len(x)):
+            s = streams[c % self.ns]
+            s.wait_event(ready[c])
+            with torch.cuda.stream(s):
+                infos.append(_solve_channel(x[c], y[c], self.z[c], self.w[c], self.rho,
+                                            _rhs_buffer(self.dim, self.dev), self.sett, self.dim,
+                                            self.vx))
+                solved = s.record_event()
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(solved)
+                host_out[c].copy_(y[c].dat, non_blocking=True)
+        self.free[slot] = self.d2h.record_event()
+        return infos
+
+    def drain(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.d2h)
+        torch.cuda.current_stream(self.dev).wait_stream(self.h2d)
+
+
 _copy_streams = {}
 
 

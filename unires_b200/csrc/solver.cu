@@ -328,9 +328,11 @@ __global__ void __launch_bounds__(256)
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
+static int g_vec_blocks_per_sm = 8;  // grid of the CG vector kernels (ur_tune "vec_blocks")
+
 static unsigned vec_blocks(size_t n) {
   const size_t want = (n / 4 + 255) / 256;
-  const size_t cap = (size_t)sm_count() * 8;
+  const size_t cap = (size_t)sm_count() * g_vec_blocks_per_sm;
   return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
@@ -725,6 +727,8 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_rpt = (value == 1 || value == 2) ? value : 0;
   } else if (!strcmp(name, "fast_depth")) {
     fast_depth = value < 1 ? 1 : value;
+  } else if (!strcmp(name, "vec_blocks")) {
+    g_vec_blocks_per_sm = value < 1 ? 1 : value;
   } else if (!strcmp(name, "r_reverse")) {
     g_r_reverse = value != 0;
   } else if (!strcmp(name, "fast_pfd")) {
