@@ -69,7 +69,8 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
       }
       e = ((T.off % r) + r) % r;
       if (T.axis == 2) {
-        kind = FK_THICK_Z;
+        // register scheme when the ratio divides the quad, per-lane windows otherwise
+        kind = ((kp == 5 && r == 4) || (kp == 3 && r == 2)) ? FK_THICK_Z : FK_THICK_ZG;
         S.lo_z = 0;
         S.hi_z = A.nz;
       } else {
@@ -93,7 +94,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.a_z = A.rl2 * iv_z;
   S.d0 = A.w_ident + 2.f * ((S.a_m + S.a_o) + S.a_z);
 
-  int rpt = kind == FK_THICK_M ? 1 : 2;
+  int rpt = kind == FK_THICK_M ? 1 : 2;  // measured at 256^3: 8-row tiles win with a deep ring
   if (fast_rpt == 1 || fast_rpt == 2) rpt = fast_rpt;
   if (S.no <= NWARP) rpt = 1;
 
@@ -116,7 +117,18 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
       kernel = fast_lookup_combine(kind, kp, r, ez, rpt);
       break;
   }
+  if (!kernel && rpt == 2) {  // some specialisations exist for 8-row tiles only
+    rpt = 1;
+    switch (mode) {
+      case LHS_PLAIN: kernel = fast_lookup_plain(kind, kp, r, ez, rpt); break;
+      case LHS_RESID: kernel = fast_lookup_resid(kind, kp, r, ez, rpt); break;
+      case LHS_ENERGY: kernel = fast_lookup_energy(kind, kp, r, ez, rpt); break;
+      case LHS_ECOMBINE: kernel = fast_lookup_ecombine(kind, kp, r, ez, rpt); break;
+      default: kernel = fast_lookup_combine(kind, kp, r, ez, rpt); break;
+    }
+  }
   if (!kernel) return UR_ERR_UNSUPPORTED;
+  const int hz = fast_hz(kind, kp), sz = TZ + 2 * hz;
 
   const int to = NWARP * rpt;
   const int L = kind == FK_THICK_M ? kp - 1 : 1;
@@ -125,15 +137,15 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.ns = L + 3 + 2 * depth;
   S.nrs = combine ? S.ns - L - 1 : 0;
   if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
-  const size_t plane_b = ((size_t)(to + 2) * SZ * 4 + 127) / 128 * 128;
+  const size_t plane_b = ((size_t)(to + 2) * sz * 4 + 127) / 128 * 128;
   const size_t smem = (size_t)(S.ns + S.nrs) * plane_b + 128;
   if (smem > 200u * 1024u) return UR_ERR_UNSUPPORTED;
 
   CUtensorMap map_v, map_r, map_x;
-  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_v, pitch))
+  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, sz, march, to + 2, &map_v, pitch))
     return UR_ERR_UNSUPPORTED;
   map_r = map_v;
-  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, SZ, march, to + 2, &map_r, pitch))
+  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, sz, march, to + 2, &map_r, pitch))
     return UR_ERR_UNSUPPORTED;
   map_x = map_v;
   if (x_fused && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))

@@ -33,14 +33,15 @@ namespace ur {
 namespace fast {
 
 constexpr int TZ = 128;          // z extent of a tile (32 lanes x float4)
-constexpr int HZ = 4;            // z halo (one quad each side)
-constexpr int SZ = TZ + 2 * HZ;  // floats per tile row in shared memory
+// z halo of a tile row: one quad each side; two for the generic thick-z kind with > 5 taps
+constexpr int fast_hz(int kind, int kp) { return (kind == 4 && kp - 1 > 4) ? 8 : 4; }
 constexpr int NTHR = 256;
 constexpr int NWARP = NTHR / 32;
 constexpr int kMaxSlots = 32;
-constexpr int kTaps = 8;
+constexpr int kTaps = 16;
 
-enum { FK_NONE = 0, FK_POINT = 1, FK_THICK_M = 2, FK_THICK_Z = 3 };
+// FK_THICK_Z: ratio divides 4 (register scheme); FK_THICK_ZG: any ratio (per-lane windows)
+enum { FK_NONE = 0, FK_POINT = 1, FK_THICK_M = 2, FK_THICK_Z = 3, FK_THICK_ZG = 4 };
 
 struct FastArgs {
   int nm, no, nz;
@@ -157,18 +158,24 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                     const __grid_constant__ CUtensorMap tmap_x,
                     const __grid_constant__ FastArgs a) {
   constexpr int TO = NWARP * RPT;
+  constexpr int HZ = fast_hz(KIND, KP);
+  constexpr int SZ = TZ + 2 * HZ;  // floats per tile row in shared memory
   constexpr uint32_t ROWB = SZ * 4u;
   constexpr uint32_t PLANE_BYTES = (TO + 2) * ROWB;
   constexpr uint32_t PLANE_B = (PLANE_BYTES + 127u) / 128u * 128u;
   constexpr bool THICK_M = KIND == FK_THICK_M;
   constexpr bool THICK_Z = KIND == FK_THICK_Z;
+  constexpr bool THICK_ZG = KIND == FK_THICK_ZG;
+  constexpr int NW = THICK_ZG ? (KP + 2) / R + 1 : 1;  // candidate windows per quad (generic z)
   constexpr int L = THICK_M ? KP - 1 : 1;    // look-ahead planes of the march
   constexpr int B = THICK_M ? KP - 1 : 0;    // pre-roll planes before the first output plane
   constexpr int PRE = THICK_M ? 0 : 1;       // plane u_begin - 1 needed (D'D of the first plane)
   // COMBINE: both fused modes (an in-place update of the tile + halo from a second TMA ring)
   constexpr bool COMBINE = MODE == LHS_COMBINE || MODE == LHS_ECOMBINE;
   constexpr bool ECOMB = MODE == LHS_ECOMBINE;
-  static_assert(!THICK_M || (KP - 1 <= R && KP <= 2 * R), "thick-m: two live rows, aligned cuts");
+  static_assert(!THICK_M || KP <= 2 * R, "thick-m: two live low-res rows");
+  static_assert(!THICK_ZG || KP - 1 <= HZ, "thick-z: windows inside the z halo");
+  static_assert(2 * R <= kTaps || !THICK_M, "kerT zero padding");
   static_assert(!THICK_Z || (4 % R == 0 && KP - 1 <= HZ), "thick-z: ratio divides the quad");
   constexpr int NRZ = THICK_Z ? 8 / R : 1;  // candidate low-res rows per quad (thick along z)
 
@@ -203,8 +210,8 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   if (MODE == LHS_ENERGY && a.update_p) beta_e = (float)a.fin.st->beta;
 
   // halo quad of this thread (COMBINE): rows 0 and TO+1 entirely, first/last quad of the others
-  constexpr int SZ4 = SZ / 4;
-  constexpr int HALO_N = 2 * SZ4 + 2 * TO;
+  constexpr int SZ4 = SZ / 4, HQ = HZ / 4;
+  constexpr int HALO_N = 2 * SZ4 + 2 * HQ * TO;
   static_assert(HALO_N <= NTHR, "one halo quad per thread");
   uint32_t h_off = 0;
   const bool h_has = COMBINE && tid < HALO_N;
@@ -218,8 +225,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       h_c4 = tid - SZ4;
     } else {
       const int k = tid - 2 * SZ4;
-      h_row = 1 + (k >> 1);
-      h_c4 = (k & 1) ? SZ4 - 1 : 0;
+      h_row = 1 + k / (2 * HQ);
+      const int sq = k - (h_row - 1) * (2 * HQ);
+      h_c4 = sq < HQ ? sq : SZ4 - 2 * HQ + sq;
     }
     h_off = (uint32_t)(h_row * SZ + 4 * h_c4) * 4u;
   }
@@ -262,7 +270,8 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     const int u_begin = m0 - B;
     const int first = u_begin - PRE;
     int last = m1 - 1 + L;
-    if (THICK_M && m1 < a.nm) last = m1;  // cut at a row start: the last row ends at plane m1
+    // cut at a row start: the last row of the segment starts at m1 - R and ends at m1 - R + KP - 1
+    if (THICK_M && m1 < a.nm) last = m1 + (KP - 1 > R ? KP - 1 - R : 0);
     const int u_start = first - L - 1;    // first (virtual) trip: arrives plane `first`
 
     // ---- per-thread constants of this column ----
@@ -271,6 +280,32 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     float4 Dq[RPT];
     float4 tm[RPT];        // POINT: tau x FOV mask per voxel; THICK_M: FOV mask of the row quad
     float czr[RPT][NRZ];   // THICK_Z: validity x scaling of the candidate low-res rows
+    // THICK_ZG: per-lane candidate windows (start offset in bytes from the own quad, weights of
+    // the four output voxels, validity x scaling per row)
+    int g_so[NW];
+    float g_w[NW][4], g_c[RPT][NW];
+    if (THICK_ZG) {
+      const int lo = z - (KP - 1);
+      const int s0 = lo + ((((a.off - lo) % R) + R) % R);
+#pragma unroll
+      for (int n = 0; n < NW; ++n) {
+        const int sn = s0 + n * R;
+        const int j = (sn - a.off) / R;  // exact: sn = off (mod R); may be negative
+        const bool ok = sn <= z + 3 && sn - a.off >= 0 && j < a.nj;
+        g_so[n] = (sn - z) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tap = z + k - sn;
+          g_w[n][k] = (ok && tap >= 0 && tap < KP) ? a.kerT[tap] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int o = o_first + i;
+          const bool o_in = o >= a.lo_o && o < a.hi_o;
+          g_c[i][n] = (ok && o_in) ? (a.scl_conv ? ((j & 1) ? a.s_odd : a.s_even) : 1.f) : 0.f;
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const int o = o_first + i;
@@ -558,7 +593,23 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             } else {
               zl = lds32(ca - 4u);
               zr = lds32(ca + 16u);
-              if (THICK_M) {
+              if (THICK_ZG) {
+                if (m_in) {
+#pragma unroll
+                  for (int n = 0; n < NW; ++n) {
+                    if (g_c[i][n] == 0.f) continue;
+                    const uint32_t wa = ca + (uint32_t)g_so[n];
+                    float lr = 0.f;
+#pragma unroll
+                    for (int tt = 0; tt < KP; ++tt) lr = fmaf(a.ker[tt], lds32(wa + 4u * tt), lr);
+                    lr *= g_c[i][n];
+                    dat.x = fmaf(g_w[n][0], lr, dat.x);
+                    dat.y = fmaf(g_w[n][1], lr, dat.y);
+                    dat.z = fmaf(g_w[n][2], lr, dat.z);
+                    dat.w = fmaf(g_w[n][3], lr, dat.w);
+                  }
+                }
+              } else if (THICK_M) {
                 dat.x = fmaf(w1, lro[i].x, w0 * lrc[i].x);
                 dat.y = fmaf(w1, lro[i].y, w0 * lrc[i].y);
                 dat.z = fmaf(w1, lro[i].z, w0 * lrc[i].z);
@@ -673,6 +724,25 @@ FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
         if (kp == 3 && r == 2)                                                             \
           return R1 ? lhs_fast_kernel<MODE, FK_THICK_M, 3, 2, 0, 1>                        \
                     : lhs_fast_kernel<MODE, FK_THICK_M, 3, 2, 0, 2>;                       \
+        if (!R1) return nullptr;                                                           \
+        if (kp == 5 && r == 3) return lhs_fast_kernel<MODE, FK_THICK_M, 5, 3, 0, 1>;       \
+        if (kp == 7 && r == 5) return lhs_fast_kernel<MODE, FK_THICK_M, 7, 5, 0, 1>;       \
+        if (kp == 7 && r == 6) return lhs_fast_kernel<MODE, FK_THICK_M, 7, 6, 0, 1>;       \
+        if (kp == 9 && r == 8) return lhs_fast_kernel<MODE, FK_THICK_M, 9, 8, 0, 1>;       \
+        return nullptr;                                                                    \
+      case FK_THICK_ZG:                                                                    \
+        if (kp == 5 && r == 3)                                                             \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 1>                       \
+                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 2>;                      \
+        if (kp == 7 && r == 5)                                                             \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 7, 5, 0, 1>                       \
+                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 7, 5, 0, 2>;                      \
+        if (kp == 7 && r == 6)                                                             \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 7, 6, 0, 1>                       \
+                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 7, 6, 0, 2>;                      \
+        if (kp == 9 && r == 8)                                                             \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 8, 0, 1>                       \
+                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 8, 0, 2>;                      \
         return nullptr;                                                                    \
       case FK_THICK_Z:                                                                     \
         if (kp == 5 && r == 4) {                                                           \
