@@ -29,6 +29,11 @@ CONFIGS = {
     'thickz2_384x8': dict(dim_y=(384, 384, 384), fov=None, vx_y=1.0, thick=[(2, 2)] * 8),
     # configs[4]: 0.5 mm recon of 1 mm isotropic data, 512^3 (ratio 2 on every axis)
     'iso2_512': dict(dim_y=(512, 512, 512), fov=None, vx_y=0.5, thick=[None] * 3, vx_x=1.0),
+    # other clinical slice ratios (tuning / coverage of the lean kernel's specialisations)
+    'thick3_256': dict(dim_y=(256, 256, 256), fov=None, vx_y=1.0, thick=[(0, 3), (1, 3), (2, 3)]),
+    'thick6_256': dict(dim_y=(256, 256, 256), fov=None, vx_y=1.0, thick=[(0, 6), (1, 6), (2, 6)]),
+    'thick5_256': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0,
+                       thick=[(0, 5), (1, 5), (2, 5)]),
     # reduced copy of sr3_256 for quick CPU checks of bench.py
     'sr3_48': dict(dim_y=(48, 48, 48), fov=(34, 41, 34), vx_y=1.0, thick=[(0, 4), (1, 4), (2, 4)]),
     # configs[0]: single-channel denoise on the BrainWeb grid
