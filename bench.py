@@ -41,7 +41,7 @@ def parse():
     ap.add_argument('--workload', default='sr3_256')
     ap.add_argument('--cg-iters', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-sample-iters', type=int, default=2)
+    ap.add_argument('--cpu-sample-iters', type=int, default=10)
     ap.add_argument('--channel-streams', type=int, default=None)
     ap.add_argument('--tune', action='append', default=[], help='knob=value (ur_tune)')
     return ap.parse_args()
@@ -354,8 +354,11 @@ def run_reference(args):
             'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': n, 'warmup': 1,
             'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s (channel 0 only, recon grid %s): bounded sample, one CG '
-                                   'iteration per step' % (args.workload, 'x'.join(map(str, dim)))},
+            'config': {'workload': '%s: 3-channel thick-slice super-resolution, recon grid %s, CG '
+                                   'y-update (tolerance 0); bounded sample: each step is ONE full-size '
+                                   'CG iteration of channel 0 on the host cores'
+                                   % (args.workload, 'x'.join(map(str, dim))),
+                       'channels': 1, 'recon_grid': list(dim), 'cg_iters_per_channel': 1},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(),
                              'kind': 'port',
                              'sample': '%d full-size CG iterations of channel 0 after 1 untimed '

@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(for wl in thick3_256 thick5_256 thick6_256; do for v in 0 2; do echo "== $wl lhs_variant $v"; timeout 200 python scripts/microbench_cg.py $wl 20 3 lhs_variant=$v 2>&1 | tail -3 | cut -c1-100; done; done) | tee gpurun_out/ratios.log
+( time python bench.py ) > gpurun_out/bench_default.log 2>&1; tail -5 gpurun_out/bench_default.log | cut -c1-2500
+( time python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/bench_reference.log 2>&1; tail -5 gpurun_out/bench_reference.log | cut -c1-900
+nproc; python -c "import torch; print(torch.get_num_threads())"
