@@ -142,9 +142,51 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
     return out.reshape((B, C) + shape)
 
 
-def grid_grad(*args, **kwargs):  # pragma: no cover - off the hot path
-    raise NotImplementedError('grid_grad is only used by the rigid update '
-                              '(unires/_update.py:541-710), out of scope')
+def grid_grad(input, grid, interpolation='linear', bound='zero', extrapolate=False):
+    """Spatial gradient of the trilinearly interpolated volume with respect to the voxel
+    coordinates, sampled at `grid` (unires/_update.py:505).  input (B,C,*in), grid (B,*out,3)
+    -> (B,C,*out,3).  Along axis d the two corner weights (1 - t, t) become (-1, +1); corners
+    outside the volume contribute zero and samples outside the field of view are zero, like
+    grid_pull (A.2).  [EXT-UNVERIFIED] restated from nitorch's published behaviour."""
+    order = _check_opts(bound, interpolation)
+    if order != 1:
+        raise NotImplementedError('grid_grad: linear interpolation only')
+    B, C = input.shape[:2]
+    shape = tuple(input.shape[2:])
+    nd = len(shape)
+    oshape = tuple(grid.shape[1:-1])
+    out = input.new_zeros((B, C) + oshape + (nd,))
+    for b in range(B):
+        g = grid[b].reshape(-1, nd).to(input.dtype)
+        msk = _inbounds(g, shape, extrapolate)
+        src = input[b].reshape(C, -1)
+        g0 = torch.floor(g)
+        w1 = g - g0
+        w0 = 1 - w1
+        i0 = g0.long()
+        acc = input.new_zeros((C, g.shape[0], nd))
+        for corner in range(2 ** nd):
+            flat = torch.zeros(g.shape[0], dtype=torch.long, device=g.device)
+            valid = torch.ones(g.shape[0], dtype=torch.bool, device=g.device)
+            bits = [(corner >> (nd - 1 - d)) & 1 for d in range(nd)]
+            for d, n in enumerate(shape):
+                i = i0[:, d] + bits[d]
+                valid &= (i >= 0) & (i < n)
+                flat = flat * n + i.clamp(0, n - 1)
+            if msk is not None:
+                valid = valid & msk
+            v = src[:, flat] * valid.to(input.dtype)
+            for a in range(nd):  # derivative along axis a
+                wgt = None
+                for d in range(nd):
+                    if d == a:
+                        w = torch.full_like(w1[:, d], 1.0 if bits[d] else -1.0)
+                    else:
+                        w = w1[:, d] if bits[d] else w0[:, d]
+                    wgt = w if wgt is None else wgt * w
+                acc[:, :, a] += v * wgt
+        out[b] = acc.reshape((C,) + oshape + (nd,))
+    return out
 
 
 def _vx(vx, ref):

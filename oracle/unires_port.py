@@ -16,6 +16,7 @@ Reference lines restated (relative to /root/reference):
   compute_nll                unires/_update.py:396-427
   update_admm                unires/_update.py:105-195
   even_odd / update_scaling  unires/_update.py:430-445, 270-393
+  rigid_match / update_rigid_channel / update_rigid   unires/_update.py:448-538, 541-710, 198-267
 """
 import math
 import types
@@ -64,7 +65,7 @@ def Settings(**kw):
 # operator geometry  (unires/_project.py:193-297)
 # ----------------------------------------------------------------------------
 def proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0,
-              gap=0.0, scl=0.0):
+              gap=0.0, scl=0.0, samp=0):
     po = types.SimpleNamespace()
     mat_y = mat_y.to(F64)
     mat_x = mat_x.to(F64)
@@ -77,6 +78,16 @@ def proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0,
     # thick-slice axis: first maximum of the input voxel size (:241)
     thick = int(torch.max(po.vx_x, dim=0)[1])
     po.dim_thick = thick
+    po.D_x = po.D_y = None
+    if samp > 0:
+        # sub-sampled observation grid for the rigid update (:245-264): keep every sk-th voxel,
+        # sk = max(1, round(samp / vx_x)).  (Upstream's high-res branch compares vx_x with
+        # itself and never fires, so D_y stays None.)
+        sk = torch.clamp(torch.floor(samp / po.vx_x + 0.5), min=1.0)
+        po.D_x = torch.diag(torch.cat([sk, torch.ones(1, dtype=F64)]))
+        po.mat_x = mat_x = mat_x @ po.D_x
+        po.dim_x = tuple(int(math.floor(d / k)) for d, k in zip(po.dim_x, sk.tolist()))
+        po.vx_x = S.voxel_size(mat_x)
     profile = [prof_ip] * nd
     profile[thick] = prof_tp
     gaps = [0.0] * nd
@@ -390,4 +401,133 @@ def update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=4):
                     armijo = armijo * 0.5
             po.scl = scl
             sll = sll + ll
+    return x, sll
+
+
+# ----------------------------------------------------------------------------
+# rigid Gauss-Newton update  (unires/_update.py:198-267, 448-710)
+# ----------------------------------------------------------------------------
+def expm(q, basis, grad=False):
+    from oracle.nitorch_shim.core._linalg_expm import _expm
+    return _expm(q, basis, grad_X=grad)
+
+
+def rigid_match(dat_x, dat_y, po, tau, rigid, sett, CtC=None, diff=False):
+    """Matching term 0.5 tau sum_{x != 0} (x - A y)^2 for the rigid matrix `rigid` and, with
+    diff=True, its first / second derivatives w.r.t. the sampling coordinates on the
+    intermediate grid: (ll, gr (*dim, 3), Hes (*dim, 6))  (:448-538)."""
+    sr = sett.method == 'super-resolution'
+    dim, src_mat = (po.dim_yx, po.mat_yx) if sr else (po.dim_x, po.mat_x)
+    vox = torch.linalg.solve(po.mat_y, rigid @ src_mat)
+    grid = S.affine_grid(vox.to(torch.float32), dim)[None]
+    kw = dict(bound=sett.bound, extrapolate=False, interpolation=sett.interpolation)
+    warped = S.grid_pull(dat_y, grid, **kw)[0, 0]
+    if sr:
+        warped = F.conv3d(warped[None, None], po.smo_ker, stride=po.ratio)[0, 0]
+        if po.scl != 0:
+            warped = apply_scaling(warped, po.scl, int(po.dim_thick))
+    msk = dat_x != 0
+    ll = 0.5 * tau * torch.sum((dat_x[msk] - warped[msk]) ** 2, dtype=F64)
+    if not diff:
+        return ll, None, None
+    g = S.grid_grad(dat_y, grid, **kw)[0, 0]
+    res = warped - dat_x
+    res[~(msk & (warped != 0))] = 0
+    pairs = ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))
+    Hes = torch.stack([g[..., a] * g[..., b] for a, b in pairs], dim=-1)
+    if sr:
+        Hes = Hes * CtC[..., None]
+        res = F.conv_transpose3d(res[None, None], po.smo_ker, stride=po.ratio)[0, 0]
+    return ll, g * res[..., None], Hes
+
+
+def update_rigid_channel(xc, yc, sett, max_niter_gn=1, num_linesearch=4, samp=3):
+    """Gauss-Newton update of rigid_q (and po.rigid) of every observation of one channel
+    (:541-710).  Returns (xc, sll)."""
+    basis = sett.rigid_basis
+    num_q = basis.shape[0]
+    lkp = ((0, 3, 4), (3, 1, 5), (4, 5, 2))
+    sr = sett.method == 'super-resolution'
+    one = torch.tensor(1.0, dtype=F64)
+    sll = torch.tensor(0, dtype=F64)
+    for obs in xc:
+        q, tau = obs.rigid_q, obs.tau
+        armijo = torch.tensor(1, dtype=q.dtype)
+        po = proj_info(obs.po.dim_y, obs.po.mat_y, obs.po.dim_x, obs.po.mat_x, rigid=obs.po.rigid,
+                       prof_ip=sett.profile_ip, prof_tp=sett.profile_tp, gap=sett.gap,
+                       scl=obs.po.scl, samp=samp)
+        dim, src_mat = (po.dim_yx, po.mat_yx) if sr else (po.dim_x, po.mat_x)
+        dat_y = yc.dat[None, None]
+        if samp > 0 and po.D_x is not None:
+            grid = S.affine_grid(po.D_x.to(torch.float32), po.dim_x)[None]
+            dat_x = S.grid_pull(obs.dat[None, None], grid, bound='zero', extrapolate=False,
+                                interpolation=0)[0, 0]
+        else:
+            dat_x = obs.dat
+        CtC = None
+        if sr:  # C'C 1: diagonal scaling of the Gauss-Newton Hessian
+            CtC = F.conv3d(torch.ones((1, 1) + tuple(dim), dtype=torch.float32), po.smo_ker,
+                           stride=po.ratio)
+            CtC = F.conv_transpose3d(CtC, po.smo_ker, stride=po.ratio)[0, 0]
+        ident = S.identity_grid(dim, dtype=torch.float32)
+        rigid, ll = obs.po.rigid, torch.tensor(0, dtype=F64)
+        for _ in range(max_niter_gn):
+            rigid, d_rigid = expm(q, basis, grad=True)
+            # derivative of the voxel-to-voxel matrix mat_y \ rigid mat w.r.t. q_i
+            dM = [torch.linalg.solve(po.mat_y, d_rigid[i] @ src_mat) for i in range(num_q)]
+            ll, gr_m, Hes_m = rigid_match(dat_x, dat_y, po, tau, rigid, sett, CtC=CtC, diff=True)
+            # d(coordinate d) / d q_i at every voxel of the intermediate grid (float32, as torch
+            # evaluates `float64 scalar * float32 volume`)
+            dA = [[dM[i][d, 0] * ident[..., 0] + dM[i][d, 1] * ident[..., 1]
+                   + dM[i][d, 2] * ident[..., 2] + dM[i][d, 3] for d in range(3)]
+                  for i in range(num_q)]
+            gr = torch.zeros(num_q, 1, dtype=F64)
+            Hes = torch.zeros(num_q, num_q, dtype=F64)
+            for d in range(3):
+                for i in range(num_q):
+                    gr[i] += torch.sum(gr_m[..., d] * dA[i][d], dtype=F64)
+            for d1 in range(3):
+                for d2 in range(3):
+                    for i1 in range(num_q):
+                        left = Hes_m[..., lkp[d1][d2]] * dA[i1][d1]
+                        for i2 in range(i1, num_q):
+                            Hes[i1, i2] += torch.sum(left * dA[i2][d2], dtype=F64)
+            Hes = torch.triu(Hes) + torch.triu(Hes, 1).T
+            step = torch.linalg.solve(Hes, gr)[:, 0]
+            old_ll, old_q, old_rigid = ll.clone(), q.clone(), rigid.clone()
+            if num_linesearch == 0:
+                q = old_q - armijo * step
+                rigid = expm(q, basis)
+            for _ls in range(num_linesearch):
+                q = old_q - armijo * step
+                rigid = expm(q, basis)
+                ll = rigid_match(dat_x, dat_y, po, tau, rigid, sett)[0]
+                if ll < old_ll:
+                    armijo = torch.min(1.25 * armijo, one)
+                    break
+                ll, q, rigid = old_ll, old_q, old_rigid
+                armijo = armijo * 0.5
+        obs.rigid_q = q
+        obs.po.rigid = rigid
+        sll = sll + ll
+    return xc, sll
+
+
+def update_rigid(x, y, sett, mean_correct=True, max_niter_gn=1, num_linesearch=4, samp=3):
+    """Rigid update of every observation, optionally mean-corrected over all of them (:198-267)."""
+    sll = torch.tensor(0, dtype=F64)
+    for c in range(len(x)):
+        x[c], s = update_rigid_channel(x[c], y[c], sett, max_niter_gn=max_niter_gn,
+                                       num_linesearch=num_linesearch, samp=samp)
+        sll = sll + s
+    if mean_correct:
+        qs = [obs.rigid_q for xc in x for obs in xc]
+        total = torch.zeros(sett.rigid_basis.shape[0], dtype=F64)
+        for q in qs:
+            total += q
+        mean_q = total / float(len(qs))
+        for xc in x:
+            for obs in xc:
+                obs.rigid_q -= mean_q
+                obs.po.rigid = expm(obs.rigid_q, sett.rigid_basis)
     return x, sll
