@@ -271,6 +271,26 @@ int ur_scaling_sums(const float *d_x, const float *d_y, const int32_t dim[3], in
 int ur_scale_slices(const float *d_in, float *d_out, const int32_t dim[3], float f_even,
                     float f_odd, int axis, ur_stream stream);
 
+/* ---------------------------------------------------------------- rigid
+ * Gauss-Newton update, _update_rigid / _rigid_match / _update_rigid_channel
+ * (unires/_update.py:198-267, 448-710).
+ * ur_affine_grad: nitorch.spatial.grid_grad (unires/_update.py:505) with the
+ * coordinates evaluated from the 3x4 matrix: d_out (ox,oy,oz,3) = gradient of
+ * the trilinearly interpolated d_src w.r.t. the sampling coordinates, zero
+ * bound.  ur_rigid_sums: the chain-rule reductions of unires/_update.py:
+ * 616-640 in one pass: with g = d_grad, res = d_res (C'(Ay - x), masked),
+ * ctc = d_ctc (C'C 1, may be NULL) and dA[i][d] the float32 field
+ * ((dm[i][d][0] ix + dm[i][d][1] iy) + dm[i][d][2] iz) + dm[i][d][3],
+ *   d_out[i]            = sum_d sum_vox (g_d res) dA[i][d]            i < 6
+ *   d_out[6 + tri(i,j)] = sum_{d1,d2} sum_vox ((g_d1 g_d2 ctc) dA[i][d1]) dA[j][d2]
+ * for i <= j in row-major upper-triangular order (21 values), float64.      */
+int ur_affine_grad(const float *d_src, const int32_t sdim[3], const float mat[12],
+                   float *d_out, const int32_t odim[3], int extrapolate,
+                   ur_stream stream);
+int ur_rigid_sums(const float *d_grad, const float *d_res, const float *d_ctc,
+                  const int32_t dim[3], const float dm[72], double *d_out,
+                  ur_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,11 +132,12 @@ def main():
               '%.0f KB' % (os.path.getsize(path) / 1024))
 
 
-if __name__ == '__main__' and '--fit' not in sys.argv and '--scaling' not in sys.argv:
+if __name__ == '__main__' and not {'--fit', '--scaling', '--rigid'} & set(sys.argv):
     main()
     main_fit()
     main_fit(scaling=True)
     main_scaling()
+    main_rigid()
 
 
 # ---------------------------------------------------------------------------
@@ -240,8 +241,57 @@ def main_scaling():
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'scaling_update.npz'), **out)
 
 
+# ---------------------------------------------------------------------------
+# rigid Gauss-Newton update (unires/_update.py::_update_rigid) fixture
+# ---------------------------------------------------------------------------
+RIGID_CASES = {
+    # name -> (recipe, samp, initial q of channel 0; channel c gets (-1)^c q)
+    'sr2_lattice': (dict(base='sr3_256', dim_y=(24, 28, 26), n_channels=2, sd=10.0, scl=0.0,
+                         rigid=None, admm_iters=2), 1, [0.6, -0.4, 0.3, 0.01, -0.015, 0.02]),
+    'thickz2_samp2': (dict(base='thickz2_256', dim_y=(26, 22, 28), n_channels=2, sd=10.0, scl=0.05,
+                           rigid=None, admm_iters=2), 2, [-0.5, 0.3, 0.4, -0.02, 0.01, 0.015]),
+}
+RIGID_STEPS = 3
+
+
+def prepare_rigid(sc, q0, expm):
+    """Mis-register every observation's operator by exp(+-q0) (the data are aligned)."""
+    from oracle.nitorch_shim.spatial import affine_basis
+    sc.sett.rigid_basis = affine_basis(group='SE', dtype=torch.float64)
+    for c, xc in enumerate(sc.x):
+        for o in xc:
+            o.rigid_q = torch.tensor(q0, dtype=torch.float64) * (1 if c % 2 == 0 else -1)
+            o.po.rigid = expm(o.rigid_q, sc.sett.rigid_basis)
+    return sc
+
+
+def main_rigid():
+    from oracle.adapters import reference_namespaces
+    from oracle.load_reference import load_reference
+    ref = load_reference()
+    ops, structs = reference_namespaces()
+    out = {}
+    for name, (recipe, samp, q0) in RIGID_CASES.items():
+        torch.manual_seed(0)
+        sc = prepare_fit(build(recipe, ops, structs), reference=True)
+        prepare_rigid(sc, q0, ref._update._expm)
+        qs, sll = [], []
+        for k in range(RIGID_STEPS):
+            _, s = ref._update._update_rigid(sc.x, sc.y, sc.sett, mean_correct=(k == RIGID_STEPS - 1),
+                                             max_niter_gn=1, num_linesearch=6, verbose=0, samp=samp)
+            qs.append([o.rigid_q.tolist() for xc in sc.x for o in xc])
+            sll.append(float(s))
+        out[name + '_q'] = np.array(qs, dtype=np.float64)
+        out[name + '_sll'] = np.array(sll, dtype=np.float64)
+        out[name + '_rigid'] = np.stack([o.po.rigid.numpy() for xc in sc.x for o in xc])
+        print('rigid', name, sll, qs[-1][0])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'rigid_update.npz'), **out)
+
+
 if __name__ == '__main__' and '--fit' in sys.argv:
     main_fit()
     main_fit(scaling=True)
+if __name__ == '__main__' and '--rigid' in sys.argv:
+    main_rigid()
 if __name__ == '__main__' and '--scaling' in sys.argv:
     main_scaling()

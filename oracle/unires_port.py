@@ -55,7 +55,7 @@ def Settings(**kw):
                               tolerance=1e-4, profile_ip=2, profile_tp=0,
                               gap=0.0, max_iter=512, reg_scl=4.0, sched_num=3,
                               rigid_mod=1, clean_fov=False, scaling=False,
-                              unified_rigid=False)
+                              unified_rigid=False, rigid_samp=1, rigid_basis=None)
     for k, v in kw.items():
         setattr(s, k, v)
     return s
@@ -313,6 +313,9 @@ def fit(x, y, sett):
             countdown0 = 6
         if getattr(sett, 'scaling', False):  # unires/run.py:115-122
             x, _ = update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=6)
+        if getattr(sett, 'unified_rigid', False) and n_iter > 0 and n_iter % sett.rigid_mod == 0:
+            x, _ = update_rigid(x, y, sett, mean_correct=False, max_niter_gn=1, num_linesearch=6,
+                                samp=sett.rigid_samp)  # unires/run.py:127-135
         if cnt_scl + 1 < len(reg) and cnt_scl_iter > 16 and gain.abs() < 1e-3:
             countdown1 -= 1
             if countdown1 == 0:

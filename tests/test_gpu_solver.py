@@ -252,3 +252,40 @@ def test_scaling_sums_kernel(cuda):
                 xs, ys, ms = (P.even_odd(t, which, axis) for t in (xx, yy, m))
                 want.append(torch.sum(fn(xs, ys)[ms], dtype=torch.float64).item())
         assert np.allclose(out.cpu().numpy(), want, rtol=1e-12)
+
+
+@pytest.mark.parametrize('name', sorted(gen_golden.RIGID_CASES))
+def test_update_rigid_vs_golden(cuda, name):
+    """_update_rigid on the GPU (ur_affine_grad + ur_rigid_sums + the operator kernels) against
+    the reference's trajectory: same line-search decisions, q within 1e-3 of the step size."""
+    from unires_b200 import _update
+    g = np.load(U.GOLDEN_DIR + '/rigid_update.npz', allow_pickle=False)
+    recipe, samp, q0 = gen_golden.RIGID_CASES[name]
+    sc = gen_golden.prepare_rigid(U.build(recipe, *U.port_namespaces()), q0, P.expm)
+    x, y, sett = U.to_device(sc, cuda)
+    sett.rigid_basis = sc.sett.rigid_basis
+    for c, xc in enumerate(x):
+        for n, o in enumerate(xc):
+            o.rigid_q = sc.x[c][n].rigid_q.clone()
+    for k in range(gen_golden.RIGID_STEPS):
+        x, sll = _update._update_rigid(x, y, sett, mean_correct=(k == gen_golden.RIGID_STEPS - 1),
+                                       max_niter_gn=1, num_linesearch=6, samp=samp)
+        got = np.array([o.rigid_q.cpu().tolist() for xc in x for o in xc])
+        want = g[name + '_q'][k]
+        assert np.allclose(got, want, rtol=2e-3, atol=2e-5), (k, got, want)
+        assert abs(float(sll) - float(g[name + '_sll'][k])) < 1e-4 * float(g[name + '_sll'][k])
+    rig = np.stack([o.po.rigid.cpu().numpy() for xc in x for o in xc])
+    assert np.allclose(rig, g[name + '_rigid'], atol=1e-4)
+
+
+def test_affine_grad_vs_oracle(cuda):
+    from oracle.nitorch_shim import spatial as S
+    from unires_b200 import spatial
+    g = torch.Generator().manual_seed(9)
+    v = torch.rand((11, 13, 9), generator=g)
+    mat = torch.tensor([[0.98, 0.05, -0.02, 0.7], [-0.04, 1.01, 0.03, -0.4], [0.02, -0.03, 0.97, 1.1],
+                        [0, 0, 0, 1.0]])
+    shape = (12, 10, 11)
+    want = S.grid_grad(v[None, None], S.affine_grid(mat, shape)[None])[0, 0]
+    got = spatial.affine_grad(v.to(cuda), mat, shape)
+    assert U.rel_l2(got, want) < 1e-5

@@ -65,3 +65,25 @@ def test_port_update_scaling_matches_reference_bitwise(name):
         assert float(sll_p) == float(sll_r)
         for xp, xr in zip(sp.x, sr.x):
             assert float(xp[0].po.scl) == float(xr[0].po.scl)
+
+
+@pytest.mark.parametrize('name', ['sr2_lattice', 'thickz2_samp2'])
+def test_port_update_rigid_matches_reference_bitwise(name):
+    """Rigid Gauss-Newton update (unires/_update.py:198-267, 448-710) incl. sub-sampling and
+    mean correction."""
+    from oracle import gen_golden
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    recipe, samp, q0 = gen_golden.RIGID_CASES[name]
+    sp = gen_golden.prepare_rigid(U.build(recipe, *U.port_namespaces()), q0, P.expm)
+    sr = gen_golden.prepare_rigid(gen_golden.prepare_fit(
+        U.build(recipe, *reference_namespaces()), reference=True), q0, ref._update._expm)
+    for k in range(2):
+        _, sll_p = P.update_rigid(sp.x, sp.y, sp.sett, mean_correct=(k == 1), max_niter_gn=1,
+                                  num_linesearch=6, samp=samp)
+        _, sll_r = ref._update._update_rigid(sr.x, sr.y, sr.sett, mean_correct=(k == 1),
+                                             max_niter_gn=1, num_linesearch=6, verbose=0, samp=samp)
+        assert float(sll_p) == float(sll_r)
+        for xp, xr in zip(sp.x, sr.x):
+            assert torch.equal(xp[0].rigid_q, xr[0].rigid_q)
+            assert torch.equal(xp[0].po.rigid, xr[0].po.rigid)

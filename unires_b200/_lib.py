@@ -88,6 +88,10 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     'ur_scale_slices': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_float,
                                   C.c_float, C.c_int, C.c_void_p]),
+    'ur_affine_grad': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                 C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p]),
+    'ur_rigid_sums': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     'ur_im_gradient': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_im_divergence': (C.c_int, [_p, _p, _i3, _f3, _p]),
     'ur_dtd': (C.c_int, [_p, _p, _i3, _f3, _p]),
@@ -227,3 +231,9 @@ def workspace(nbytes, device, tag='ws'):
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def copy_bag(obj):
+    """Shallow copy of an attribute bag (struct._proj_op and friends)."""
+    import copy
+    return copy.copy(obj)

@@ -38,9 +38,6 @@ def _proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0, gap
 
     Returns a `_proj_op` with the reference's fields.  The geometry is tiny
     float64 host arithmetic; tensors are placed on `device` like upstream."""
-    if samp:
-        raise NotImplementedError('samp > 0 (sub-sampling for the rigid update, '
-                                  'unires/_project.py:245-264) is out of scope')
     po = _proj_op()
     nd = len(dim_y)
     cpu = lambda t: torch.as_tensor(t).detach().to('cpu', _F64)
@@ -50,6 +47,16 @@ def _proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0, gap
     vx_x, vx_y = voxel_size(m_x), voxel_size(m_y)
     # thick-slice axis = first arg-max of the observed voxel size
     thick = int(torch.max(vx_x, dim=0)[1])
+    D_x = None
+    if samp > 0:
+        # sub-sampled observation grid for the rigid update (unires/_project.py:245-264): keep
+        # every sk-th voxel, sk = max(1, round(samp / vx_x)); upstream's high-res branch
+        # compares vx_x with itself and never fires, so D_y stays None
+        sk = torch.clamp(torch.floor(samp / vx_x + 0.5), min=1.0)
+        D_x = torch.diag(torch.cat([sk, torch.ones(1, dtype=_F64)]))
+        m_x = m_x @ D_x
+        d_x = [int(math.floor(d / k)) for d, k in zip(d_x, sk.tolist())]
+        vx_x = voxel_size(m_x)
     profile = [prof_ip] * nd
     profile[thick] = prof_tp
     slice_gap = [0.0] * nd
@@ -76,6 +83,8 @@ def _proj_info(dim_y, mat_y, dim_x, mat_x, rigid=None, prof_ip=0, prof_tp=0, gap
     po.vx_y, po.vx_x = vx_y.to(dev), vx_x.to(dev)
     po.rigid = (torch.eye(nd + 1, dtype=_F64) if rigid is None else cpu(rigid)).to(dev)
     po.smo_ker = ker.to(dev)
+    po.D_x = None if D_x is None else D_x.to(dev)
+    po.D_y = None
     po.dim_thick = torch.tensor(thick, device=dev)
     po.scl = scl if isinstance(scl, torch.Tensor) else torch.tensor(scl, dtype=torch.float32,
                                                                     device=dev)
@@ -152,6 +161,27 @@ def _proj_apply(operator, dat, po, method='super-resolution', bound='zero',
     check(lib.ur_proj_apply(_lib.OPS[operator], C.byref(s), ptr(d), ptr(out), ptr(ws),
                             ws.numel(), stream()))
     return out
+
+
+def _slice_profile(vol, po, transpose=False):
+    """The separable slice-profile correlation C (dim_yx -> dim_x, stride = ratio) or its
+    transpose C' on one (X, Y, Z) volume: F.conv3d / F.conv_transpose3d of unires/_project.py:
+    153-154 as three `ur_conv_axis` passes (dirac axes skipped)."""
+    from .kernels import separable_factors
+    d = require_cuda_f32(vol, 'vol')
+    factors = separable_factors(po.smo_ker)
+    order = (0, 1, 2) if not transpose else (2, 1, 0)
+    for a in order:
+        f, r = factors[a], int(po.ratio[a])
+        if len(f) == 1 and r == 1 and f[0] == 1.0:
+            continue
+        shape = list(d.shape)
+        shape[a] = (shape[a] - 1) * r + len(f) if transpose else (shape[a] - len(f)) // r + 1
+        out = torch.empty(shape, dtype=torch.float32, device=d.device)
+        check(lib.ur_conv_axis(ptr(d), i3(d.shape), ptr(out), a, _lib.farr(f), len(f), r,
+                               1 if transpose else 0, stream()))
+        d = out
+    return d
 
 
 def _apply_scaling(dat, scl, dim):

@@ -3,6 +3,7 @@ arguments, in-place behaviour and return values as unires/_update.py:
 
     _admm_aux      unires/_update.py:17-32
     _update_scaling unires/_update.py:270-393 (even/odd slice scaling, Gauss-Newton)
+    _update_rigid / _update_rigid_channel / _rigid_match   unires/_update.py:198-267, 448-710
     _step_size     unires/_update.py:35-64
     _compute_nll   unires/_update.py:396-427
     _update_admm   unires/_update.py:105-195
@@ -434,3 +435,152 @@ def _update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=4, verbose=0):
             po.scl = torch.tensor(scl, dtype=torch.float64, device=dev)
             sll += ll
     return x, torch.tensor(sll, dtype=torch.float64, device=dev)
+
+
+# ---------------------------------------------------------------------------
+# rigid Gauss-Newton update  (unires/_update.py:198-267, 448-710)
+# ---------------------------------------------------------------------------
+def _expm(q, basis, grad_X=False):
+    """exp(sum_i q_i B_i) (4x4, float64, host) and optionally d/dq_i, via the exact identity
+    exp([[X, B], [0, X]]) = [[exp X, dexp_X(B)], [0, exp X]] (nitorch.core._linalg_expm)."""
+    q = torch.as_tensor(q).detach().to('cpu', torch.float64)
+    basis = torch.as_tensor(basis).detach().to('cpu', torch.float64)
+    X = torch.einsum('k,kij->ij', q, basis)
+    R = torch.linalg.matrix_exp(X)
+    if not grad_X:
+        return R
+    n = X.shape[-1]
+    dR = []
+    for B in basis:
+        blk = torch.zeros(2 * n, 2 * n, dtype=torch.float64)
+        blk[:n, :n] = X
+        blk[n:, n:] = X
+        blk[:n, n:] = B
+        dR.append(torch.linalg.matrix_exp(blk)[:n, n:])
+    return R, torch.stack(dR)
+
+
+def _rigid_match(dat_x, dat_y, po, tau, rigid, sett, CtC=None, diff=False, verbose=0):
+    """Rigid matching term and (diff=True) its derivatives w.r.t. the sampling coordinates on
+    the intermediate grid (unires/_update.py:448-538).  Returns (ll, gr (*dim, 3), res) where
+    gr is the UNSCALED spatial gradient of the warped recon and res = C'(A y - x) (masked):
+    the reference's gr_m = gr * res and Hes_m = (gr_a gr_b) CtC are formed inside
+    `ur_rigid_sums`, which reduces them against d(coordinates)/dq in the same pass."""
+    from ._project import _proj_apply, _slice_profile, proj_struct
+    from .spatial import affine_grad
+    sr = sett.method == 'super-resolution'
+    trial = _lib.copy_bag(po)
+    trial.rigid = rigid
+    trial.__dict__.pop('_c_cache', None)
+    Ay = _proj_apply('A', dat_y, trial, method=sett.method, bound=sett.bound,
+                     interpolation=sett.interpolation)[0, 0]
+    out = torch.zeros(1, dtype=torch.float64, device=Ay.device)
+    check(lib.ur_nll_data(ptr(dat_x), ptr(Ay), dat_x.numel(), float(np.float32(tau)), ptr(out), 0,
+                          stream()))
+    if not diff:
+        return out[0], None, None
+    dim = tuple(po.dim_yx) if sr else tuple(po.dim_x)
+    s = proj_struct(trial, sett.method)
+    mat = torch.tensor(list(s.mat), dtype=torch.float32).reshape(3, 4)
+    gr = affine_grad(dat_y[0, 0], mat, dim)
+    res = Ay - dat_x
+    res[(dat_x == 0) | (Ay == 0)] = 0
+    if sr:
+        res = _slice_profile(res, po, transpose=True)
+    return out[0], gr, res
+
+
+def _update_rigid_channel(xc, yc, sett, max_niter_gn=1, num_linesearch=4, verbose=0, samp=3, c=1):
+    """Gauss-Newton update of rigid_q / po.rigid of every observation of one channel
+    (unires/_update.py:541-710).  The 6 + 21 chain-rule sums run in one kernel
+    (`ur_rigid_sums`); the 6x6 solve and the line-search logic stay on the host."""
+    from ._project import _proj_info, _slice_profile
+    from .spatial import affine_grid, grid_pull
+    dev = yc.dat.device
+    basis = torch.as_tensor(sett.rigid_basis).detach().to('cpu', torch.float64)
+    num_q = basis.shape[0]
+    if num_q != 6:
+        raise NotImplementedError('rigid update: SE(3) basis (6 parameters) only')
+    sr = sett.method == 'super-resolution'
+    sums = torch.zeros(27, dtype=torch.float64, device=dev)
+    cpu64 = lambda t: torch.as_tensor(t).detach().to('cpu', torch.float64)
+    sll = 0.0
+    for obs in xc:
+        q = cpu64(obs.rigid_q)
+        tau = _hs(obs.tau)
+        armijo = 1.0
+        po = _proj_info(obs.po.dim_y, obs.po.mat_y, obs.po.dim_x, obs.po.mat_x, rigid=obs.po.rigid,
+                        prof_ip=sett.profile_ip, prof_tp=sett.profile_tp, gap=sett.gap,
+                        device=dev, scl=obs.po.scl, samp=samp)
+        dim = tuple(po.dim_yx) if sr else tuple(po.dim_x)
+        src_mat = cpu64(po.mat_yx if sr else po.mat_x)
+        mat_y = cpu64(po.mat_y)
+        dat_y = yc.dat[None, None, ...]
+        if samp > 0 and po.D_x is not None:
+            grid = affine_grid(po.D_x.to(torch.float32), tuple(po.dim_x))
+            dat_x = grid_pull(obs.dat[None, None, ...], grid[None, ...], bound='zero',
+                              extrapolate=False, interpolation=0)[0, 0]
+        else:
+            dat_x = obs.dat
+        dat_x = require_cuda_f32(dat_x, 'x.dat')
+        CtC = None
+        if sr:
+            ones = torch.ones(dim, dtype=torch.float32, device=dev)
+            CtC = _slice_profile(_slice_profile(ones, po), po, transpose=True)
+        rigid, ll = cpu64(obs.po.rigid), 0.0
+        for _ in range(max_niter_gn):
+            rigid, d_rigid = _expm(q, basis, grad_X=True)
+            dm = torch.stack([torch.linalg.solve(mat_y, d_rigid[i] @ src_mat)[:3, :]
+                              for i in range(num_q)]).to(torch.float32)
+            ll_t, gr, res = _rigid_match(dat_x, dat_y, po, tau, rigid, sett, CtC=CtC, diff=True)
+            check(lib.ur_rigid_sums(ptr(gr), ptr(res), ptr(CtC) if CtC is not None else None,
+                                    i3(dim), _lib.farr(dm.reshape(-1).tolist()), ptr(sums),
+                                    stream()))
+            vals = sums.tolist()
+            ll = float(ll_t)
+            g = torch.tensor(vals[:6], dtype=torch.float64).reshape(6, 1)
+            H = torch.zeros(6, 6, dtype=torch.float64)
+            iu = torch.triu_indices(6, 6)
+            H[iu[0], iu[1]] = torch.tensor(vals[6:], dtype=torch.float64)
+            H = torch.triu(H) + torch.triu(H, 1).T
+            step = torch.linalg.solve(H, g)[:, 0]
+            old_ll, old_q, old_rigid = ll, q.clone(), rigid.clone()
+            if num_linesearch == 0:
+                q = old_q - armijo * step
+                rigid = _expm(q, basis)
+            for _ls in range(num_linesearch):
+                q = old_q - armijo * step
+                rigid = _expm(q, basis)
+                ll = float(_rigid_match(dat_x, dat_y, po, tau, rigid, sett)[0])
+                if ll < old_ll:
+                    armijo = min(1.25 * armijo, 1.0)
+                    break
+                ll, q, rigid = old_ll, old_q, old_rigid
+                armijo *= 0.5
+        obs.rigid_q = q.to(dev)
+        obs.po.rigid = rigid.to(dev)
+        sll += ll
+    return xc, torch.tensor(sll, dtype=torch.float64, device=dev)
+
+
+def _update_rigid(x, y, sett, mean_correct=True, max_niter_gn=1, num_linesearch=4, verbose=0,
+                  samp=3):
+    """Rigid registration parameters of every observation (unires/_update.py:198-267);
+    returns (x, sll).  With mean_correct the mean of all q is subtracted afterwards."""
+    dev = y[0].dat.device
+    sll = torch.zeros((), dtype=torch.float64, device=dev)
+    for c in range(len(x)):
+        x[c], s = _update_rigid_channel(x[c], y[c], sett, max_niter_gn=max_niter_gn,
+                                        num_linesearch=num_linesearch, verbose=verbose,
+                                        samp=samp, c=c)
+        sll = sll + s
+    if mean_correct:
+        basis = torch.as_tensor(sett.rigid_basis).detach().to('cpu', torch.float64)
+        qs = [torch.as_tensor(o.rigid_q).detach().to('cpu', torch.float64) for xc in x for o in xc]
+        mean_q = sum(qs) / float(len(qs))
+        for xc in x:
+            for o in xc:
+                qn = torch.as_tensor(o.rigid_q).detach().to('cpu', torch.float64) - mean_q
+                o.rigid_q = qn.to(dev)
+                o.po.rigid = _expm(qn, basis).to(dev)
+    return x, sll

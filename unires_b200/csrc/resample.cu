@@ -125,6 +125,44 @@ __global__ void lattice_shift_kernel(const float *__restrict__ in, float *__rest
   }
 }
 
+// Spatial gradient of the trilinearly interpolated volume w.r.t. the sampling coordinates
+// (nitorch grid_grad, unires/_update.py:505): along axis a the corner weights (1 - t, t) become
+// (-1, +1).  out is (ox, oy, oz, 3); zero bound, FOV tolerance as the pull.
+__global__ void affine_grad_kernel(const float *__restrict__ in, float *__restrict__ out, Dim3i s,
+                                   Dim3i o, CoordAffine coord, int extrapolate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= o.z || j >= o.y) return;
+  const size_t lin = ((size_t)i * o.y + j) * o.z + k;
+  float cx, cy, cz;
+  coord.get(i, j, k, lin, cx, cy, cz);
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  if (extrapolate || in_fov(cx, cy, cz, s)) {
+    const size_t sy = s.z, sx = (size_t)s.y * s.z;
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const float wx1 = cx - fx, wy1 = cy - fy, wz1 = cz - fz;
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int bx = (c >> 2) & 1, by = (c >> 1) & 1, bz = c & 1;
+      const int px = ix + bx, py = iy + by, pz = iz + bz;
+      if (px < 0 || px >= s.x || py < 0 || py >= s.y || pz < 0 || pz >= s.z) continue;
+      const float v = __ldg(in + px * sx + py * sy + pz);
+      const float wx = bx ? wx1 : wx0, wy = by ? wy1 : wy0, wz = bz ? wz1 : wz0;
+      const float sgx = bx ? 1.f : -1.f, sgy = by ? 1.f : -1.f, sgz = bz ? 1.f : -1.f;
+      // same association as the oracle: (w_x * w_y) * w_z with the differentiated weight +-1
+      g0 += v * ((sgx * wy) * wz);
+      g1 += v * ((wx * sgy) * wz);
+      g2 += v * ((wx * wy) * sgz);
+    }
+  }
+  out[3 * lin + 0] = g0;
+  out[3 * lin + 1] = g1;
+  out[3 * lin + 2] = g2;
+}
+
 static inline void shape_for(const Dim3i &o, dim3 &grid, dim3 &block) {
   block = dim3(64, 4, 1);
   grid = dim3(div_up(o.z, 64), div_up(o.y, 4), o.x);
@@ -228,6 +266,19 @@ extern "C" int ur_affine_push(const float *d_in, const int32_t idim[3], const fl
   UR_REQUIRE(order == 0 || order == 1, "ur_affine_push: interpolation order must be 0 or 1");
   return affine_push(d_in, make_dim(idim), mat, d_out, make_dim(sdim), order, extrapolate, scale,
                      (cudaStream_t)stream);
+}
+
+extern "C" int ur_affine_grad(const float *d_src, const int32_t sdim[3], const float mat[12],
+                              float *d_out, const int32_t odim[3], int extrapolate,
+                              ur_stream stream) {
+  UR_REQUIRE(d_src && mat && d_out && dims_ok(sdim) && dims_ok(odim), "ur_affine_grad: bad args");
+  Dim3i s = make_dim(sdim), o = make_dim(odim);
+  dim3 grid, block;
+  shape_for(o, grid, block);
+  affine_grad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_src, d_out, s, o,
+                                                               make_affine(mat), extrapolate);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
 }
 
 extern "C" int ur_affine_grid(const float mat[12], float *d_grid, const int32_t odim[3],

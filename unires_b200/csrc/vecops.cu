@@ -200,6 +200,108 @@ extern "C" int ur_scaling_sums(const float *d_x, const float *d_y, const int32_t
   return UR_OK;
 }
 
+// Gradient and Gauss-Newton Hessian of the rigid matching term w.r.t. the 6 Lie parameters
+// (unires/_update.py:616-640).  Per voxel of the intermediate grid: g = spatial gradient of the
+// warped recon (3), res = C'(A y - x) (masked), ctc = C'C 1; gr_m = g res, Hes_m = (g_a g_b) ctc.
+// With dA[i][d] = ((m0 ix + m1 iy) + m2 iz) + m3, the float32 image of d(coordinate d)/d q_i
+// (dm = 6 x 3 x 4 floats, rows of mat_y \ dR_i mat):
+//   out[i]            = sum_d sum_vox gr_m[d] dA[i][d]                          (i < 6)
+//   out[6 + tri(i,j)] = sum_{d1,d2} sum_vox (Hes_m[d1,d2] dA[i][d1]) dA[j][d2]   (i <= j)
+// float32 products summed in float64, deterministic two-stage reduction.
+struct RigidDm {
+  float m[6][3][4];
+};
+
+__global__ void __launch_bounds__(256)
+    rigid_sums_kernel(const float *__restrict__ g, const float *__restrict__ res,
+                      const float *__restrict__ ctc, Dim3i d, RigidDm dm, GridReduce gr,
+                      double *out) {
+  constexpr int NS = 27;
+  __shared__ double s_red[NS][kMaxWarps];
+  __shared__ bool s_last;
+  double part[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) part[k] = 0.0;
+  const size_t n = d.numel(), stride = (size_t)gridDim.x * blockDim.x;
+  const size_t sx = (size_t)d.y * d.z;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n; v += stride) {
+    const float fx = (float)(v / sx), fy = (float)((v / d.z) % d.y), fz = (float)(v % d.z);
+    const float gv[3] = {g[3 * v], g[3 * v + 1], g[3 * v + 2]};
+    const float rv = res[v], cv = ctc ? ctc[v] : 1.f;
+    float dA[6][3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        dA[i][a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dm.m[i][a][0], fx),
+                                                 __fmul_rn(dm.m[i][a][1], fy)),
+                                       __fmul_rn(dm.m[i][a][2], fz)),
+                             dm.m[i][a][3]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float gm = __fmul_rn(gv[a], rv);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) part[i] += (double)__fmul_rn(gm, dA[i][a]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float h = __fmul_rn(gv[a < b ? a : b], gv[a < b ? b : a]);
+        if (ctc) h = __fmul_rn(h, cv);
+        int t = 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float left = __fmul_rn(h, dA[i][a]);
+#pragma unroll
+          for (int j = i; j < 6; ++j) part[t++] += (double)__fmul_rn(left, dA[j][b]);
+        }
+      }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const double w = warp_sum(part[k]);
+    if (lane == 0) s_red[k][wid] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double w = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) w += s_red[threadIdx.x][q];
+    gr.partials[blockIdx.x * NS + threadIdx.x] = w;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(gr.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < NS) {
+    double w = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) w += __ldcg(gr.partials + b * NS + threadIdx.x);
+    out[threadIdx.x] = w;
+  }
+  if (threadIdx.x == 0) *gr.counter = 0u;
+}
+
+extern "C" int ur_rigid_sums(const float *d_grad, const float *d_res, const float *d_ctc,
+                             const int32_t dim[3], const float dm[72], double *d_out,
+                             ur_stream stream) {
+  UR_REQUIRE(d_grad && d_res && dm && d_out && dim && dim[0] > 0 && dim[1] > 0 && dim[2] > 0,
+             "ur_rigid_sums: bad args");
+  GridReduce gr;
+  int rc = scratch_reduce(&gr);
+  if (rc) return rc;
+  RigidDm m;
+  for (int k = 0; k < 72; ++k) (&m.m[0][0][0])[k] = dm[k];
+  const Dim3i d = make_dim(dim);
+  unsigned nb = red_blocks(d.numel());
+  if (nb > 2048) nb = 2048;  // 27 partials per block in the shared scratch
+  rigid_sums_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(d_grad, d_res, d_ctc, d, m, gr, d_out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
 extern "C" int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream) {
   UR_REQUIRE(d_e && d_out && n > 0, "ur_sqrt_sum: bad args");
   GridReduce gr;

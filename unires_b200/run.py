@@ -3,16 +3,17 @@ unires/run.py:24-207 -- coarse-to-fine regularisation schedule (unires/_core.py:
 ADMM iterations, convergence test on the objective, clean-FOV mask and output clamp
 (unires/_core.py:619-627).
 
-Scope: the reference's path without `sett.unified_rigid` (the rigid Gauss-Newton update raises
-NotImplementedError); `sett.scaling` runs the even/odd slice-scaling update
-(`_update._update_scaling`) after every ADMM iteration like unires/run.py:115-122; nothing is
+`sett.scaling` runs the even/odd slice-scaling update (`_update._update_scaling`) after every
+ADMM iteration (unires/run.py:115-122) and `sett.unified_rigid` the rigid Gauss-Newton update
+(`_update._update_rigid`) every `rigid_mod` iterations (unires/run.py:127-135); nothing is
 written to disk.  `init` / `preproc` (I/O, hyper-parameter estimation, co-registration) are out of
 scope: the caller supplies x (observations with tau, mu, po) and y (recon with lam0, mat).
 """
 import torch
 
 from . import _lib
-from ._update import _admm_aux, _step_size, _update_admm, _update_scaling
+from ._update import (_admm_aux, _expm, _step_size, _update_admm, _update_rigid,
+                      _update_scaling)
 from .optim import get_gain
 from .spatial import affine_grid
 
@@ -49,11 +50,10 @@ def fit(x, y, sett):
 
     Returns (dat_y, mat_y, pth_y, R, label, pth_label) like the reference: dat_y is the
     reconstruction as float32 (X, Y, Z, C); pth_y is empty and label None (nothing is
-    written); R holds one identity matrix per observation (no rigid update).
+    written); R holds the rigid matrix exp(sum q_i B_i) of every observation.
     `fit.last` keeps {'n_iter', 'obj', 'jtv', 'reg_scl'} of the run."""
-    if getattr(sett, 'unified_rigid', False):
-        raise NotImplementedError('the rigid Gauss-Newton update is out of scope '
-                                  '(SURVEY.md section 8f)')
+    if getattr(sett, 'unified_rigid', False) and getattr(sett, 'rigid_basis', None) is None:
+        raise ValueError('sett.unified_rigid needs sett.rigid_basis (the SE(3) Lie basis)')
     with torch.no_grad():
         N = sum(len(xc) for xc in x)
         sett = _get_sched(N, sett)
@@ -84,6 +84,11 @@ def fit(x, y, sett):
             # even/odd slice scaling (unires/run.py:115-122)
             if getattr(sett, 'scaling', False):
                 x, _ = _update_scaling(x, y, sett, max_niter_gn=1, num_linesearch=6)
+            # rigid alignment of every observation (unires/run.py:127-135)
+            if getattr(sett, 'unified_rigid', False) and n_iter > 0 and \
+                    n_iter % sett.rigid_mod == 0:
+                x, _ = _update_rigid(x, y, sett, mean_correct=False, max_niter_gn=1,
+                                     num_linesearch=6, samp=sett.rigid_samp)
             # coarse-to-fine: next regularisation level, new ADMM step size
             if cnt_scl + 1 < len(sett.reg_scl) and cnt_scl_iter > 16 and bool(gain.abs() < 1e-3):
                 countdown1 -= 1
@@ -107,6 +112,11 @@ def fit(x, y, sett):
             chans.append(yc.dat[..., None])
         dat_y = torch.cat(chans, dim=3)
         R = torch.eye(4, dtype=torch.float64, device=sett.device).repeat(N, 1, 1)
+        if getattr(sett, 'rigid_basis', None) is not None:
+            obs_all = [o for xc in x for o in xc]
+            for k, o in enumerate(obs_all):
+                if getattr(o, 'rigid_q', None) is not None:
+                    R[k] = _expm(o.rigid_q, sett.rigid_basis).to(sett.device)
         fit.last = {'n_iter': n_done, 'obj': obj[:n_done].clone(), 'jtv': tmp,
                     'reg_scl': sett.reg_scl}
         return dat_y, y[0].mat, [], R, None, None

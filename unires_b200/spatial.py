@@ -188,3 +188,15 @@ def im_divergence(dat, vx=None, which='forward', bound='zero'):
     out = torch.empty(tuple(d.shape[1:]), dtype=torch.float32, device=d.device)
     check(lib.ur_im_divergence(ptr(d), ptr(out), i3(d.shape[1:]), f3(_vx3(vx)), stream()))
     return out
+
+
+def affine_grad(dat, mat, shape, extrapolate=False):
+    """nitorch.spatial.grid_grad for an affine sampling grid (unires/_update.py:505): the
+    gradient of the trilinearly interpolated (X, Y, Z) volume `dat` w.r.t. the sampling
+    coordinates at grid[i,j,k] = mat[:3,:3] (i,j,k) + mat[:3,3]; returns (*shape, 3)."""
+    d = require_cuda_f32(dat, 'dat')
+    m = torch.as_tensor(mat).detach().to('cpu', torch.float32)[:3, :].reshape(-1).tolist()
+    out = torch.empty(tuple(shape) + (3,), dtype=torch.float32, device=d.device)
+    check(lib.ur_affine_grad(ptr(d), i3(d.shape), _lib.farr(m), ptr(out), i3(shape),
+                             1 if extrapolate else 0, stream()))
+    return out
