@@ -136,6 +136,7 @@ if __name__ == '__main__' and not {'--fit', '--scaling', '--rigid'} & set(sys.ar
     main()
     main_fit()
     main_fit(scaling=True)
+    main_fit(rigid=True)
     main_scaling()
     main_rigid()
 
@@ -151,14 +152,23 @@ FIT_SCALING_RECIPE = dict(base='thickz2_256', dim_y=(16, 14, 20), n_channels=2, 
                           rigid=None, max_iter=40)
 
 
-def prepare_fit(sc, reference=False, scaling=False):
+FIT_RIGID_RECIPE = dict(base='sr3_256', dim_y=(20, 24, 22), n_channels=2, sd=10.0, scl=0.0,
+                        rigid=None, max_iter=30, q0=[0.6, -0.4, 0.3, 0.01, -0.015, 0.02])
+
+
+def prepare_fit(sc, reference=False, scaling=False, rigid=False):
     """Settings of the fit fixture (and the fields only the reference's fit touches)."""
     s = sc.sett
-    recipe = FIT_SCALING_RECIPE if scaling else FIT_RECIPE
+    recipe = FIT_SCALING_RECIPE if scaling else (FIT_RIGID_RECIPE if rigid else FIT_RECIPE)
     s.max_iter, s.tolerance, s.reg_scl, s.sched_num = recipe['max_iter'], 1e-4, 4.0, 3
     s.clean_fov, s.scaling, s.unified_rigid, s.rigid_mod = True, scaling, False, 1
+    s.rigid_samp = 1
     if scaling:  # the data carry exp(+-0.1); the fit starts from 0 and has to find it
         prepare_scaling(sc, 0.0)
+    if rigid:  # the operators start mis-registered; the fit has to re-align them
+        from oracle.unires_port import expm
+        s.unified_rigid = True
+        prepare_rigid(sc, FIT_RIGID_RECIPE['q0'], expm)
     if reference:
         from oracle.nitorch_shim.spatial import affine_basis
         s.rigid_basis = affine_basis(group='SE', dtype=torch.float64)
@@ -166,18 +176,19 @@ def prepare_fit(sc, reference=False, scaling=False):
             False, False, False, False, None, 0
         for xc in sc.x:
             for o in xc:
-                o.rigid_q = torch.zeros(6, dtype=torch.float64)
+                if not rigid:
+                    o.rigid_q = torch.zeros(6, dtype=torch.float64)
                 o.direc = o.nam = None
     return sc
 
 
-def main_fit(scaling=False):
+def main_fit(scaling=False, rigid=False):
     from oracle.adapters import reference_namespaces
     from oracle.load_reference import load_reference
     ref = load_reference()
     ops, structs = reference_namespaces()
-    recipe = FIT_SCALING_RECIPE if scaling else FIT_RECIPE
-    sc = prepare_fit(build(recipe, ops, structs), reference=True, scaling=scaling)
+    recipe = FIT_SCALING_RECIPE if scaling else (FIT_RIGID_RECIPE if rigid else FIT_RECIPE)
+    sc = prepare_fit(build(recipe, ops, structs), reference=True, scaling=scaling, rigid=rigid)
     obj_rows = []
     orig = ref.run._update_admm
 
@@ -188,13 +199,17 @@ def main_fit(scaling=False):
 
     ref.run._update_admm = spy
     try:
-        dat_y = ref.run.fit(sc.x, sc.y, sc.sett)[0]
+        fit_out = ref.run.fit(sc.x, sc.y, sc.sett)
+        dat_y = fit_out[0]
     finally:
         ref.run._update_admm = orig
     out = {'recipe': json.dumps(recipe), 'dat_y': dat_y.numpy(),
            'obj': torch.stack(obj_rows).numpy(), 'n_iter': np.int32(len(obj_rows)),
-           'scl': np.array([float(o.po.scl) for xc in sc.x for o in xc])}
-    path = os.path.join(GOLDEN_DIR, 'fit_scaling.npz' if scaling else 'fit_sr2.npz')
+           'scl': np.array([float(o.po.scl) for xc in sc.x for o in xc]),
+           'q': np.array([o.rigid_q.tolist() for xc in sc.x for o in xc]),
+           'R': fit_out[3].numpy()}
+    path = os.path.join(GOLDEN_DIR, 'fit_scaling.npz' if scaling else
+                        ('fit_rigid.npz' if rigid else 'fit_sr2.npz'))
     np.savez_compressed(path, **out)
     print(os.path.basename(path), 'scl', out['scl'].tolist(), 'n_iter', len(obj_rows), 'obj', obj_rows[0][0].item(), '->', obj_rows[-1][0].item(),
           '%.0f KB' % (os.path.getsize(path) / 1024))
@@ -291,6 +306,7 @@ def main_rigid():
 if __name__ == '__main__' and '--fit' in sys.argv:
     main_fit()
     main_fit(scaling=True)
+    main_fit(rigid=True)
 if __name__ == '__main__' and '--rigid' in sys.argv:
     main_rigid()
 if __name__ == '__main__' and '--scaling' in sys.argv:

@@ -70,9 +70,37 @@ def test_fit_with_scaling_matches_reference_fixture(cuda):
     assert U.rel_l2(dat_y, g['dat_y']) < 1e-3
 
 
-def test_fit_rejects_out_of_scope_updates(cuda):
+def test_fit_with_rigid_matches_reference_fixture(cuda):
+    """sett.unified_rigid: observations whose operators start mis-registered by exp(+-q0) are
+    re-aligned by the Gauss-Newton update interleaved with the ADMM iterations
+    (unires/run.py:127-135); trajectory against the reference's own fit."""
+    from unires_b200 import run
+    g = np.load(U.GOLDEN_DIR + '/fit_rigid.npz', allow_pickle=False)
+    recipe = json.loads(str(g['recipe']))
+    sc = gen_golden.prepare_fit(U.build(recipe, *U.port_namespaces()), rigid=True)
+    x, y, sett = U.to_device(sc, cuda)
+    for k in ('max_iter', 'tolerance', 'reg_scl', 'sched_num', 'clean_fov', 'scaling',
+              'unified_rigid', 'rigid_mod', 'rigid_samp', 'rigid_basis'):
+        setattr(sett, k, getattr(sc.sett, k))
+    for c in range(len(y)):
+        y[c].lam0 = torch.tensor(float(sc.y[c].lam0), device=cuda)
+        for n, o in enumerate(x[c]):
+            o.dim = tuple(sc.x[c][n].dat.shape)
+            o.tau = torch.tensor(float(sc.x[c][n].tau), device=cuda)
+            o.rigid_q = sc.x[c][n].rigid_q.clone()
+    dat_y, _, _, R, _, _ = run.fit(x, y, sett)
+    last = run.fit.last
+    assert last['n_iter'] == int(g['n_iter'])
+    q = np.array([o.rigid_q.cpu().tolist() for xc in x for o in xc])
+    assert np.allclose(q, g['q'], rtol=5e-3, atol=1e-4), (q, g['q'])
+    assert np.allclose(R.cpu().numpy(), g['R'], atol=1e-3)
+    assert np.allclose(last['obj'].cpu().numpy(), g['obj'], rtol=2e-3)
+    assert U.rel_l2(dat_y, g['dat_y']) < 2e-3
+
+
+def test_fit_unified_rigid_needs_a_basis(cuda):
     from unires_b200 import run, struct
     s = struct.settings()
     s.unified_rigid = True
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         run.fit([], [], s)
