@@ -29,6 +29,8 @@ CONFIGS = {
     'thickz2_384x8': dict(dim_y=(384, 384, 384), fov=None, vx_y=1.0, thick=[(2, 2)] * 8),
     # configs[4]: 0.5 mm recon of 1 mm isotropic data, 512^3 (ratio 2 on every axis)
     'iso2_512': dict(dim_y=(512, 512, 512), fov=None, vx_y=0.5, thick=[None] * 3, vx_x=1.0),
+    # one channel of configs[3] (what one GPU holds)
+    'thickz2_384': dict(dim_y=(384, 384, 384), fov=None, vx_y=1.0, thick=[(2, 2)]),
     # other clinical slice ratios (tuning / coverage of the lean kernel's specialisations)
     'thick3_256': dict(dim_y=(256, 256, 256), fov=None, vx_y=1.0, thick=[(0, 3), (1, 3), (2, 3)]),
     'thick6_256': dict(dim_y=(256, 256, 256), fov=None, vx_y=1.0, thick=[(0, 6), (1, 6), (2, 6)]),
