@@ -17,6 +17,7 @@ Reference lines restated (relative to /root/reference):
   update_admm                unires/_update.py:105-195
   even_odd / update_scaling  unires/_update.py:430-445, 270-393
   rigid_match / update_rigid_channel / update_rigid   unires/_update.py:448-538, 541-710, 198-267
+  init_y_dat                 unires/_core.py:371-399
 """
 import math
 import types
@@ -534,3 +535,28 @@ def update_rigid(x, y, sett, mean_correct=True, max_niter_gn=1, num_linesearch=4
                 obs.rigid_q -= mean_q
                 obs.po.rigid = expm(obs.rigid_q, sett.rigid_basis)
     return x, sll
+
+
+# ----------------------------------------------------------------------------
+# initial estimate  (unires/_core.py:371-399)
+# ----------------------------------------------------------------------------
+def init_y_dat(x, y, sett):
+    """Trilinear pull of every observation into the recon grid, clamped to the observation's
+    range, averaged over the repeats that are positive at a voxel."""
+    dim_y, mat_y = tuple(y[0].dim), y[0].mat
+    for c in range(len(x)):
+        total = torch.zeros(dim_y, dtype=torch.float32)
+        count = torch.zeros(dim_y, dtype=torch.float32)
+        for obs in x[c]:
+            dat = obs.dat[None, None]
+            vox = torch.linalg.solve(obs.mat, mat_y)
+            grid = S.affine_grid(vox.to(dat.dtype), dim_y)[None]
+            lo, hi = torch.min(dat), torch.max(dat)
+            pulled = S.grid_pull(dat, grid, bound='zero', extrapolate=False, interpolation=1)
+            pulled[pulled < lo] = lo
+            pulled[pulled > hi] = hi
+            count = count + (pulled[0, 0] > 0)
+            total = total + pulled[0, 0]
+        count[count == 0] = 1.0
+        y[c].dat = total / count
+    return y

@@ -179,3 +179,15 @@ def test_check_adjoint(cuda):
                                  scl=0.1, device=cuda)
         val = _project._check_adjoint(po, 'super-resolution', 'zero', 'linear')
         assert abs(val.item()) < 1e-2  # float32 sums of O(1e4) terms (reference prints ~1e-6..1e-3)
+
+
+def test_init_y_dat_vs_oracle(cuda):
+    """Initial estimate (unires/_core.py:371-399) on the CUDA pull kernel against the port."""
+    from oracle import gen_golden
+    from unires_b200 import io
+    sc = U.build(gen_golden.RECIPES['sr2_rigid'], *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    P.init_y_dat(sc.x, sc.y, sc.sett)
+    io._init_y_dat(x, y, sett)
+    for a, b in zip(y, sc.y):
+        assert U.rel_l2(a.dat, b.dat) < 1e-5

@@ -87,3 +87,18 @@ def test_port_update_rigid_matches_reference_bitwise(name):
         for xp, xr in zip(sp.x, sr.x):
             assert torch.equal(xp[0].rigid_q, xr[0].rigid_q)
             assert torch.equal(xp[0].po.rigid, xr[0].po.rigid)
+
+
+def test_port_init_y_dat_matches_reference_bitwise():
+    """Initial estimate by trilinear pull + averaging (unires/_core.py:371-399)."""
+    from oracle import gen_golden
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    recipe = gen_golden.RECIPES['sr2_rigid']
+    sp = U.build(recipe, *U.port_namespaces())
+    sr = U.build(recipe, *reference_namespaces())
+    sr.sett.device = 'cpu'
+    P.init_y_dat(sp.x, sp.y, sp.sett)
+    ref._core._init_y_dat(sr.x, sr.y, sr.sett)
+    for a, b in zip(sp.y, sr.y):
+        assert torch.equal(a.dat, b.dat)
