@@ -14,6 +14,8 @@ namespace ur {
 int affine_pull(const float *, Dim3i, const float[12], float *, Dim3i, int, int, cudaStream_t);
 int affine_push(const float *, Dim3i, const float[12], float *, Dim3i, int, int, float,
                 cudaStream_t);
+int affine_push_gather(const float *, Dim3i, const float[12], float *, Dim3i, int, float,
+                       cudaStream_t);
 int lattice_pull(const float *, Dim3i, const float[12], float *, Dim3i, cudaStream_t);
 int lattice_push(const float *, Dim3i, const float[12], float *, Dim3i, float, cudaStream_t);
 int conv_axis(const float *, Dim3i, float *, int, const float *, int, int, bool, cudaStream_t,
@@ -189,6 +191,9 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
     if (rc) return rc;
   }
   if (lat) return lattice_push(cur, dsrc, po->mat, d_out, dy, scale, st);
+  // rotated operators: deterministic gather-form push; the atomic scatter only as a fallback
+  rc = affine_push_gather(cur, dsrc, po->mat, d_out, dy, 0, scale, st);
+  if (rc != UR_ERR_UNSUPPORTED) return rc;
   return affine_push(cur, dsrc, po->mat, d_out, dy, 1, 0, scale, st);
 }
 

@@ -104,6 +104,52 @@ __global__ void affine_grid_kernel(float *__restrict__ grid, Dim3i o, CoordAffin
   grid[3 * lin + 2] = cz;
 }
 
+// Gather form of the trilinear push for an AFFINE grid (deterministic, no atomics): a thread
+// owns one TARGET voxel q and enumerates the source voxels p whose mapped coordinate
+// c(p) = A p + t falls strictly within one voxel of q on every axis -- the preimage of that
+// cube is contained in the box  A^-1 (q - t) +- sum_b |A^-1[a][b]|.  Coordinates, FOV test and
+// corner weights are evaluated exactly like the scatter form (same float32 expressions), so
+// the two differ only in summation order.  dst[q] += scale * sum_p w(p, q) in[p].
+struct AffineInv {
+  float m[12];  // rows of [A^-1 | -A^-1 t]
+  float h[3];   // half extents of the candidate box per source axis
+};
+
+__global__ void affine_push_gather_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                          Dim3i s, Dim3i o, CoordAffine coord, AffineInv inv,
+                                          int extrapolate, float scale) {
+  const int qz = blockIdx.x * blockDim.x + threadIdx.x;
+  const int qy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int qx = blockIdx.z;
+  if (qz >= s.z || qy >= s.y) return;
+  const float fqx = (float)qx, fqy = (float)qy, fqz = (float)qz;
+  int lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pc = inv.m[4 * a + 0] * fqx + inv.m[4 * a + 1] * fqy + inv.m[4 * a + 2] * fqz +
+                     inv.m[4 * a + 3];
+    const int n = a == 0 ? o.x : (a == 1 ? o.y : o.z);
+    lo[a] = max(0, (int)ceilf(pc - inv.h[a]));
+    hi[a] = min(n - 1, (int)floorf(pc + inv.h[a]));
+  }
+  float acc = 0.f;
+  for (int i = lo[0]; i <= hi[0]; ++i)
+    for (int j = lo[1]; j <= hi[1]; ++j)
+      for (int k = lo[2]; k <= hi[2]; ++k) {
+        const size_t lin = ((size_t)i * o.y + j) * o.z + k;
+        float cx, cy, cz;
+        coord.get(i, j, k, lin, cx, cy, cz);
+        if (!(extrapolate || in_fov(cx, cy, cz, s))) continue;
+        const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+        const int bx = qx - (int)fx, by = qy - (int)fy, bz = qz - (int)fz;
+        if ((unsigned)bx > 1u || (unsigned)by > 1u || (unsigned)bz > 1u) continue;
+        const float wx1 = cx - fx, wy1 = cy - fy, wz1 = cz - fz;
+        const float wgt = ((bx ? wx1 : 1.f - wx1) * (by ? wy1 : 1.f - wy1)) * (bz ? wz1 : 1.f - wz1);
+        acc += (scale * __ldg(in + lin)) * wgt;
+      }
+  out[((size_t)qx * s.y + qy) * s.z + qz] += acc;
+}
+
 // Lattice-aligned operators (identity rotation, integer translation): pull is a shifted crop,
 // push a shifted zero-pad embed -- one corner of weight exactly 1, a one-to-one mapping, so
 // the push needs no atomics.  o = grid of the coordinates, s = the volume they point into.
@@ -190,6 +236,48 @@ int affine_push(const float *in, Dim3i o, const float mat[12], float *out, Dim3i
   shape_for(o, grid, block);
   resample_kernel<CoordAffine, true>
       <<<grid, block, 0, st>>>(in, out, s, o, make_affine(mat), order, extrapolate, scale);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+// Deterministic push for an affine grid; returns UR_ERR_UNSUPPORTED when the linear part is
+// (numerically) singular or the candidate box would be unreasonably large.
+int affine_push_gather(const float *in, Dim3i o, const float mat[12], float *out, Dim3i s,
+                       int extrapolate, float scale, cudaStream_t st) {
+  const double a[3][3] = {{mat[0], mat[1], mat[2]}, {mat[4], mat[5], mat[6]}, {mat[8], mat[9], mat[10]}};
+  const double t[3] = {mat[3], mat[7], mat[11]};
+  const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
+                     a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                     a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+  if (!(fabs(det) > 1e-9)) return UR_ERR_UNSUPPORTED;
+  double iv[3][3];
+  iv[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det;
+  iv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+  iv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det;
+  iv[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+  iv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det;
+  iv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+  iv[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det;
+  iv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+  iv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+  AffineInv inv;
+  double cand = 1.0;
+  for (int r = 0; r < 3; ++r) {
+    double h = 0.0, off = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      inv.m[4 * r + c] = (float)iv[r][c];
+      h += fabs(iv[r][c]);
+      off -= iv[r][c] * t[c];
+    }
+    inv.m[4 * r + 3] = (float)off;
+    inv.h[r] = (float)(h * 1.0005 + 1e-2);  // float32 slack on coordinates up to ~1e3
+    cand *= 2.0 * inv.h[r] + 1.0;
+  }
+  if (cand > 4096.0) return UR_ERR_UNSUPPORTED;
+  dim3 grid, block;
+  shape_for(s, grid, block);
+  affine_push_gather_kernel<<<grid, block, 0, st>>>(in, out, s, o, make_affine(mat), inv,
+                                                    extrapolate, scale);
   UR_LAUNCH_CHECK();
   return UR_OK;
 }
