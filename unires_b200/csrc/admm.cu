@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 
+int jtv_block_rows = 4;  // measured at 3x256^3: 8 rows 502 us, 4 rows 478 us, 2 rows 484 us
+
 static bool ptr16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
 static int fill(ChannelPtrs *ch, const float *const *y, const float *lam, int C) {
@@ -282,7 +284,8 @@ static int launch(const float *const *y, float *z, float *w, float *nrm2, float 
   if (vec) {
     const bool wide = C <= 2 || MODE == JTV_PRIOR;
     const int V = wide ? 4 : 2;
-    dim3 vblock(32, 8, 1), vgrid(div_up(g.nz, 32 * V), div_up(g.ny, 8), g.nx);
+    const int by = jtv_block_rows;  // rows per block (tuning knob "jtv_rows": 8 | 4 | 2)
+    dim3 vblock(32, by, 1), vgrid(div_up(g.nz, 32 * V), div_up(g.ny, by), g.nx);
 #define UR_JTV_V(CT, VV)                                                                    \
   jtv_kernel_vec<MODE, CT, VV><<<vgrid, vblock, 0, st>>>(ch, z, w, nrm2, jtv, g, accumulate)
     switch (C) {

@@ -572,6 +572,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
 extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
+extern int jtv_block_rows;  // admm.cu
 extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock;  // lhs_fast.cu
 static int g_lhs_variant = 0;
 static int g_cg_fuse = 1;
@@ -727,6 +728,8 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_rpt = (value == 1 || value == 2) ? value : 0;
   } else if (!strcmp(name, "fast_depth")) {
     fast_depth = value < 1 ? 1 : value;
+  } else if (!strcmp(name, "jtv_rows")) {
+    jtv_block_rows = (value == 2 || value == 8) ? value : 4;
   } else if (!strcmp(name, "vec_blocks")) {
     g_vec_blocks_per_sm = value < 1 ? 1 : value;
   } else if (!strcmp(name, "r_reverse")) {
