@@ -1,3 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(for r in 8 4 2; do echo "== jtv_rows $r"; timeout 300 python scripts/microbench_admm.py sr3_256 1e-3 jtv_rows=$r 2>&1 | grep "jtv prox"; done) | tee gpurun_out/jtv_rows.log
+python -c "
+import cProfile, pstats, sys, io
+sys.argv = ['sr_demo.py', '--max-iter', '40']
+sys.path.insert(0, 'demos')
+import runpy
+pr = cProfile.Profile()
+pr.enable()
+try:
+    runpy.run_path('demos/sr_demo.py', run_name='__main__')
+finally:
+    pr.disable()
+    s = io.StringIO()
+    pstats.Stats(pr, stream=s).sort_stats('cumulative').print_stats(45)
+    print(s.getvalue()[:9000])
+" > gpurun_out/demo_profile.log 2>&1
+tail -70 gpurun_out/demo_profile.log | cut -c1-160
