@@ -264,3 +264,60 @@ def test_cg_padded_rows_for_odd_nz(cuda, case, stop, tol):
     assert res[0][1] == res[1][1] == OO.cg.last_n_iter
     assert U.rel_l2(res[0][0], res[1][0]) < 1e-5
     assert U.rel_l2(res[0][0], xo) < U.REL_TOL
+
+
+def _fuzz_cases(n, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < n:
+        axis = rng.choice([0, 1, 2])
+        factor = rng.choice([2, 3, 4, 5, 6, 8])
+        dim = [rng.randrange(9, 40), rng.randrange(9, 40), 4 * rng.randrange(3, 70)]
+        dim[axis] = max(dim[axis], 3 * factor + rng.randrange(0, 30)) if axis < 2 else \
+            4 * ((3 * factor + rng.randrange(4, 200)) // 4 + 1)
+        fov = None
+        if rng.random() < 0.6:
+            fov = [max(factor + 2 if a == axis else 4, d - rng.randrange(0, 9)) for a, d in enumerate(dim)]
+        scl = rng.choice([0.0, 0.0, 0.1, -0.07])
+        cases.append((tuple(dim), None if fov is None else tuple(fov), axis, factor, scl,
+                      rng.choice([0, 0, 1, 2, 3, 5]), rng.choice([0, 1, 2])))
+    return cases
+
+
+@pytest.mark.parametrize('case', _fuzz_cases(40, 1234), ids=lambda c: '%dx%dx%d-a%d-r%d' % (c[0] + (c[2], c[3])))
+def test_lean_kernel_fuzz_vs_direct(cuda, case):
+    """Random grids / fields of view / thick axes / ratios / work splits: the lean kernel (plain
+    matvec with its dot product, and whole fused CG solves under both stop rules) against the
+    direct one-thread-per-voxel kernel."""
+    from unires_b200 import _project, optim
+    dim_y, fov, axis, factor, scl, chunk, rpt = case
+    obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    v = (torch.rand(dim_y, generator=g) - 0.3).to(cuda)
+    b = (torch.rand(dim_y, generator=g) * 0.1).to(cuda)
+    op = _project.LhsOperator([obs_g], rec_g, rho=1.1, vx_y=[1.0, 1.2, 0.9])
+    res = {}
+    try:
+        for variant in (1, 0):
+            _reset()
+            _tune('lhs_variant', variant)
+            if variant == 0:
+                _select('fast', chunk, rpt)
+            dot = torch.zeros(1, dtype=torch.float64, device=cuda)
+            out = op(v, dot=dot)
+            path = _last_path()
+            sol = []
+            for stop, tol in (('max_gain', 1e-3), ('residual', 0.0)):
+                x = v.clone()
+                optim.cg(A=op, b=b, x=x, max_iter=6, tolerance=tol, stop=stop)
+                sol.append((x, optim.cg.last.n_iter))
+            res[variant] = (out, dot.item(), sol, path)
+    finally:
+        _reset()
+    assert res[0][3] == 2 and res[1][3] == 0
+    assert U.rel_l2(res[0][0], res[1][0]) < 2e-6
+    assert abs(res[0][1] - res[1][1]) < 1e-5 * abs(res[1][1])
+    for (xa, na), (xb, nb) in zip(res[0][2], res[1][2]):
+        assert na == nb
+        assert U.rel_l2(xa, xb) < 1e-5
