@@ -45,10 +45,12 @@ def test_cg_per_iterate_parity_and_trip_count(cuda, name, stop):
         info = optim.cg.last
         assert info.n_iter == n_ref, (name, c, stop)
         assert U.rel_l2(xg, xo) < U.REL_TOL
-        # the objective trace: 1e-5 under the energy rule; sqrt(r.r) of the recursively updated
-        # residual amplifies the kernels' different float32 rounding towards convergence
-        assert np.allclose(info.obj, obj_ref.numpy(), rtol=1e-5 if stop == 'max_gain' else 1e-4,
-                           atol=1e-8 * abs(obj_ref[0].item()))
+        # the objective trace.  The kernels round D'D differently from the reference
+        # (diag*c - sum(neighbours) vs differences of differences); the energy 0.5 x'Ax - b'x and
+        # sqrt(r.r) of the recursively updated residual both lose relative accuracy as they
+        # shrink towards convergence, hence an absolute floor relative to the first value
+        assert np.allclose(info.obj, obj_ref.numpy(), rtol=1e-4,
+                           atol=1e-6 * abs(obj_ref[0].item()))
         # per-iterate parity: fixed trip counts, no stop test
         for k in sorted(set([1, 2, 3, n_ref])):
             xk = x0.clone()

@@ -25,7 +25,8 @@ static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 
 // dry_run: eligibility check only, nothing is launched
 int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   using namespace fast;
-  if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
+  if (A.nterm > 1) return UR_ERR_UNSUPPORTED;  // solver.cu splits several terms into passes
+  if (!a16(A.acc)) return UR_ERR_UNSUPPORTED;
   const int pitch = A.pitch > 0 ? A.pitch : A.nz;
   if (pitch % 4 != 0 || pitch < A.nz || pitch - A.nz >= 4 || A.nz < 4) return UR_ERR_UNSUPPORTED;
   if ((long long)A.nx * A.ny * pitch + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)
@@ -210,6 +211,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.update_p = A.update_p;
   S.p_out = A.p_out;
   S.xup = A.xup;
+  S.acc = A.acc;
   S.done = A.done;
   S.gr = A.gr;
   S.fin = A.fin;

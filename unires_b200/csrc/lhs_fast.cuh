@@ -72,6 +72,7 @@ struct FastArgs {
   int update_p;
   float *p_out;
   float *xup;
+  const float *acc;  // optional volume added to A v (other observations' terms, general path)
   const int *done;
   GridReduce gr;
   FinalizeArgs fin;
@@ -642,6 +643,13 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             }
             if (act[i]) {
               const int gi = goff_u + i * a.gs_o;
+              if (a.acc != nullptr) {  // may alias `out` (read before the store below)
+                const float4 aq = *reinterpret_cast<const float4 *>(a.acc + gi);
+                val[0] += aq.x;
+                val[1] += aq.y;
+                val[2] += aq.z;
+                val[3] += aq.w;
+              }
               if (MODE == LHS_PLAIN || MODE == LHS_COMBINE) {
                 *reinterpret_cast<float4 *>(a.out + gi) =
                     make_float4(val[0], val[1], val[2], val[3]);

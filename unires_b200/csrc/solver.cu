@@ -535,7 +535,8 @@ static size_t lhs_partials_bytes(const LhsPlan &P) {
 
 static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
   size_t s = 256 + lhs_partials_bytes(P);
-  if (P.n_general) s += vol_bytes(lhs) + align_up(P.proj_ws);
+  // accumulator volume: general-path observations and / or all but one lattice term
+  if (P.n_general || P.args.nterm > 1) s += vol_bytes(lhs) + align_up(P.proj_ws);
   return s;
 }
 
@@ -557,7 +558,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   w.acc = nullptr;
   w.proj = nullptr;
   w.proj_bytes = 0;
-  if (P.n_general) {
+  if (P.n_general || P.args.nterm > 1) {
     w.acc = (float *)c;
     c += vol_bytes(lhs);
     w.proj = c;
@@ -599,6 +600,32 @@ static cudaEvent_t prof_event(int which) {
   return g_prof.ev[2 * g_prof.used + which];
 }
 
+// One lattice term of a multi-observation operator as a stand-alone "term only" operator.
+static LhsArgs single_term(const LhsArgs &A, int t, bool with_regulariser) {
+  LhsArgs T = A;
+  T.nterm = 1;
+  T.term[0] = A.term[t];
+  if (!with_regulariser) {
+    T.rl2 = 0.f;
+    T.w_ident = 0.f;
+  }
+  return T;
+}
+
+// Can the lean TMA kernel evaluate `mode` for these arguments?  Several lattice terms (one
+// channel observed by several scans) are evaluated as passes: every term but the last is
+// accumulated by a plain "term only" launch, the last one carries D'D and the CG epilogue.
+static bool lean_supports(int mode, const LhsArgs &A, cudaStream_t st) {
+  if (A.nterm <= 1) return lhs_fast_launch(mode, A, true, st) == UR_OK;
+  if (mode == LHS_COMBINE || mode == LHS_ECOMBINE) return false;  // v is formed in-kernel
+  for (int t = 0; t + 1 < A.nterm; ++t) {
+    LhsArgs T = single_term(A, t, false);
+    T.out = const_cast<float *>(A.v);  // any aligned pointer: eligibility only
+    if (lhs_fast_launch(LHS_PLAIN, T, true, st) != UR_OK) return false;
+  }
+  return lhs_fast_launch(mode, single_term(A, A.nterm - 1, true), true, st) == UR_OK;
+}
+
 // Launch one lhs evaluation.  `A` carries the mode-specific pointers.
 static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs &w, LhsArgs A,
                       int variant, cudaStream_t st) {
@@ -615,6 +642,21 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
   }
   A.gr = GridReduce{w.partials, w.counter};
+  if (A.nterm > 1 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc != nullptr &&
+      lean_supports(mode, A, st)) {
+    // several lattice observations: term-only passes into the accumulator, then the last term
+    // with the regulariser and the epilogue (each pass marches along its own thick axis)
+    for (int t = 0; t + 1 < A.nterm; ++t) {
+      LhsArgs T = single_term(A, t, false);
+      T.out = w.acc;
+      T.acc = (t > 0 || P.n_general) ? w.acc : nullptr;
+      T.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, nullptr};
+      int rc = lhs_fast_launch(LHS_PLAIN, T, false, st);
+      if (rc) return rc;
+    }
+    A = single_term(A, A.nterm - 1, true);
+    A.acc = w.acc;
+  }
   const bool is_matvec = mode == LHS_PLAIN || mode == LHS_COMBINE;
   const bool lean_only = mode == LHS_ECOMBINE || (mode == LHS_COMBINE && A.xup == nullptr);
   cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
@@ -895,9 +937,8 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
     T.r = cw.r;
     T.p = cw.p;
     T.out = cw.Ap;
-    padded = lhs_fast_launch(LHS_RESID, T, true, st) == UR_OK &&
-             lhs_fast_launch(LHS_PLAIN, T, true, st) == UR_OK &&
-             lhs_fast_launch(LHS_ENERGY, T, true, st) == UR_OK;
+    padded = lean_supports(LHS_RESID, T, st) && lean_supports(LHS_PLAIN, T, st) &&
+             lean_supports(LHS_ENERGY, T, st);
   }
   if (padded) {
     UR_CUDA_CHECK(cudaMemsetAsync(cw.b_pad, 0, 2 * vol_bytes(lhs), st));  // b_pad and x_pad
