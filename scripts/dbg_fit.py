@@ -6,6 +6,9 @@ from oracle import gen_golden
 from tests import _util as U
 from unires_b200 import run, _update
 cuda = torch.device('cuda:0')
+from unires_b200 import _lib
+if len(sys.argv) > 1:
+    _lib.check(_lib.lib.ur_tune(b'fast_diag_residue', int(sys.argv[1])))
 g = np.load(U.GOLDEN_DIR + '/fit_sr2.npz', allow_pickle=False)
 recipe = json.loads(str(g['recipe']))
 sc = gen_golden.prepare_fit(U.build(recipe, *U.port_namespaces()))

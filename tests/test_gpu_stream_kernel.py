@@ -373,3 +373,56 @@ def test_multi_view_channel_through_lean_passes(cuda, dim_y, fov):
     for k in range(2):
         assert res[0][1][k][1] == res[1][1][k][1] == sols_o[k][1]
         assert U.rel_l2(res[0][1][k][0], sols_o[k][0]) < U.REL_TOL
+
+
+@pytest.mark.parametrize('dim_y,zoom,fov_off', [
+    ((24, 28, 32), (2.0, 2.0, 2.0), (0.0, 0.0, 0.0)),   # BASELINE configs[4] geometry (0.5 -> 1 mm)
+    ((26, 30, 40), (2.0, 1.0, 2.0), (1.0, 3.0, 2.0)),   # two decimated axes + a cropped one
+    ((20, 36, 28), (1.0, 3.0, 2.0), (2.0, 0.0, 1.0)),
+])
+def test_multi_axis_decimation_through_chained_lean_passes(cuda, dim_y, zoom, fov_off):
+    """Several decimated axes: A'A = prod_a (B_a' B_a) runs as chained single-axis lean passes
+    instead of the general path; against the oracle (dense 3-D conv / conv_transpose)."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim, struct
+    mat_y = torch.eye(4, dtype=torch.float64)
+    shift = torch.eye(4, dtype=torch.float64)
+    shift[:3, 3] = torch.tensor(fov_off, dtype=torch.float64)
+    mat_x = mat_y @ shift @ torch.diag(torch.tensor(list(zoom) + [1.0], dtype=torch.float64))
+    dim_x = tuple(int((d - 2 * o) // z) for d, z, o in zip(dim_y, zoom, fov_off))
+    po_o = P.proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0)
+    po_g = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, device=cuda)
+    obs_o = P.Observation(torch.zeros(dim_x), mat_x, tau=0.02, po=po_o)
+    obs_g = struct._input(tau=0.02, po=po_g)
+    rec_o = P.Recon(torch.zeros(dim_y), mat_y, lam=0.25)
+    rec_g = struct._output(dim=dim_y, mat=mat_y, lam=0.25)
+    g = torch.Generator().manual_seed(23)
+    v = torch.rand(dim_y, generator=g) - 0.4
+    b = torch.rand(dim_y, generator=g) * 0.1
+    x0 = torch.rand(dim_y, generator=g)
+    vx = torch.ones(3)
+    lhs_o = lambda t: P.proj('AtA', t, [obs_o], rec_o, rho=1.2, vx_y=vx)
+    op = _project.LhsOperator([obs_g], rec_g, rho=1.2, vx_y=vx)
+    ref = lhs_o(v)
+    res = {}
+    try:
+        for variant in (1, 0):
+            _reset()
+            _tune('lhs_variant', variant)
+            out = op(v.to(cuda))
+            path = _last_path()
+            sols = []
+            for stop in ('max_gain', 'residual'):
+                x = x0.clone().to(cuda)
+                optim.cg(A=op, b=b.to(cuda), x=x, max_iter=8, tolerance=1e-3, stop=stop)
+                sols.append((x, optim.cg.last.n_iter))
+            res[variant] = (out, path, sols)
+    finally:
+        _reset()
+    assert res[0][1] == 2 and res[1][1] == 0
+    assert U.rel_l2(res[1][0], ref) < 1e-5 and U.rel_l2(res[0][0], ref) < 1e-5
+    for k, stop in enumerate(('max_gain', 'residual')):
+        xo = x0.clone()
+        OO.cg(A=lhs_o, b=b, x=xo, max_iter=8, tolerance=1e-3, stop=stop)
+        assert res[0][2][k][1] == res[1][2][k][1] == OO.cg.last_n_iter
+        assert U.rel_l2(res[0][2][k][0], xo) < U.REL_TOL

@@ -19,6 +19,7 @@ int fast_depth = 1;   // prefetch depth of the ring in plane pairs (>= 1)
 int fast_q_units = 0; // units per CTA override (0 automatic)
 int fast_pfd = 0;     // planes prefetched into L2 ahead of the ring
 int fast_lock = 1;    // cut every column into the same segments (neighbours march in step)
+int fast_diag_residue = 1;  // carry the rounding residue of the stencil diagonal (debug knob)
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
@@ -93,7 +94,12 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.a_m = A.rl2 * iv_m;
   S.a_o = A.rl2 * iv_o;
   S.a_z = A.rl2 * iv_z;
-  S.d0 = A.w_ident + 2.f * ((S.a_m + S.a_o) + S.a_z);
+  // diag - sum(neighbour weights) must cancel exactly: carry the float rounding residue of the
+  // diagonal separately (6e-8 relative to d0, but coherent over the volume: it would act as a
+  // spurious identity term on the large near-constant part of an image)
+  const double d0_exact = (double)A.w_ident + 2.0 * ((double)S.a_m + (double)S.a_o + (double)S.a_z);
+  S.d0 = (float)d0_exact;
+  S.nd0l = fast_diag_residue ? (float)((double)S.d0 - d0_exact) : 0.f;
 
   int rpt = kind == FK_THICK_M ? 1 : 2;  // measured at 256^3: 8-row tiles win with a deep ring
   if (fast_rpt == 1 || fast_rpt == 2) rpt = fast_rpt;

@@ -48,7 +48,9 @@ struct FastArgs {
   int gs_m, gs_o;  // element strides of the march / row axis
   int march_y;
   float a_m, a_o, a_z;  // rho lam^2 / vx^2 per axis
-  float d0;             // w_ident + 2 (a_m + a_o + a_z)
+  float d0;             // w_ident + 2 (a_m + a_o + a_z), rounded to float ...
+  float nd0l;           // ... and minus the rounding residue: constants stay in the null space of
+                        // D'D (an uncorrected residue e acts as a spurious e * identity term)
   // observation term (lattice aligned)
   float tau;
   int off, nj;
@@ -174,9 +176,10 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   // COMBINE: both fused modes (an in-place update of the tile + halo from a second TMA ring)
   constexpr bool COMBINE = MODE == LHS_COMBINE || MODE == LHS_ECOMBINE;
   constexpr bool ECOMB = MODE == LHS_ECOMBINE;
-  static_assert(!THICK_M || KP <= 2 * R, "thick-m: two live low-res rows");
+  constexpr int NT = THICK_M ? (KP + R - 1) / R : 1;  // low-res rows alive at a plane (thick m)
+  static_assert(NT <= 5, "thick-m: at most five live low-res rows");
   static_assert(!THICK_ZG || KP - 1 <= HZ, "thick-z: windows inside the z halo");
-  static_assert(2 * R <= kTaps || !THICK_M, "kerT zero padding");
+  static_assert(!THICK_M || (R - 1) + (NT - 1) * R < kTaps, "kerT zero padding");
   static_assert(!THICK_Z || (4 % R == 0 && KP - 1 <= HZ), "thick-z: ratio divides the quad");
   constexpr int NRZ = THICK_Z ? 8 / R : 1;  // candidate low-res rows per quad (thick along z)
 
@@ -381,11 +384,13 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     int goff_c = first * a.gs_m + o_first * a.gs_o + z;    // plane being combined
     int goff_u = u_begin * a.gs_m + o_first * a.gs_o + z;  // plane being output
     float4 prev[RPT], cur[RPT];
-    float4 lrc[RPT], lro[RPT];  // THICK_M: current / previous low-res row (registers)
+    float4 lr[NT][RPT];  // THICK_M: the live low-res rows, newest first (registers)
     float4 xr[2][RPT];          // COMBINE: x quads of the next two planes to combine
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      prev[i] = cur[i] = lrc[i] = lro[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      prev[i] = cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) lr[n][i] = make_float4(0.f, 0.f, 0.f, 0.f);
       xr[0][i] = xr[1][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (x_fused) {
@@ -537,11 +542,12 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 acc.z = fmaf(a.ker[tt], q.z, acc.z);
                 acc.w = fmaf(a.ker[tt], q.w, acc.w);
               }
-              lro[i] = lrc[i];
-              lrc[i].x = acc.x * (sc * tm[i].x);
-              lrc[i].y = acc.y * (sc * tm[i].y);
-              lrc[i].z = acc.z * (sc * tm[i].z);
-              lrc[i].w = acc.w * (sc * tm[i].w);
+#pragma unroll
+              for (int n = NT - 1; n > 0; --n) lr[n][i] = lr[n - 1][i];
+              lr[0][i].x = acc.x * (sc * tm[i].x);
+              lr[0][i].y = acc.y * (sc * tm[i].y);
+              lr[0][i].z = acc.z * (sc * tm[i].z);
+              lr[0][i].w = acc.w * (sc * tm[i].w);
             }
           }
         }
@@ -554,11 +560,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
           const float4 om_edge = lds128(sa_cur + own_b - ROWB);
           const float4 op_edge = lds128(sa_cur + own_b + RPT * ROWB);
           const bool m_in = uu >= a.lo_m && uu < a.hi_m;
-          float w0 = 0.f, w1 = 0.f;
-          if (THICK_M) {
-            w0 = a.kerT[ph];
-            w1 = a.kerT[ph + R];
-          }
+          float wt[NT];  // tap of live row n at this plane: kerT[ph + n R] (zero padded)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) wt[n] = THICK_M ? a.kerT[ph + n * R] : 0.f;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const uint32_t ca = sa_cur + own_b + i * ROWB;
@@ -611,10 +615,17 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                   }
                 }
               } else if (THICK_M) {
-                dat.x = fmaf(w1, lro[i].x, w0 * lrc[i].x);
-                dat.y = fmaf(w1, lro[i].y, w0 * lrc[i].y);
-                dat.z = fmaf(w1, lro[i].z, w0 * lrc[i].z);
-                dat.w = fmaf(w1, lro[i].w, w0 * lrc[i].w);
+                dat.x = wt[0] * lr[0][i].x;
+                dat.y = wt[0] * lr[0][i].y;
+                dat.z = wt[0] * lr[0][i].z;
+                dat.w = wt[0] * lr[0][i].w;
+#pragma unroll
+                for (int n = 1; n < NT; ++n) {
+                  dat.x = fmaf(wt[n], lr[n][i].x, dat.x);
+                  dat.y = fmaf(wt[n], lr[n][i].y, dat.y);
+                  dat.z = fmaf(wt[n], lr[n][i].z, dat.z);
+                  dat.w = fmaf(wt[n], lr[n][i].w, dat.w);
+                }
               } else if (KIND == FK_POINT) {
                 if (m_in) {
                   Dk.x += tm[i].x;
@@ -633,7 +644,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               const float s_m = cmpv(prev[i], k) + cmpv(next[i], k);
               const float s_o = cmpv(om, k) + cmpv(op, k);
               const float s_z = lft + rgt;
-              const float S = fmaf(a.a_z, s_z, fmaf(a.a_o, s_o, a.a_m * s_m));
+              const float S = fmaf(a.a_z, s_z, fmaf(a.a_o, s_o, fmaf(a.a_m, s_m, a.nd0l * c)));
               val[k] = fmaf(cmpv(Dk, k), c, cmpv(dat, k)) - S;
             }
             if (ztail) {
@@ -737,8 +748,12 @@ FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
         if (kp == 7 && r == 5) return lhs_fast_kernel<MODE, FK_THICK_M, 7, 5, 0, 1>;       \
         if (kp == 7 && r == 6) return lhs_fast_kernel<MODE, FK_THICK_M, 7, 6, 0, 1>;       \
         if (kp == 9 && r == 8) return lhs_fast_kernel<MODE, FK_THICK_M, 9, 8, 0, 1>;       \
+        if (kp == 9 && r == 2) return lhs_fast_kernel<MODE, FK_THICK_M, 9, 2, 0, 1>;       \
         return nullptr;                                                                    \
       case FK_THICK_ZG:                                                                    \
+        if (kp == 9 && r == 2)                                                             \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 2, 0, 1>                       \
+                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 2, 0, 2>;                      \
         if (kp == 5 && r == 3)                                                             \
           return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 1>                       \
                     : lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 2>;                      \

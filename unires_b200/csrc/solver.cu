@@ -27,6 +27,8 @@ int scratch_reduce(GridReduce *gr);  // vecops.cu
 int lhs_stream_launch(int mode, const LhsArgs &a, int variant, cudaStream_t st);
 int lhs_fast_launch(int mode, const LhsArgs &a, bool dry_run, cudaStream_t st);  // lhs_fast.cu
 
+static int g_lhs_variant = 0;  // ur_tune("lhs_variant")
+
 __device__ __forceinline__ float eval_term(const LatticeTerm &T, const float *__restrict__ v,
                                            const int (&i)[3], size_t lin, const int (&n)[3],
                                            const size_t (&st)[3]) {
@@ -344,6 +346,8 @@ struct LhsPlan {
   int n_general;            // observations routed through the general path
   int general[UR_MAX_OBS];  // their indices
   size_t proj_ws;           // max general-path workspace
+  int n_chain;              // > 0: the (single) observation is a chain of single-axis terms
+  LatticeTerm chain[3];
   dim3 grid, block;
 };
 
@@ -389,6 +393,60 @@ static bool lattice_term(const ur_proj *po, float tau, LatticeTerm *T) {
     }
   }
   T->tau = w;
+  return true;
+}
+
+// A lattice observation decimated along SEVERAL axes (e.g. isotropic 1 mm data reconstructed
+// at 0.5 mm: ratio 2 on every axis).  The 1-D decimating correlations B_a act on different axes
+// and commute, so  A'A = prod_a (B_a' B_a)  -- a CHAIN of single-axis terms, each of which the
+// lean kernel evaluates as a "term only" pass; FOV crops on the remaining axes are projections
+// (idempotent, commuting) and ride along in every pass.  chain[0] carries tau.
+static bool lattice_chain(const ur_proj *po, float tau, LatticeTerm chain[3], int *n_chain) {
+  *n_chain = 0;
+  if (!ur_proj_is_lattice(po) || po->method != UR_SUPERRES) return false;
+  if (po->scl != 0.f) return false;  // even/odd scaling with several decimated axes: general path
+  int lo[3], hi[3];
+  bool conv[3];
+  float w = tau;
+  for (int a = 0; a < 3; ++a) {
+    const int shift = (int)lrintf(po->mat[4 * a + 3]);
+    conv[a] = po->ksize[a] > 1 || po->ratio[a] > 1;
+    if (conv[a]) {
+      lo[a] = 0;
+      hi[a] = po->dim_y[a];
+    } else {
+      const float k = po->ker[a][0];
+      w *= k * k;
+      lo[a] = shift > 0 ? shift : 0;
+      const int h = shift + po->dim_x[a];
+      hi[a] = h < po->dim_y[a] ? h : po->dim_y[a];
+    }
+  }
+  int n = 0;
+  for (int a = 0; a < 3; ++a) {
+    if (!conv[a]) continue;
+    LatticeTerm &T = chain[n];
+    memset(&T, 0, sizeof(T));
+    T.axis = a;
+    T.scl_axis = -1;
+    T.s_even = T.s_odd = 1.f;
+    int k0 = 0, k1 = po->ksize[a];
+    while (k1 - k0 > 1 && po->ker[a][k0] == 0.f) ++k0;
+    while (k1 - k0 > 1 && po->ker[a][k1 - 1] == 0.f) --k1;
+    T.K = k1 - k0;
+    for (int t = 0; t < T.K; ++t) T.ker[t] = po->ker[a][k0 + t];
+    T.off = (int)lrintf(po->mat[4 * a + 3]) + k0;
+    T.r = po->ratio[a];
+    T.nj = po->dim_x[a];
+    for (int b = 0; b < 3; ++b) {
+      T.lo[b] = lo[b];
+      T.hi[b] = hi[b];
+    }
+    T.tau = n == 0 ? w : 1.f;
+    ++n;
+  }
+  if (n < 2) return false;  // a single decimated axis is an ordinary lattice term
+  *n_chain = n;
   return true;
 }
 
@@ -499,6 +557,12 @@ static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
       UR_REQUIRE(po->dim_y[a] == lhs->dim_y[a], "ur_lhs: observation %d dim_y mismatch", n);
     if (A.nterm < kMaxFused && lattice_term(po, lhs->tau[n], &A.term[A.nterm])) {
       ++A.nterm;
+    } else if (lhs->n_obs == 1 && g_lhs_variant == 0 &&
+               lattice_chain(po, lhs->tau[n], P->chain, &P->n_chain)) {
+      // evaluated by chained lean passes in launch_lhs (checked there; general path otherwise)
+      P->general[P->n_general++] = n;
+      const size_t w = proj_workspace_bytes(po);
+      if (w > P->proj_ws) P->proj_ws = w;
     } else {
       P->general[P->n_general++] = n;
       const size_t w = proj_workspace_bytes(po);
@@ -537,6 +601,7 @@ static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
   size_t s = 256 + lhs_partials_bytes(P);
   // accumulator volume: general-path observations and / or all but one lattice term
   if (P.n_general || P.args.nterm > 1) s += vol_bytes(lhs) + align_up(P.proj_ws);
+  if (P.n_chain) s += vol_bytes(lhs);  // second buffer of the chained passes
   return s;
 }
 
@@ -544,6 +609,7 @@ struct LhsWs {
   unsigned *counter;
   double *partials;
   float *acc;
+  float *acc2;
   void *proj;
   size_t proj_bytes;
 };
@@ -563,7 +629,10 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
     c += vol_bytes(lhs);
     w.proj = c;
     w.proj_bytes = align_up(P.proj_ws);
+    c += w.proj_bytes;
   }
+  w.acc2 = nullptr;
+  if (P.n_chain) w.acc2 = (float *)c;
   return w;
 }
 
@@ -574,8 +643,7 @@ extern int stream_mc_override;  // lhs_stream.cu
 extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
 extern int jtv_block_rows;  // admm.cu
-extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock;  // lhs_fast.cu
-static int g_lhs_variant = 0;
+extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock, fast_diag_residue;  // lhs_fast.cu
 static int g_cg_fuse = 1;
 static int g_r_reverse = 0;   // residual update sweeps the volume end -> start
 static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
@@ -629,7 +697,48 @@ static bool lean_supports(int mode, const LhsArgs &A, cudaStream_t st) {
 // Launch one lhs evaluation.  `A` carries the mode-specific pointers.
 static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs &w, LhsArgs A,
                       int variant, cudaStream_t st) {
-  if (P.n_general) {
+  bool chained = false;
+  if (P.n_chain > 0 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc && w.acc2 &&
+      mode != LHS_COMBINE && mode != LHS_ECOMBINE) {
+    // several decimated axes: A'A v = prod_a (B_a' B_a) v as chained term-only lean passes
+    // (ping-pong between two scratch volumes), then D'D v + the chain result + the epilogue
+    bool ok = true;
+    for (int k = 0; k < P.n_chain && ok; ++k) {
+      LhsArgs T = A;
+      T.nterm = 1;
+      T.term[0] = P.chain[k];
+      T.rl2 = T.w_ident = 0.f;
+      T.out = w.acc;
+      ok = lhs_fast_launch(LHS_PLAIN, T, true, st) == UR_OK;
+    }
+    if (ok) {
+      LhsArgs F = A;
+      F.nterm = 0;
+      F.acc = w.acc;
+      ok = lhs_fast_launch(mode, F, true, st) == UR_OK;
+    }
+    if (ok) {
+      float *bufs[2] = {w.acc, w.acc2};
+      const float *src = A.v;
+      for (int k = 0; k < P.n_chain; ++k) {
+        LhsArgs T = A;
+        T.nterm = 1;
+        T.term[0] = P.chain[k];
+        T.rl2 = T.w_ident = 0.f;
+        T.v = src;
+        T.out = bufs[k & 1];
+        T.acc = nullptr;
+        T.gr = GridReduce{w.partials, w.counter};
+        T.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, nullptr};
+        int rc = lhs_fast_launch(LHS_PLAIN, T, false, st);
+        if (rc) return rc;
+        src = bufs[k & 1];
+      }
+      A.acc = src;
+      chained = true;
+    }
+  }
+  if (P.n_general && !chained) {
     // NOTE: the general path cannot early-out on the device-side `done` flag
     // for its memset; its kernels are cheap relative to a full iteration.
     UR_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, vol_bytes(lhs), st));
@@ -780,6 +889,8 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_pfd = value < 0 ? 0 : value;
   } else if (!strcmp(name, "fast_lock")) {
     fast_lock = value != 0;
+  } else if (!strcmp(name, "fast_diag_residue")) {  // debug: 0 drops the diagonal's residue term
+    fast_diag_residue = value != 0;
   } else if (!strcmp(name, "fast_q")) {
     fast_q_units = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {
