@@ -72,7 +72,8 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
       e = ((T.off % r) + r) % r;
       if (T.axis == 2) {
         // register scheme when the ratio divides the quad, per-lane windows otherwise
-        kind = ((kp == 5 && r == 4) || (kp == 3 && r == 2)) ? FK_THICK_Z : FK_THICK_ZG;
+        kind = ((kp == 5 && r == 4) || (kp == 3 && r == 2) || (kp == 9 && r == 2)) ? FK_THICK_Z
+                                                                                    : FK_THICK_ZG;
         S.lo_z = 0;
         S.hi_z = A.nz;
       } else {

@@ -33,8 +33,8 @@ namespace ur {
 namespace fast {
 
 constexpr int TZ = 128;          // z extent of a tile (32 lanes x float4)
-// z halo of a tile row: one quad each side; two for the generic thick-z kind with > 5 taps
-constexpr int fast_hz(int kind, int kp) { return (kind == 4 && kp - 1 > 4) ? 8 : 4; }
+// z halo of a tile row: one quad each side; two for the thick-z kinds with > 5 taps
+constexpr int fast_hz(int kind, int kp) { return ((kind == 3 || kind == 4) && kp - 1 > 4) ? 8 : 4; }
 constexpr int NTHR = 256;
 constexpr int NWARP = NTHR / 32;
 constexpr int kMaxSlots = 32;
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   static_assert(!THICK_ZG || KP - 1 <= HZ, "thick-z: windows inside the z halo");
   static_assert(!THICK_M || (R - 1) + (NT - 1) * R < kTaps, "kerT zero padding");
   static_assert(!THICK_Z || (4 % R == 0 && KP - 1 <= HZ), "thick-z: ratio divides the quad");
-  constexpr int NRZ = THICK_Z ? 8 / R : 1;  // candidate low-res rows per quad (thick along z)
+  constexpr int NQ = HZ / 4;  // halo quads each side of the own quad
+  // THICK_Z: candidate low-res rows per quad = windows starting in [z - 4 NQ, z + 3]
+  constexpr int NRZ = THICK_Z ? 4 * (NQ + 1) / R : 1;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kMaxWarps];
@@ -329,8 +331,8 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       for (int n = 0; n < NRZ; ++n) {
         czr[i][n] = 0.f;
         if (THICK_Z) {
-          // window n starts at z - 4 + E + n R  ( = R j + off )
-          const int s = z - 4 + E + n * R - a.off;
+          // window n starts at z - 4 NQ + E + n R  ( = R j + off )
+          const int s = z - 4 * NQ + E + n * R - a.off;
           const int j = s / R;  // exact when s >= 0
           if (o_in && s >= 0 && j < a.nj)
             czr[i][n] = a.scl_conv ? ((j & 1) ? a.s_odd : a.s_even) : 1.f;
@@ -577,20 +579,32 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               zl = ql.w;
               zr = qr.x;
               if (m_in) {
-                const float V[12] = {ql.x,     ql.y,     ql.z,     ql.w,     cur[i].x, cur[i].y,
-                                     cur[i].z, cur[i].w, qr.x,     qr.y,     qr.z,     qr.w};
+                // the 2 NQ + 1 quads around the own one, in registers
+                float V[4 * (2 * NQ + 1)];
+                if constexpr (NQ == 2) {
+                  const float4 ql2 = lds128(ca - 32u);
+                  const float4 qr2 = lds128(ca + 32u);
+                  V[0] = ql2.x, V[1] = ql2.y, V[2] = ql2.z, V[3] = ql2.w;
+                  V[16] = qr2.x, V[17] = qr2.y, V[18] = qr2.z, V[19] = qr2.w;
+                }
+                constexpr int VB = 4 * (NQ - 1);
+                V[VB + 0] = ql.x, V[VB + 1] = ql.y, V[VB + 2] = ql.z, V[VB + 3] = ql.w;
+                V[VB + 4] = cur[i].x, V[VB + 5] = cur[i].y, V[VB + 6] = cur[i].z;
+                V[VB + 7] = cur[i].w;
+                V[VB + 8] = qr.x, V[VB + 9] = qr.y, V[VB + 10] = qr.z, V[VB + 11] = qr.w;
 #pragma unroll
                 for (int n = 0; n < NRZ; ++n) {
-                  const int s0 = E + n * R;  // window start relative to z - 4
-                  if (s0 + KP - 1 < 4 || s0 > 7) continue;  // cannot touch the own quad
+                  const int s0 = E + n * R;  // window start relative to z - 4 NQ
+                  // cannot touch the own quad
+                  if (s0 + KP - 1 < 4 * NQ || s0 > 4 * NQ + 3) continue;
                   float lr = 0.f;
 #pragma unroll
                   for (int tt = 0; tt < KP; ++tt)
-                    if (s0 + tt < 12) lr = fmaf(a.ker[tt], V[s0 + tt], lr);
+                    if (s0 + tt < 4 * (2 * NQ + 1)) lr = fmaf(a.ker[tt], V[s0 + tt], lr);
                   lr *= czr[i][n];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const int tap = k + 4 - s0;
+                    const int tap = k + 4 * NQ - s0;
                     if (tap >= 0 && tap < KP) cmp(dat, k) = fmaf(a.kerT[tap], lr, cmpv(dat, k));
                   }
                 }
@@ -751,9 +765,6 @@ FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
         if (kp == 9 && r == 2) return lhs_fast_kernel<MODE, FK_THICK_M, 9, 2, 0, 1>;       \
         return nullptr;                                                                    \
       case FK_THICK_ZG:                                                                    \
-        if (kp == 9 && r == 2)                                                             \
-          return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 2, 0, 1>                       \
-                    : lhs_fast_kernel<MODE, FK_THICK_ZG, 9, 2, 0, 2>;                      \
         if (kp == 5 && r == 3)                                                             \
           return R1 ? lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 1>                       \
                     : lhs_fast_kernel<MODE, FK_THICK_ZG, 5, 3, 0, 2>;                      \
@@ -790,6 +801,13 @@ FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
                       : lhs_fast_kernel<MODE, FK_THICK_Z, 3, 2, 0, 2>;                     \
           return R1 ? lhs_fast_kernel<MODE, FK_THICK_Z, 3, 2, 1, 1>                        \
                     : lhs_fast_kernel<MODE, FK_THICK_Z, 3, 2, 1, 2>;                       \
+        }                                                                                  \
+        if (kp == 9 && r == 2) { /* two-quad halo, 5 quads in registers */                 \
+          if (e == 0)                                                                      \
+            return R1 ? lhs_fast_kernel<MODE, FK_THICK_Z, 9, 2, 0, 1>                      \
+                      : lhs_fast_kernel<MODE, FK_THICK_Z, 9, 2, 0, 2>;                     \
+          return R1 ? lhs_fast_kernel<MODE, FK_THICK_Z, 9, 2, 1, 1>                        \
+                    : lhs_fast_kernel<MODE, FK_THICK_Z, 9, 2, 1, 2>;                       \
         }                                                                                  \
         return nullptr;                                                                    \
     }                                                                                      \
