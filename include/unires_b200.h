@@ -291,6 +291,26 @@ int ur_rigid_sums(const float *d_grad, const float *d_res, const float *d_ctc,
                   const int32_t dim[3], const float dm[72], double *d_out,
                   ur_stream stream);
 
+/* ---------------------------------------------------------------- intensity
+ * statistics for the hyper-parameter estimate, _estimate_hyperpar
+ * (unires/_core.py:96-142).  The reference compacts the volume by
+ * boolean masks (dat[dat >= 0] at _core.py:118, then nitorch's estimate_noise
+ * drops zeros and the maximum) and bins it with torch.histc; here the
+ * selections are folded into two streaming passes.  Selection of a voxel v:
+ * non-finite -> 0; drop_negative: only v >= 0; mask: v != 0 and v != mask_value.
+ * ur_intensity_range: h_out[0] = min, h_out[1] = max of the selected voxels
+ * (HOST floats; synchronises the stream), *h_any = 0 if nothing was selected.
+ * ur_histc: d_counts[b] (device, `bins` uint64, zeroed here) = number of
+ * selected voxels with mn <= v <= mx in bin (int)((v - mn) * bins / (mx - mn))
+ * (v == mx in the last bin), computed in float64 like torch.histc on the
+ * reference's float64 copy.                                                   */
+int ur_intensity_range(const float *d_dat, size_t n, int drop_negative, int mask,
+                       float mask_value, float h_out[2], int32_t *h_any,
+                       ur_stream stream);
+int ur_histc(const float *d_dat, size_t n, int drop_negative, int mask,
+             float mask_value, double mn, double mx, int bins,
+             unsigned long long *d_counts, ur_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,10 @@ _SIGNATURES = {
     'ur_nll_data': (C.c_int, [_p, _p, _sz, C.c_float, _p, C.c_int, _p]),
     'ur_nll_prior_energy': (C.c_int, [C.POINTER(_p), _p, C.c_int, _f3, _i3, _f3, C.c_int, _p]),
     'ur_sqrt_sum': (C.c_int, [_p, _sz, _p, _p]),
+    'ur_intensity_range': (C.c_int, [_p, _sz, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_int32), _p]),
+    'ur_histc': (C.c_int, [_p, _sz, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_int,
+                           _p, _p]),
 }
 
 for _name, (_res, _args) in _SIGNATURES.items():

@@ -6,11 +6,12 @@ resolve to the sm_100a kernels:
     nc.install()          # registers nitorch, nitorch.spatial, nitorch.core.*
     import unires         # now runs on unires_b200
 
-Only the functions on the ADMM/CG path exist.
+Only the functions on the ADMM/CG path exist, plus
+nitorch.tools.img_statistics.estimate_noise (hyper-parameter estimate).
 """
 import sys
 
-from . import spatial, core  # noqa: F401
+from . import spatial, core, tools  # noqa: F401
 
 
 def install(force=False):
@@ -24,4 +25,6 @@ def install(force=False):
     sys.modules['nitorch.core'] = core
     sys.modules['nitorch.core.kernels'] = core.kernels
     sys.modules['nitorch.core.optim'] = core.optim
+    sys.modules['nitorch.tools'] = tools
+    sys.modules['nitorch.tools.img_statistics'] = tools.img_statistics
     return True
