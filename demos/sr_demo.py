@@ -8,11 +8,13 @@ reference's demos/demo_single_channel.ipynb / demo_multi_channel.ipynb (cell 4):
 
     python demos/sr_demo.py                                   # synthetic 3-channel 128^3 phantom
     python demos/sr_demo.py t1.nii.gz t2.nii.gz pd.nii.gz     # e.g. the BrainWeb volumes in data/
-    options: --thick 4 --sd 25 --max-iter 60 --scaling --out out_dir
+    options: --thick 4 --sd 25 --max-iter 60 --scaling --estimate --out out_dir
 
-Hyper-parameters follow the reference: tau = 1/sd^2, lam0 = sqrt(1/C) / mean foreground
-(unires/_core.py:134-136, 279); what is NOT reproduced is the noise estimation and
-co-registration of unires/_core.py (they need nitorch.tools) -- sd is known here.
+Hyper-parameters follow the reference: tau = 1/sd^2, lam0 = sqrt(1/C) / mu (unires/_core.py:
+134-136, 279).  By default sd is the known simulation value and mu the mean foreground; with
+--estimate the noise is added everywhere (like the notebooks) and tau, mu come from
+`_core._estimate_hyperpar` (mixture fit to the intensity histogram, unires/_core.py:96-142).
+What is NOT reproduced is the co-registration of unires/_core.py (needs nitorch.tools).
 """
 import argparse
 import math
@@ -25,7 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from unires_b200 import _project, io, run, struct, synth  # noqa: E402
+from unires_b200 import _core, _project, io, run, struct, synth  # noqa: E402
 
 
 def main():
@@ -36,6 +38,7 @@ def main():
     ap.add_argument('--max-iter', type=int, default=60)
     ap.add_argument('--dim', type=int, default=128)
     ap.add_argument('--scaling', action='store_true')
+    ap.add_argument('--estimate', action='store_true')
     ap.add_argument('--out', default=None)
     a = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -66,11 +69,18 @@ def main():
                                  scl=0.1 if a.scaling else 0.0)
         clean = _project._proj_apply('A', truth[c][None, None], po, method=sett.method)[0, 0]
         noise = (a.sd * torch.randn(tuple(clean.shape), generator=g)).to(dev)
-        obs = struct._input(dat=torch.where(clean != 0, clean + noise, torch.zeros((), device=dev))
-                            .float().contiguous(), dim=dim_x, mat=mat_x.to(dev),
+        noisy = clean + noise if a.estimate else \
+            torch.where(clean != 0, clean + noise, torch.zeros((), device=dev))
+        obs = struct._input(dat=noisy.float().contiguous(), dim=dim_x, mat=mat_x.to(dev),
                             tau=torch.tensor(1.0 / a.sd ** 2, device=dev), sd=a.sd, ct=False)
         fg = obs.dat[obs.dat > 0]
         obs.mu = float(fg.mean())
+        if a.estimate:
+            _core._estimate_hyperpar([[obs]], sett)
+            print('  channel %d: estimated sd %.2f (simulated %g; a Rician fit of Gaussian noise '
+                  'with the negatives dropped reads sd / sqrt(2) at zero signal), mu %.1f'
+                  % (c, float(obs.sd), a.sd, float(obs.mu)))
+            obs.mu = float(obs.mu)
         if a.scaling:  # the fit starts from scl = 0 and has to find exp(+-0.1)
             po = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=sett.profile_ip,
                                      prof_tp=sett.profile_tp, gap=sett.gap, device=dev, scl=0.0)

@@ -18,8 +18,9 @@ def _estimate_hyperpar(x, sett=None):
         for obs in xc:
             prm_noise, prm_not_noise = estimate_noise(obs.dat, num_class=2,
                                                       drop_negative=not getattr(obs, 'ct', False))
-            sd_bg = prm_noise['sd'].float()
+            dev = obs.dat.device  # the reference's estimates live on the data's device
+            sd_bg = prm_noise['sd'].float().to(dev)
             obs.sd = sd_bg
             obs.tau = 1 / sd_bg ** 2
-            obs.mu = torch.abs(prm_not_noise['mean'].float() - prm_noise['mean'].float())
+            obs.mu = torch.abs(prm_not_noise['mean'].float() - prm_noise['mean'].float()).to(dev)
     return x
