@@ -121,6 +121,9 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
     case LHS_ECOMBINE:
       kernel = fast_lookup_ecombine(kind, kp, r, ez, rpt);
       break;
+    case LHS_TERM:
+      kernel = fast_lookup_term(kind, kp, r, ez, rpt);
+      break;
     default:
       kernel = fast_lookup_combine(kind, kp, r, ez, rpt);
       break;
@@ -132,6 +135,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
       case LHS_RESID: kernel = fast_lookup_resid(kind, kp, r, ez, rpt); break;
       case LHS_ENERGY: kernel = fast_lookup_energy(kind, kp, r, ez, rpt); break;
       case LHS_ECOMBINE: kernel = fast_lookup_ecombine(kind, kp, r, ez, rpt); break;
+      case LHS_TERM: kernel = fast_lookup_term(kind, kp, r, ez, rpt); break;
       default: kernel = fast_lookup_combine(kind, kp, r, ez, rpt); break;
     }
   }

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   // COMBINE: both fused modes (an in-place update of the tile + halo from a second TMA ring)
   constexpr bool COMBINE = MODE == LHS_COMBINE || MODE == LHS_ECOMBINE;
   constexpr bool ECOMB = MODE == LHS_ECOMBINE;
+  constexpr bool TERM = MODE == LHS_TERM;  // term only: no stencil, no dot product
   constexpr int NT = THICK_M ? (KP + R - 1) / R : 1;  // low-res rows alive at a plane (thick m)
   static_assert(NT <= 5, "thick-m: at most five live low-res rows");
   static_assert(!THICK_ZG || KP - 1 <= HZ, "thick-z: windows inside the z halo");
@@ -555,12 +556,15 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
         }
 
         if (uu >= m0) {
-          if (uu == 0) {  // low edge of the march axis: (c - hi), i.e. lo := c
+          if (!TERM && uu == 0) {  // low edge of the march axis: (c - hi), i.e. lo := c
 #pragma unroll
             for (int i = 0; i < RPT; ++i) prev[i] = cur[i];
           }
-          const float4 om_edge = lds128(sa_cur + own_b - ROWB);
-          const float4 op_edge = lds128(sa_cur + own_b + RPT * ROWB);
+          float4 om_edge = make_float4(0.f, 0.f, 0.f, 0.f), op_edge = om_edge;
+          if (!TERM) {
+            om_edge = lds128(sa_cur + own_b - ROWB);
+            op_edge = lds128(sa_cur + own_b + RPT * ROWB);
+          }
           const bool m_in = uu >= a.lo_m && uu < a.hi_m;
           float wt[NT];  // tap of live row n at this plane: kerT[ph + n R] (zero padded)
 #pragma unroll
@@ -610,8 +614,11 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 }
               }
             } else {
-              zl = lds32(ca - 4u);
-              zr = lds32(ca + 16u);
+              zl = zr = 0.f;
+              if (!TERM) {
+                zl = lds32(ca - 4u);
+                zr = lds32(ca + 16u);
+              }
               if (THICK_ZG) {
                 if (m_in) {
 #pragma unroll
@@ -652,6 +659,10 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             float val[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (TERM) {
+                val[k] = cmpv(dat, k);
+                continue;
+              }
               const float c = cmpv(cur[i], k);
               const float lft = k == 0 ? zl : cmpv(cur[i], k - 1);
               const float rgt = k == 3 ? zr : cmpv(cur[i], k + 1);
@@ -675,7 +686,10 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 val[2] += aq.z;
                 val[3] += aq.w;
               }
-              if (MODE == LHS_PLAIN || MODE == LHS_COMBINE) {
+              if (TERM) {
+                *reinterpret_cast<float4 *>(a.out + gi) =
+                    make_float4(val[0], val[1], val[2], val[3]);
+              } else if (MODE == LHS_PLAIN || MODE == LHS_COMBINE) {
                 *reinterpret_cast<float4 *>(a.out + gi) =
                     make_float4(val[0], val[1], val[2], val[3]);
 #pragma unroll
@@ -729,6 +743,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
       }
     }
   }
+  if (TERM) return;
   double total_sum;
   if (grid_sum(part, a.gr, s_red, &total_sum) && tid == 0) finalize(a.fin, total_sum);
 }
@@ -739,6 +754,7 @@ FastKernel fast_lookup_resid(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_energy(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_combine(int kind, int kp, int r, int e, int rpt);
 FastKernel fast_lookup_ecombine(int kind, int kp, int r, int e, int rpt);
+FastKernel fast_lookup_term(int kind, int kp, int r, int e, int rpt);
 
 #define UR_FAST_LOOKUP_BODY(MODE)                                                          \
   {                                                                                        \

@@ -689,7 +689,7 @@ static bool lean_supports(int mode, const LhsArgs &A, cudaStream_t st) {
   for (int t = 0; t + 1 < A.nterm; ++t) {
     LhsArgs T = single_term(A, t, false);
     T.out = const_cast<float *>(A.v);  // any aligned pointer: eligibility only
-    if (lhs_fast_launch(LHS_PLAIN, T, true, st) != UR_OK) return false;
+    if (lhs_fast_launch(LHS_TERM, T, true, st) != UR_OK) return false;
   }
   return lhs_fast_launch(mode, single_term(A, A.nterm - 1, true), true, st) == UR_OK;
 }
@@ -709,7 +709,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
       T.term[0] = P.chain[k];
       T.rl2 = T.w_ident = 0.f;
       T.out = w.acc;
-      ok = lhs_fast_launch(LHS_PLAIN, T, true, st) == UR_OK;
+      ok = lhs_fast_launch(LHS_TERM, T, true, st) == UR_OK;
     }
     if (ok) {
       LhsArgs F = A;
@@ -730,7 +730,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
         T.acc = nullptr;
         T.gr = GridReduce{w.partials, w.counter};
         T.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, nullptr};
-        int rc = lhs_fast_launch(LHS_PLAIN, T, false, st);
+        int rc = lhs_fast_launch(LHS_TERM, T, false, st);
         if (rc) return rc;
         src = bufs[k & 1];
       }
@@ -760,7 +760,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
       T.out = w.acc;
       T.acc = (t > 0 || P.n_general) ? w.acc : nullptr;
       T.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, nullptr};
-      int rc = lhs_fast_launch(LHS_PLAIN, T, false, st);
+      int rc = lhs_fast_launch(LHS_TERM, T, false, st);
       if (rc) return rc;
     }
     A = single_term(A, A.nterm - 1, true);

@@ -81,7 +81,16 @@ struct LatticeTerm {
 //   x_new = x_old + alpha p (tile + halo, on-chip; written to a second buffer),
 //   0.5 (A x_new - 2 b).x_new  -- with LHS_COMBINE (without its x update) and the residual
 // update this is the energy-rule iteration in 44 instead of 52 bytes per voxel.
-enum LhsMode { LHS_PLAIN = 0, LHS_RESID = 1, LHS_ENERGY = 2, LHS_COMBINE = 3, LHS_ECOMBINE = 4 };
+// LHS_TERM (lean kernel only): out = (acc +) tau A'S^2A v of ONE lattice term -- no D'D, no
+// identity term, no dot product: the passes of a multi-view / multi-axis evaluation.
+enum LhsMode {
+  LHS_PLAIN = 0,
+  LHS_RESID = 1,
+  LHS_ENERGY = 2,
+  LHS_COMBINE = 3,
+  LHS_ECOMBINE = 4,
+  LHS_TERM = 5
+};
 
 struct LhsArgs {
   int nx, ny, nz;
