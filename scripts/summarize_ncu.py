@@ -80,13 +80,16 @@ def full(rep, dst):
         if len(src) > 2:
             h = src[1]
             ix = {c: i for i, c in enumerate(h)}
-            data = src[2:]
-            tot = sum(int(r[ix['Instructions Executed']] or 0) for r in data)
+            need = max(ix['Instructions Executed'], ix['Source'])
+            # several kernels in one report: section / repeated header rows are skipped
+            data = [r for r in src[2:] if len(r) > need and
+                    (r[ix['Instructions Executed']] or '0').replace(',', '').isdigit()]
+            tot = sum(int((r[ix['Instructions Executed']] or '0').replace(',', '')) for r in data)
             ops = collections.Counter()
             for r in data:
                 m = re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ix['Source']].strip())
-                ops[m.group(2).split('.')[0] if m else '?'] += int(r[ix['Instructions Executed']] or 0)
-            f.write('\n-- executed warp instructions by opcode (first kernel): total %d\n' % tot)
+                ops[m.group(2).split('.')[0] if m else '?'] += int((r[ix['Instructions Executed']] or '0').replace(',', ''))
+            f.write('\n-- executed warp instructions by opcode (all captured kernels): total %d\n' % tot)
             for op, c in ops.most_common(24):
                 f.write('%-10s %12d %5.1f%%\n' % (op, c, 100.0 * c / max(tot, 1)))
 
