@@ -426,3 +426,53 @@ def test_multi_axis_decimation_through_chained_lean_passes(cuda, dim_y, zoom, fo
         OO.cg(A=lhs_o, b=b, x=xo, max_iter=8, tolerance=1e-3, stop=stop)
         assert res[0][2][k][1] == res[1][2][k][1] == OO.cg.last_n_iter
         assert U.rel_l2(res[0][2][k][0], xo) < U.REL_TOL
+
+
+@pytest.mark.parametrize('method', ['denoising', 'super-resolution'])
+@pytest.mark.parametrize('dim_y,fov', [((24, 28, 32), (17, 21, 23)), ((21, 26, 36), (21, 19, 36))])
+def test_fov_crop_only_observation(cuda, method, dim_y, fov):
+    """The literal reading of BASELINE configs[1]: 1 mm observations on a larger 1 mm recon grid.
+    A = integer-shift crop, A' = zero-pad embed (unires/_project.py:148-150,180-188 for the
+    denoising method, identity slice profile for super-resolution): A'A is a per-voxel FOV mask
+    folded into the lean kernel's diagonal.  Lean vs direct kernel vs oracle."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim, struct, synth
+    cfg = dict(dim_y=dim_y, fov=fov, vx_y=1.0, thick=[None])
+    dim_x, mat_x, _, mat_y = synth.geometry(cfg, 0)
+    assert dim_x == tuple(fov)
+    po_o = P.proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=0, prof_tp=0)
+    po_g = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=0, prof_tp=0, device=cuda)
+    obs_o = P.Observation(torch.zeros(dim_x), mat_x, tau=0.017, po=po_o)
+    rec_o = P.Recon(torch.zeros(dim_y), mat_y, lam=0.23)
+    obs_g, rec_g = struct._input(tau=0.017, po=po_g), struct._output(dim=dim_y, mat=mat_y, lam=0.23)
+    vx = torch.ones(3)
+    g = torch.Generator().manual_seed(5)
+    v = torch.rand(dim_y, generator=g) - 0.4
+    b = torch.rand(dim_y, generator=g) * 0.1
+    x0 = torch.rand(dim_y, generator=g)
+    lhs_o = lambda t: P.proj('AtA', t, [obs_o], rec_o, method=method, rho=1.1, vx_y=vx)
+    op = _project.LhsOperator([obs_g], rec_g, method=method, rho=1.1, vx_y=vx)
+    ref = lhs_o(v)
+    # A'A of a crop is the indicator of the field of view
+    mask = P.proj('AtA', torch.ones(dim_y), [obs_o], rec_o, method=method, rho=0.0, vx_y=vx) / 0.017
+    assert float((mask - mask.round()).abs().max()) < 1e-5
+    assert int(mask.round().sum()) == fov[0] * fov[1] * fov[2] and float(mask.max()) < 1.5
+    xo = x0.clone()
+    OO.cg(A=lhs_o, b=b, x=xo, max_iter=10, tolerance=1e-3, stop='max_gain')
+    res = {}
+    try:
+        for variant in (1, 0):
+            _reset()
+            _tune('lhs_variant', variant)
+            out = op(v.to(cuda))
+            path = _last_path()
+            x = x0.clone().to(cuda)
+            optim.cg(A=op, b=b.to(cuda), x=x, max_iter=10, tolerance=1e-3, stop='max_gain')
+            res[variant] = (out, path, x, optim.cg.last.n_iter)
+    finally:
+        _reset()
+    assert res[0][1] == 2 and res[1][1] == 0
+    for variant in (0, 1):
+        assert U.rel_l2(res[variant][0], ref) < 1e-6
+        assert res[variant][3] == OO.cg.last_n_iter
+        assert U.rel_l2(res[variant][2], xo) < U.REL_TOL

@@ -22,6 +22,9 @@ CONFIGS = {
     # each channel thick-sliced x4 along a different axis (notebook recipe)
     'sr3_256': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0,
                     thick=[(0, 4), (1, 4), (2, 4)]),
+    # configs[1], literal reading: 1 mm observations (181x217x181) on the 256^3 grid -- the
+    # operator is an integer-shift crop / zero-pad embed, A'A a field-of-view mask
+    'crop3_256': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0, thick=[None] * 3),
     # configs[2]: 3-channel 2 mm -> 1 mm thick-slice (z x2), 256^3
     'thickz2_256': dict(dim_y=(256, 256, 256), fov=None, vx_y=1.0,
                         thick=[(2, 2), (2, 2), (2, 2)]),
