@@ -55,6 +55,22 @@ def peaks():
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+WORKLOADS = {
+    'sr3_256': 'thick-slice super-resolution',
+    'sr3_48': 'thick-slice super-resolution',
+    'crop3_256': '1 mm observations on a larger 1 mm grid (crop / embed operator)',
+    'thickz2_256': 'thick-slice super-resolution (z x2)',
+    'thickz2_384': 'thick-slice super-resolution (z x2)',
+    'thickz2_384x8': 'thick-slice super-resolution (z x2)',
+    'iso2_512': '0.5 mm reconstruction of 1 mm isotropic data (ratio 2 on every axis)',
+    'denoise_181': 'denoising (identity operator)',
+}
+
+
+def describe(workload):
+    return WORKLOADS.get(workload, 'thick-slice super-resolution')
+
+
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
     committed `ncu --set full` capture of this workload (profiles/traffic.json), else None."""
@@ -260,10 +276,10 @@ def run_ours(args):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': '%s: %d-channel thick-slice super-resolution, recon grid %s, '
+        'config': {'workload': '%s: %d-channel %s, recon grid %s, '
                                'CG y-update with %d fixed iterations per channel (tolerance 0); '
-                               'one subject per GPU' % (args.workload, C, 'x'.join(map(str, dim)),
-                                                        args.cg_iters),
+                               'one subject per GPU' % (args.workload, C, describe(args.workload),
+                                                        'x'.join(map(str, dim)), args.cg_iters),
                    'channels': C, 'recon_grid': list(dim), 'cg_iters_per_channel': args.cg_iters,
                    'channel_streams': int(getattr(sett, 'channel_streams', 1)),
                    'l2': 'inputs larger than L2: CG working set per channel 5 volumes = %.0f MB '
@@ -354,10 +370,11 @@ def run_reference(args):
             'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': n, 'warmup': 1,
             'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s: 3-channel thick-slice super-resolution, recon grid %s, CG '
+            'config': {'workload': '%s: %s, recon grid %s, CG '
                                    'y-update (tolerance 0); bounded sample: each step is ONE full-size '
                                    'CG iteration of channel 0 on the host cores'
-                                   % (args.workload, 'x'.join(map(str, dim))),
+                                   % (args.workload, describe(args.workload),
+                                      'x'.join(map(str, dim))),
                        'channels': 1, 'recon_grid': list(dim), 'cg_iters_per_channel': 1},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(),
                              'kind': 'port',

@@ -697,6 +697,12 @@ static bool lean_supports(int mode, const LhsArgs &A, cudaStream_t st) {
 // Launch one lhs evaluation.  `A` carries the mode-specific pointers.
 static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs &w, LhsArgs A,
                       int variant, cudaStream_t st) {
+  // profiling (ur_profile_matvec): a matvec is timed with every pass it needs (chained /
+  // per-term lean passes, general-path accumulation), not only its last launch
+  const bool is_matvec = mode == LHS_PLAIN || mode == LHS_COMBINE;
+  cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
+  cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
+  if (e0) cudaEventRecord(e0, st);
   bool chained = false;
   if (P.n_chain > 0 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc && w.acc2 &&
       mode != LHS_COMBINE && mode != LHS_ECOMBINE) {
@@ -766,11 +772,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A = single_term(A, A.nterm - 1, true);
     A.acc = w.acc;
   }
-  const bool is_matvec = mode == LHS_PLAIN || mode == LHS_COMBINE;
   const bool lean_only = mode == LHS_ECOMBINE || (mode == LHS_COMBINE && A.xup == nullptr);
-  cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
-  cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
-  if (e0) cudaEventRecord(e0, st);
   // variant 0 = automatic (lean TMA kernel, then the generic TMA streaming kernel, then the
   // direct kernel), 1 = force the direct kernel, 2 = skip the lean kernel
   if (variant == 0) variant = g_lhs_variant;
