@@ -560,3 +560,20 @@ def init_y_dat(x, y, sett):
         count[count == 0] = 1.0
         y[c].dat = total / count
     return y
+
+
+# ----------------------------------------------------------------------------
+# hyper-parameter estimate  (unires/_core.py:96-142)
+# ----------------------------------------------------------------------------
+def estimate_hyperpar(x):
+    """Noise sd / precision and mean foreground intensity of every observation from a two-class
+    mixture fit to its histogram (non-negative voxels only unless the observation is CT)."""
+    from oracle.nitorch_shim.tools.img_statistics import estimate_noise
+    for xc in x:
+        for obs in xc:
+            dat = obs.dat if obs.ct else obs.dat[obs.dat >= 0]
+            noise, rest = estimate_noise(dat, num_class=2)
+            obs.sd = noise['sd'].float()
+            obs.tau = 1 / noise['sd'].float() ** 2
+            obs.mu = torch.abs(rest['mean'].float() - noise['mean'].float())
+    return x

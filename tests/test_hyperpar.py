@@ -138,19 +138,21 @@ def test_histogram_kernels_equal_oracle(cuda, drop_negative):
 def test_estimate_hyperpar_equals_oracle(cuda):
     """_estimate_hyperpar on the GPU (MR and CT observations) against the reference's loop over
     the oracle's estimate_noise (unires/_core.py:112-136)."""
+    from oracle import unires_port as P
     from unires_b200 import _core, struct
     vols = [_volume(4, False), _volume(5, False) - 400.0]
     cts = [False, True]
     x = [[struct._input(dat=v.to(cuda), ct=ct)] for v, ct in zip(vols, cts)]
     _core._estimate_hyperpar(x, None)
-    for v, ct, xc in zip(vols, cts, x):
-        dat = v if ct else v[v >= 0]
-        noise, rest = S.estimate_noise(dat, num_class=2)
-        sd = noise['sd'].float()
-        assert abs(float(xc[0].sd) - float(sd)) <= 1e-6 * float(sd)
-        assert abs(float(xc[0].tau) - float(1 / sd ** 2)) <= 1e-6 * float(1 / sd ** 2)
-        mu = torch.abs(rest['mean'].float() - noise['mean'].float())
-        assert abs(float(xc[0].mu) - float(mu)) <= 1e-6 * float(mu)
+    # the port's control flow is pinned bitwise against the reference's own _estimate_hyperpar
+    # (tests/test_oracle_vs_reference.py)
+    xo = P.estimate_hyperpar([[P.Observation(v.clone(), torch.eye(4), tau=1.0, ct=ct)]
+                              for v, ct in zip(vols, cts)])
+    for xc, oc in zip(x, xo):
+        for k in ('sd', 'tau', 'mu'):
+            got, want = float(getattr(xc[0], k)), float(getattr(oc[0], k))
+            assert abs(got - want) <= 1e-6 * abs(want), (k, got, want)
+            assert getattr(xc[0], k).device.type == 'cuda'
 
 
 @pytest.mark.gpu

@@ -102,3 +102,30 @@ def test_port_init_y_dat_matches_reference_bitwise():
     ref._core._init_y_dat(sr.x, sr.y, sr.sett)
     for a, b in zip(sp.y, sr.y):
         assert torch.equal(a.dat, b.dat)
+
+
+def test_port_estimate_hyperpar_matches_reference_bitwise():
+    """The reference's own `_estimate_hyperpar` (unires/_core.py:96-142) driving the restated
+    `estimate_noise` against the port's restatement of that control flow: the `dat >= 0`
+    selection, float32 casts, tau = 1 / sd^2 and mu = |foreground - noise class|."""
+    from oracle import gen_golden
+    from oracle.adapters import reference_namespaces
+    ref = LR.load_reference()
+    recipe = dict(gen_golden.RECIPES['sr3_thick_xyz'])
+    sp = U.build(recipe, *U.port_namespaces())
+    sr = U.build(recipe, *reference_namespaces())
+    g = torch.Generator().manual_seed(9)
+    for xp, xr in zip(sp.x, sr.x):  # noise everywhere (negative voxels appear), like the notebooks
+        n = 25 * torch.randn(xp[0].dat.shape, generator=g)
+        xp[0].dat = xp[0].dat + n
+        xr[0].dat = xr[0].dat + n
+    sr.x[1][0].ct = sp.x[1][0].ct = True  # one observation through the Gaussian branch
+    sr.sett.do_print = 0
+    sr.sett.show_hyperpar = False
+    ref._core._estimate_hyperpar(sr.x, sr.sett)
+    P.estimate_hyperpar(sp.x)
+    for xp, xr in zip(sp.x, sr.x):
+        for k in ('sd', 'tau', 'mu'):
+            a, b = getattr(xp[0], k), getattr(xr[0], k)
+            assert a.dtype == b.dtype == torch.float32 and torch.equal(a, b), k
+        assert float(xp[0].sd) > 0
