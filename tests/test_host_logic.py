@@ -80,6 +80,11 @@ def test_no_cpu_fallback_and_reference_errors():
         _project._proj_apply('A', dat, po)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _project._DtD(torch.zeros(4, 4, 4), (1, 1, 1))
+    from unires_b200 import _core, stats
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        stats.estimate_noise(torch.rand(4, 4, 4))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _core._estimate_hyperpar([[struct._input(dat=torch.rand(4, 4, 4), ct=False)]])
 
 
 def test_settings_defaults_match_reference_fields():

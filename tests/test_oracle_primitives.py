@@ -133,3 +133,40 @@ def test_lhs_symmetric_psd():
     a, b = (f(u) * v).double().sum(), (u * f(v)).double().sum()
     assert abs(a - b) < 1e-5 * abs(a)
     assert (f(u) * u).double().sum() > 0
+
+
+def test_multi_axis_operator_factorises_into_single_axis_terms():
+    """A'A of an observation decimated along several axes (BASELINE configs[4]: ratio 2 on every
+    axis, rect-5 x gauss-9 x gauss-9) equals the product of the per-axis terms B_a' B_a built
+    from the 1-D factors of smo_ker -- the identity the chained lean passes of the CUDA path rely
+    on (unires/_project.py:153-154,164-179 evaluates it as one dense 3-D conv / conv_transpose)."""
+    import torch.nn.functional as F
+    from oracle import unires_port as P
+    from unires_b200.kernels import separable_factors
+    dim_y, zoom = (20, 24, 28), (2.0, 2.0, 2.0)
+    mat_y = torch.eye(4, dtype=torch.float64)
+    mat_x = mat_y @ torch.diag(torch.tensor(list(zoom) + [1.0], dtype=torch.float64))
+    dim_x = tuple(int(d // z) for d, z in zip(dim_y, zoom))
+    po = P.proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0)
+    assert tuple(po.smo_ker.shape[-3:]) == (5, 9, 9) and po.ratio == (2, 2, 2)
+    obs = P.Observation(torch.zeros(dim_x, dtype=torch.float64), mat_x, tau=1.0, po=po)
+    rec = P.Recon(torch.zeros(dim_y, dtype=torch.float64), mat_y, lam=0.1)
+    g = torch.Generator().manual_seed(0)
+    v = torch.rand(dim_y, generator=g, dtype=torch.float64)
+    po.smo_ker = po.smo_ker.double()
+    dense = P.proj('AtA', v, [obs], rec, rho=0.0, vx_y=torch.ones(3, dtype=torch.float64))
+    off = torch.linalg.solve(po.mat_y.double(), po.mat_yx.double())[:3, 3].round().int().tolist()
+    out = v
+    for a, k in enumerate(separable_factors(po.smo_ker)):
+        k = torch.tensor(k, dtype=torch.float64)
+        n, nyx, r = dim_y[a], po.dim_yx[a], po.ratio[a]
+        t = out.movedim(a, -1)
+        shape = t.shape
+        t = F.pad(t.reshape(-1, 1, n), (-off[a], nyx - n + off[a]))   # pull: zero-padded yx grid
+        low = F.conv1d(t, k[None, None], stride=r)                      # B_a
+        assert low.shape[-1] == dim_x[a]
+        back = F.conv_transpose1d(low, k[None, None], stride=r)         # B_a'
+        back = F.pad(back, (0, nyx - back.shape[-1]))[..., -off[a]:-off[a] + n]  # push: crop
+        out = back.reshape(shape).movedim(-1, a)
+    # smo_ker is stored in float32: its 1-D factors rebuild it to float32 rounding (1e-7)
+    assert float((out - dense).abs().max()) < 1e-6 * float(dense.abs().max())
