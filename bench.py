@@ -324,8 +324,21 @@ def oracle_problem(workload, channel=0):
     return synth.make_scenario(cfg, port_ops, port_structs, device='cpu', truth=truth)
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 for every rank: the CPU arms must still use every
+    host core this process may run on (the reference would)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def time_oracle_cg(sc, n_iters):
     """Seconds per CG iteration of the oracle port (channel 0, tolerance 0)."""
+    use_all_host_cores()
     from oracle import unires_port as P
     from oracle.nitorch_shim.core import optim as OO
     vx = torch.ones(3) * float(sc.cfg['vx_y'])
