@@ -132,7 +132,7 @@ def main():
               '%.0f KB' % (os.path.getsize(path) / 1024))
 
 
-if __name__ == '__main__' and not {'--fit', '--scaling', '--rigid'} & set(sys.argv):
+if __name__ == '__main__' and not {'--fit', '--scaling', '--rigid', '--mid'} & set(sys.argv):
     main()
     main_fit()
     main_fit(scaling=True)
@@ -311,3 +311,85 @@ if __name__ == '__main__' and '--rigid' in sys.argv:
     main_rigid()
 if __name__ == '__main__' and '--scaling' in sys.argv:
     main_scaling()
+
+
+# ---------------------------------------------------------------------------
+# mid-size fixtures: grids that span several row tiles, z tiles and column segments of the
+# streaming kernels (the small fixtures above fit one tile).  Volumes are stored as a strided
+# sample plus their float64 norm, so a fixture stays around 1 MB.
+# ---------------------------------------------------------------------------
+MID_STRIDE = 29
+MID_RECIPES = {
+    'mid_sr3': dict(base='sr3_256', dim_y=(40, 96, 260), n_channels=3, sd=25.0, scl=0.0,
+                    rigid=None, admm_iters=1),
+    'mid_sr3_rigid': dict(base='sr3_256', dim_y=(40, 96, 260), n_channels=3, sd=25.0, scl=0.04,
+                          rigid=[((2.1, -1.7, 3.3), (0.08, -0.05, 0.1)),
+                                 ((-3.2, 2.6, -1.9), (-0.1, 0.07, 0.04)),
+                                 ((2.4, 1.8, -4.4), (0.05, 0.1, -0.09))], admm_iters=1),
+}
+
+
+def mid_sample(t):
+    t = torch.as_tensor(t)
+    return t.flatten()[::MID_STRIDE].numpy().copy(), np.float64(t.double().norm().item())
+
+
+def main_mid():
+    from oracle.adapters import reference_namespaces
+    from oracle.load_reference import load_reference
+    from oracle.nitorch_shim.core import optim as shim_optim
+    ref = load_reference()
+    ops, structs = reference_namespaces()
+    for name, recipe in MID_RECIPES.items():
+        torch.manual_seed(0)
+        sc = build(recipe, ops, structs)
+        out = {'recipe': json.dumps(recipe)}
+        C = len(sc.x)
+
+        def put(key, t):
+            out[key + '_s'], out[key + '_n'] = mid_sample(t)
+
+        for c in range(C):
+            out['in_x%d_sha' % c] = digest(sc.x[c][0].dat)
+            out['in_y%d_sha' % c] = digest(sc.y[c].dat)
+            vy, vx = probe_inputs(sc, c)
+            po = sc.x[c][0].po
+            kw = dict(method=sc.sett.method)
+            put('A%d' % c, ref._project._proj_apply('A', vy[None, None], po, **kw)[0, 0])
+            put('At%d' % c, ref._project._proj_apply('At', vx[None, None], po, **kw)[0, 0])
+            vx_y = ref._update.voxel_size(sc.y[0].mat).float()
+            put('lhs%d' % c, ref._project._proj('AtA', vy, sc.x[c], sc.y[c], method=sc.sett.method,
+                                                do=sc.sett.do_proj, rho=sc.rho, vx_y=vx_y))
+        z, w = ref._update._admm_aux(sc.y, sc.sett)
+        tmp = torch.zeros(tuple(sc.y[0].dim))
+        obj = torch.zeros(1, 3, dtype=torch.float64)
+        cg_iters = []
+        orig_cg = ref._update.cg
+
+        def counting_cg(*a, **k):
+            r = orig_cg(*a, **k)
+            cg_iters.append(shim_optim.cg.last_n_iter)
+            return r
+
+        ref._update.cg = counting_cg
+        try:
+            y, z, w, tmp, obj = ref._update._update_admm(sc.x, sc.y, z, w, sc.rho, tmp, obj, 0,
+                                                         sc.sett)
+        finally:
+            ref._update.cg = orig_cg
+        for c in range(C):
+            put('y%d' % c, sc.y[c].dat)
+        put('jtv', tmp)
+        put('z', z)
+        put('w', w)
+        out['obj'] = obj.numpy()
+        out['cg_iters'] = np.array(cg_iters, dtype=np.int32)
+        out['rho'] = np.float32(float(sc.rho))
+        path = os.path.join(GOLDEN_DIR, name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, 'cg_iters', cg_iters, 'obj', obj[0].tolist(),
+              '%.0f KB' % (os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__' and '--mid' in sys.argv:
+    main_mid()

@@ -1,10 +1,11 @@
 """Import the reference's OWN control-flow files by path on top of the shim.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Only usable in the build
-container, where /root/reference exists; the GPU box does not have it, so
-nothing that runs there may call this (tests skip when ``available()`` is
-False).  No reference source is copied: the modules are executed from
-/root/reference/unires/*.py in place.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The files are looked for under
+/root/reference (build container) and then under <repo>/baseline/_ref, the
+git-ignored `pip install --no-deps --target baseline/_ref` copy of the
+reference that travels to the GPU box with the gpurun snapshot (recorded in
+DESIGN.md); tests skip when ``available()`` is False.  No reference source is
+copied into the repository's history: the modules are executed in place.
 
     ref = load_reference()          # namespace with .struct ._project ._update
     ref._project._proj_apply('A', dat, po)
@@ -14,11 +15,45 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('UNIRES_REFERENCE', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    cands = [os.environ.get('UNIRES_REFERENCE'), '/root/reference',
+             os.path.join(_REPO, 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, 'unires', '_project.py')):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, 'unires', '_project.py'))
+
+
+def load_by_path(pkg_name, mods=('struct', '_util', '_project', '_update', '_core', 'run')):
+    """Execute the reference's files in place as package `pkg_name` on top of whatever
+    `nitorch` is registered in sys.modules at this moment (the oracle shim, or the
+    product's nitorch_compat for the drop-in tests)."""
+    if not available():
+        raise FileNotFoundError('reference not found under ' + REFERENCE_ROOT)
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, 'unires')]
+    sys.modules[pkg_name] = pkg
+    ns = types.SimpleNamespace()
+    for mod in mods:
+        full = pkg_name + '.' + mod
+        spec = importlib.util.spec_from_file_location(
+            full, os.path.join(REFERENCE_ROOT, 'unires', mod + '.py'))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+        setattr(pkg, mod, m)
+        setattr(ns, mod, m)
+    return ns
 
 
 def install_shim():
@@ -58,19 +93,5 @@ def load_reference():
     if not available():
         raise FileNotFoundError('reference not found under ' + REFERENCE_ROOT)
     install_shim()
-    pkg_name = '_unires_reference'
-    pkg = types.ModuleType(pkg_name)
-    pkg.__path__ = [os.path.join(REFERENCE_ROOT, 'unires')]
-    sys.modules[pkg_name] = pkg
-    ns = types.SimpleNamespace()
-    for mod in ('struct', '_util', '_project', '_update', '_core', 'run'):
-        full = pkg_name + '.' + mod
-        spec = importlib.util.spec_from_file_location(
-            full, os.path.join(REFERENCE_ROOT, 'unires', mod + '.py'))
-        m = importlib.util.module_from_spec(spec)
-        sys.modules[full] = m
-        spec.loader.exec_module(m)
-        setattr(pkg, mod, m)
-        setattr(ns, mod, m)
-    _cache = ns
-    return ns
+    _cache = load_by_path('_unires_reference')
+    return _cache

@@ -162,8 +162,9 @@ def check(rc):
 # ---------------------------------------------------------------------------
 # tensor plumbing
 # ---------------------------------------------------------------------------
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """Current CUDA stream of `device` (default: the current device) as a void*."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):
@@ -190,6 +191,12 @@ def require_cuda_f32(t, name='tensor'):
                            '(there is no CPU fallback)' % (name, t.device))
     if t.dtype != torch.float32:
         raise TypeError('unires_b200: %s must be float32, got %s' % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream: pointers of another device would
+        # be dereferenced on the wrong GPU
+        raise RuntimeError('unires_b200: %s is on %s but the current CUDA device is cuda:%d; '
+                           'wrap the call in torch.cuda.device(...)'
+                           % (name, t.device, torch.cuda.current_device()))
     return t if t.is_contiguous() else t.contiguous()
 
 

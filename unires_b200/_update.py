@@ -344,6 +344,10 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return _update_admm(x, y, z, w, rho, tmp, obj, n_iter, sett)
     from . import parallel
+    if len(y) == 0 or len(y) > _lib.UR_MAX_CHANNELS:
+        # parallel.channel_shard rejects world_size > n_channels on every rank up front
+        raise ValueError('_update_admm_sharded: every rank needs between 1 and %d channels '
+                         '(world size > number of channels?)' % _lib.UR_MAX_CHANNELS)
     dim, vx = _geometry(y)
     n_vox = dim[0] * dim[1] * dim[2]
     rho_f = _hs(rho)

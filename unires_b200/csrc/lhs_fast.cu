@@ -168,7 +168,11 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   {
     static std::unordered_map<size_t, int> occ_cache;
     static std::mutex occ_mu;
-    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull);
+    // the opt-in to > 48 KB of dynamic shared memory and the occupancy are per DEVICE
+    int dev = 0;
+    UR_CUDA_CHECK(cudaGetDevice(&dev));
+    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull) ^
+                       ((size_t)(dev + 1) * 0xC2B2AE3D27D4EB4Full);
     std::lock_guard<std::mutex> lock(occ_mu);
     auto it = occ_cache.find(key);
     if (it != occ_cache.end()) {

@@ -858,7 +858,12 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
 #undef UR_SK_ROW
   if (!encode_fn()) return UR_ERR_UNSUPPORTED;  // no cuTensorMapEncodeTiled: no TMA path
   if (dry_run) return UR_OK;
-  static bool attr_set = false;
+  // per DEVICE: the opt-in to > 48 KB of dynamic shared memory is a device-side attribute
+  static bool attr_set_dev[64] = {false};
+  int dev = 0;
+  UR_CUDA_CHECK(cudaGetDevice(&dev));
+  UR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  bool &attr_set = attr_set_dev[dev];
   if (!attr_set) {
     for (int i = 0; i < 4; ++i)
       for (int k = 0; k < 4; ++k)
@@ -881,7 +886,8 @@ int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) 
     // the occupancy query costs several microseconds of host time: remember the answer
     static std::unordered_map<size_t, int> occ_cache;
     static std::mutex occ_mu;
-    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull);
+    const size_t key = (size_t)kernel ^ (smem * 0x9E3779B97F4A7C15ull) ^
+                       ((size_t)(dev + 1) * 0xC2B2AE3D27D4EB4Full);
     std::lock_guard<std::mutex> lock(occ_mu);
     auto it = occ_cache.find(key);
     if (it != occ_cache.end()) {

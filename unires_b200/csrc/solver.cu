@@ -20,7 +20,7 @@ int validate_proj(const ur_proj *po);
 size_t proj_workspace_bytes(const ur_proj *po);
 int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_out, float scale,
                        void *d_ws, size_t ws_bytes, cudaStream_t st);
-int scratch_reduce(GridReduce *gr);  // vecops.cu
+int scratch_reduce(GridReduce *gr, cudaStream_t st);  // vecops.cu
 
 // lhs_stream.cu: TMA-staged streaming kernel.  Returns UR_ERR_UNSUPPORTED (without
 // setting an error) when the problem does not fit it, so the caller falls back.
@@ -1254,7 +1254,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
 extern "C" int ur_cg_fetch(const void *d_ws, int32_t *n_iter, double *obj, int32_t n_obj,
                            ur_stream stream) {
   UR_REQUIRE(d_ws, "ur_cg_fetch: null workspace");
-  static CgState host;  // not re-entrant across threads; guarded by the GIL in practice
+  CgState host;
   UR_CUDA_CHECK(cudaMemcpyAsync(&host, d_ws, sizeof(CgState), cudaMemcpyDeviceToHost,
                                 (cudaStream_t)stream));
   UR_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1269,7 +1269,7 @@ extern "C" int ur_cg_update_xr(float *d_x, float *d_r, const float *d_p, const f
                                size_t n, const double *d_alpha, double *d_rr, ur_stream stream) {
   UR_REQUIRE(d_x && d_r && d_p && d_Ap && d_alpha && d_rr && n > 0, "ur_cg_update_xr: bad args");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   FinalizeArgs fin{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, d_rr};
   const bool vec = (n % 4 == 0) && aligned16(d_x) && aligned16(d_r) && aligned16(d_p) && aligned16(d_Ap);

@@ -4,6 +4,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "solver.cuh"
 
 namespace ur {
@@ -34,22 +38,25 @@ int sm_count() {
   return cached[dev];
 }
 
-// Per-device scratch for the stand-alone reductions (ur_dot, ur_cg_update_xr,
-// ur_nll_data, ur_sqrt_sum).  Calls that share it must be stream-ordered.
+// Scratch for the stand-alone reductions (ur_dot, ur_cg_update_xr, ur_nll_data, ur_sqrt_sum,
+// ur_scaling_sums, ur_rigid_sums): one ticket counter + partials buffer per (device, stream),
+// so reductions in flight on different streams (sett.channel_streams) never share a counter.
 constexpr size_t kScratchPartials = 1 << 16;
-int scratch_reduce(GridReduce *gr) {
-  static void *bufs[64] = {nullptr};
+int scratch_reduce(GridReduce *gr, cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, void *> bufs;
   int dev = 0;
   UR_CUDA_CHECK(cudaGetDevice(&dev));
-  UR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-  if (!bufs[dev]) {
+  std::lock_guard<std::mutex> lock(mu);
+  void *&slot = bufs[std::make_pair(dev, st)];
+  if (!slot) {
     void *p = nullptr;
     UR_CUDA_CHECK(cudaMalloc(&p, 256 + kScratchPartials * sizeof(double)));
     UR_CUDA_CHECK(cudaMemset(p, 0, 256));
-    bufs[dev] = p;
+    slot = p;
   }
-  gr->counter = (unsigned *)bufs[dev];
-  gr->partials = (double *)((char *)bufs[dev] + 256);
+  gr->counter = (unsigned *)slot;
+  gr->partials = (double *)((char *)slot + 256);
   return UR_OK;
 }
 
@@ -117,7 +124,7 @@ extern "C" int ur_dot(const float *d_a, const float *d_b, size_t n, double *d_ou
                       ur_stream stream) {
   UR_REQUIRE(d_a && d_b && d_out && n > 0, "ur_dot: bad args");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   reduce_kernel<0><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, 0.f, 0, gr, d_out);
   UR_LAUNCH_CHECK();
@@ -128,7 +135,7 @@ extern "C" int ur_nll_data(const float *d_x, const float *d_Ay, size_t n, float 
                            double *d_out, int accumulate, ur_stream stream) {
   UR_REQUIRE(d_x && d_Ay && d_out && n > 0, "ur_nll_data: bad args");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   reduce_kernel<1><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_x, d_Ay, n, tau, accumulate,
                                                                     gr, d_out);
@@ -191,7 +198,7 @@ extern "C" int ur_scaling_sums(const float *d_x, const float *d_y, const int32_t
              "ur_scaling_sums: bad args");
   UR_REQUIRE(axis >= 0 && axis < 3, "ur_scaling_sums: axis must be 0, 1 or 2");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   const Dim3i d = make_dim(dim);
   scaling_sums_kernel<<<red_blocks(d.numel()), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, d, axis,
@@ -290,7 +297,7 @@ extern "C" int ur_rigid_sums(const float *d_grad, const float *d_res, const floa
   UR_REQUIRE(d_grad && d_res && dm && d_out && dim && dim[0] > 0 && dim[1] > 0 && dim[2] > 0,
              "ur_rigid_sums: bad args");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   RigidDm m;
   for (int k = 0; k < 72; ++k) (&m.m[0][0][0])[k] = dm[k];
@@ -305,7 +312,7 @@ extern "C" int ur_rigid_sums(const float *d_grad, const float *d_res, const floa
 extern "C" int ur_sqrt_sum(const float *d_e, size_t n, double *d_out, ur_stream stream) {
   UR_REQUIRE(d_e && d_out && n > 0, "ur_sqrt_sum: bad args");
   GridReduce gr;
-  int rc = scratch_reduce(&gr);
+  int rc = scratch_reduce(&gr, (cudaStream_t)stream);
   if (rc) return rc;
   reduce_kernel<2><<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_e, nullptr, n, 0.f, 0, gr,
                                                                     d_out);

@@ -6,6 +6,7 @@ tensor.  Profile codes: -1 dirac, 0 rect, 1 triangle, 2 gauss; each is the
 slice profile of the given FWHM (voxels) convolved with the linear-
 interpolation basis and sampled at integer offsets.
 """
+import functools
 import math
 
 import torch
@@ -49,16 +50,21 @@ def _tri(w):
 
 
 def smooth1d(profile, fwhm):
-    """1-D factor as a list of Python floats (float64)."""
-    profile, fwhm = int(profile), float(fwhm)
+    """1-D factor as a list of Python floats (float64); memoised (the rigid update rebuilds the
+    operator, hence its taps, for every observation on every step)."""
+    return list(_smooth1d_cached(int(profile), float(fwhm)))
+
+
+@functools.lru_cache(maxsize=256)
+def _smooth1d_cached(profile, fwhm):
     if profile == -1:
-        return [1.0]
+        return (1.0,)
     if profile == 0:
-        return _rect(fwhm)
+        return tuple(_rect(fwhm))
     if profile == 1:
-        return _tri(fwhm)
+        return tuple(_tri(fwhm))
     if profile == 2:
-        return _gauss(fwhm)
+        return tuple(_gauss(fwhm))
     raise ValueError('unknown slice profile %r' % (profile,))
 
 

@@ -1,1 +1,1 @@
-from . import kernels, optim  # noqa: F401
+from . import kernels, optim, math, _linalg_expm, constants, utils  # noqa: F401

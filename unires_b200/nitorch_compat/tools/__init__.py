@@ -1,1 +1,1 @@
-from . import img_statistics  # noqa: F401
+from . import img_statistics, preproc, _preproc_fov, _preproc_utils  # noqa: F401

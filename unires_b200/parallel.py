@@ -19,6 +19,11 @@ def channel_shard(n_channels, world_size, rank):
     """Channels owned by `rank`: round-robin c -> c mod world_size."""
     if world_size < 1 or not (0 <= rank < world_size):
         raise ValueError('bad rank/world_size')
+    if world_size > n_channels:
+        # a rank without channels could not take part in the kernels between the all-reduces;
+        # every rank evaluates this with the same arguments, so all of them raise together
+        raise ValueError('channel_shard: %d ranks for %d channels (use at most one rank per '
+                         'channel)' % (world_size, n_channels))
     return [c for c in range(n_channels) if c % world_size == rank]
 
 

@@ -22,6 +22,14 @@ CONFIGS = {
     # each channel thick-sliced x4 along a different axis (notebook recipe)
     'sr3_256': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0,
                     thick=[(0, 4), (1, 4), (2, 4)]),
+    # configs[1] with the notebook's rigid misalignment (demos/demo_multi_channel.ipynb cell 4:
+    # translations within +-5 mm, rotations within +-0.1 rad): rotated operators, i.e. what
+    # every real multi-channel run executes once `unified_rigid` has moved the scans
+    'sr3_256_rigid': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0,
+                          thick=[(0, 4), (1, 4), (2, 4)],
+                          rigid=[((4.1, -2.7, 3.3), (0.08, -0.05, 0.1)),
+                                 ((-3.2, 4.6, -1.9), (-0.1, 0.07, 0.04)),
+                                 ((2.4, 1.8, -4.4), (0.05, 0.1, -0.09))]),
     # configs[1], literal reading: 1 mm observations (181x217x181) on the 256^3 grid -- the
     # operator is an integer-shift crop / zero-pad embed, A'A a field-of-view mask
     'crop3_256': dict(dim_y=(256, 256, 256), fov=(181, 217, 181), vx_y=1.0, thick=[None] * 3),
@@ -55,6 +63,8 @@ def scaled(cfg, dim_y, n_channels=None):
         c['fov'] = tuple(max(8, int(round(v * s))) for v, s in zip(cfg['fov'], f))
     if n_channels is not None:
         c['thick'] = list(cfg['thick'])[:n_channels]
+        if cfg.get('rigid') is not None:
+            c['rigid'] = list(cfg['rigid'])[:n_channels]
     return c
 
 
@@ -138,6 +148,8 @@ def make_scenario(cfg, ops, structs, device='cpu', seed=0, sd=25.0, reg_scl=4.0,
     denoise = bool(cfg.get('denoise'))
     dim_y = tuple(cfg['dim_y'])
     truth = truth if truth is not None else phantom(dim_y, C, seed)
+    if rigid is None and cfg.get('rigid') is not None:
+        rigid = [rigid_matrix(t, r) for t, r in cfg['rigid']]
     g = torch.Generator().manual_seed(seed + 1)
     sett = structs.settings()
     sett.device = device
