@@ -219,3 +219,38 @@ def test_rotated_adjoint_is_deterministic_and_matches_scatter(cuda):
     check(lib.ur_affine_push(ptr(w), i3(po.dim_x), s.mat, ptr(scatter), i3(po.dim_y), 1, 0, 1.0,
                              stream()))
     assert U.rel_l2(gather, scatter) < 1e-6
+
+
+@pytest.mark.parametrize('name', ['sr2_rigid', 'mid_sr3_rigid'])
+def test_rotated_fused_kernels_equal_general_path(cuda, name):
+    """Rotated operators: the in-tile forward kernel + gather adjoint (csrc/rot.cuh: pull, slice
+    profile, scaling and the transposed profile in shared memory; adjoint gathered inside the
+    lhs kernel) against the pull / conv / scale / conv' / push chain they replace
+    (ur_tune rot_fused=0), for A, At, AtA and the CG left-hand side; both are deterministic."""
+    from oracle import gen_golden
+    from unires_b200 import _lib, _project
+    _, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    vx_y = [float(sc.cfg['vx_y'])] * 3
+    res = {}
+    try:
+        for fused in (1, 0):
+            _lib.check(_lib.lib.ur_tune(b'rot_fused', fused))
+            outs = []
+            for c in range(len(x)):
+                vy, vx = gen_golden.probe_inputs(sc, c)
+                po = x[c][0].po
+                for op, v in (('A', vy), ('At', vx), ('AtA', vy)):
+                    outs.append(_project._proj_apply(op, v.to(cuda)[None, None], po)[0, 0].clone())
+                lhs = _project.LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj,
+                                           rho=sc.rho, vx_y=vx_y)
+                a = lhs(vy.to(cuda))
+                b = lhs(vy.to(cuda))
+                assert torch.equal(a, b)  # no atomics: bit-reproducible
+                outs.append(a)
+            res[fused] = outs
+    finally:
+        _lib.check(_lib.lib.ur_tune(b'rot_fused', 1))
+    for a, b in zip(res[1], res[0]):
+        assert a.shape == b.shape and U.rel_l2(a, b) < 2e-6

@@ -27,6 +27,7 @@ static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 
 int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   using namespace fast;
   if (A.nterm > 1) return UR_ERR_UNSUPPORTED;  // solver.cu splits several terms into passes
+  if (A.nrot > 0) return UR_ERR_UNSUPPORTED;   // rotated terms are gathered in the direct kernel
   if (!a16(A.acc)) return UR_ERR_UNSUPPORTED;
   const int pitch = A.pitch > 0 ? A.pitch : A.nz;
   if (pitch % 4 != 0 || pitch < A.nz || pitch - A.nz >= 4 || A.nz < 4) return UR_ERR_UNSUPPORTED;

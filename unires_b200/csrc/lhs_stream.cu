@@ -738,7 +738,7 @@ typedef void (*StreamKernel)(const CUtensorMap, const StreamArgs);
 // variant < 0: dry run (eligibility check only, nothing is launched)
 int lhs_stream_launch(int mode, const LhsArgs &A, int variant, cudaStream_t st) {
   const bool dry_run = variant < 0;
-  if (A.acc != nullptr || A.nterm > 1) return UR_ERR_UNSUPPORTED;
+  if (A.acc != nullptr || A.nterm > 1 || A.nrot > 0) return UR_ERR_UNSUPPORTED;
   if (A.nz % 4 != 0 || A.nz < 4) return UR_ERR_UNSUPPORTED;
   // 32-bit element offsets inside the kernel (incl. the look-ahead planes past the end)
   if ((long long)A.nx * A.ny * A.nz + 64ll * A.ny * A.nz + 64ll * A.nx * A.nz > 0x7fffffffll)

@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "rot.cuh"
 
 namespace ur {
 
@@ -21,6 +22,7 @@ int lattice_push(const float *, Dim3i, const float[12], float *, Dim3i, float, c
 int conv_axis(const float *, Dim3i, float *, int, const float *, int, int, bool, cudaStream_t,
               Dim3i *);
 int apply_scaling(const float *, float *, Dim3i, float, int, cudaStream_t);
+extern int g_rot_fused;  // rot.cu
 
 static bool identity_pass(const ur_proj *po, int a) {
   return po->ksize[a] == 1 && po->ratio[a] == 1 && po->ker[a][0] == 1.0f;
@@ -140,6 +142,22 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
   Dim3i d;
   // identity rotation + integer shift: crop / zero-pad embed instead of gather / atomic scatter
   const bool lat = ur_proj_is_lattice(po) != 0;
+  // rotated operator with at most one decimated axis: in-tile forward kernel + gather adjoint
+  // (rot.cuh) instead of pull / conv / scale / conv' / push through HBM
+  if (!lat && g_rot_fused) {
+    RotFwd F;
+    RotTerm T;
+    if (rot_describe(po, op, scale, &F, &T)) {
+      if (op == UR_OP_A) return rot_forward_launch(UR_OP_A, F, d_in, d_out, st);
+      if (op == UR_OP_AT)
+        rc = rot_expand_launch(F, d_in, bufs[0], st);
+      else
+        rc = rot_forward_launch(UR_OP_ATA, F, d_in, bufs[0], st);
+      if (rc) return rc;
+      T.u = bufs[0];
+      return rot_adjoint_launch(T, po->dim_y, d_out, 1, st);
+    }
+  }
   auto pull = [&](const float *src, float *dst) {
     return lat ? lattice_pull(src, dy, po->mat, dst, dsrc, st)
                : affine_pull(src, dy, po->mat, dst, dsrc, 1, 0, st);

@@ -1,0 +1,373 @@
+// Rotated observations (rot.cuh): the in-tile forward kernel  v -> C P v -> (S / C'S^2) and the
+// host side that maps a ur_proj onto it.  Reference: unires/_project.py:147-179.
+#include <math.h>
+#include <string.h>
+
+#include "rot.cuh"
+
+namespace ur {
+
+int g_rot_fused = 1;  // ur_tune("rot_fused")
+
+constexpr int kRotThreads = 256;
+
+struct RotTile {
+  int e[3];    // owned block of the OUTPUT index space (A: low-res rows; AtA: intermediate)
+  int pe[3];   // pulled tile extents
+  int nj_max;  // low-res rows per tile along the profile axis (AtA)
+};
+
+// trilinear pull of v at the intermediate voxel (i, j, k): same float32 expressions, FOV
+// tolerance and corner order as resample_kernel (resample.cu), i.e. as the oracle
+__device__ __forceinline__ float rot_pull(const float *__restrict__ v, const RotFwd &F, int i,
+                                          int j, int k) {
+  const float fi = (float)i, fj = (float)j, fk = (float)k;
+  const float cx = fmaf(F.m[2], fk, fmaf(F.m[1], fj, F.m[0] * fi)) + F.m[3];
+  const float cy = fmaf(F.m[6], fk, fmaf(F.m[5], fj, F.m[4] * fi)) + F.m[7];
+  const float cz = fmaf(F.m[10], fk, fmaf(F.m[9], fj, F.m[8] * fi)) + F.m[11];
+  if (!(cx > -kRotFovTol && cx < (float)(F.s[0] - 1) + kRotFovTol && cy > -kRotFovTol &&
+        cy < (float)(F.s[1] - 1) + kRotFovTol && cz > -kRotFovTol &&
+        cz < (float)(F.s[2] - 1) + kRotFovTol))
+    return 0.f;
+  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const float wx1 = cx - fx, wy1 = cy - fy, wz1 = cz - fz;
+  const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+  const int sy = F.s[2], sx = F.s[1] * F.s[2];
+  const bool vx0 = ix >= 0, vx1 = ix + 1 < F.s[0];  // ix <= s-1 and ix+1 >= 0 by the FOV test
+  const bool vy0 = iy >= 0, vy1 = iy + 1 < F.s[1];
+  const bool vz0 = iz >= 0, vz1 = iz + 1 < F.s[2];
+  const float *b = v + ((long long)ix * sx + (long long)iy * sy + iz);
+  const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+  float acc = 0.f;
+  if (vx0 && vy0 && vz0) acc += __ldg(b) * (w00 * wz0);
+  if (vx0 && vy0 && vz1) acc += __ldg(b + 1) * (w00 * wz1);
+  if (vx0 && vy1 && vz0) acc += __ldg(b + sy) * (w01 * wz0);
+  if (vx0 && vy1 && vz1) acc += __ldg(b + sy + 1) * (w01 * wz1);
+  if (vx1 && vy0 && vz0) acc += __ldg(b + sx) * (w10 * wz0);
+  if (vx1 && vy0 && vz1) acc += __ldg(b + sx + 1) * (w10 * wz1);
+  if (vx1 && vy1 && vz0) acc += __ldg(b + sx + sy) * (w11 * wz0);
+  if (vx1 && vy1 && vz1) acc += __ldg(b + sx + sy + 1) * (w11 * wz1);
+  return acc;
+}
+
+__device__ __forceinline__ int floordiv_i(int a, int b) {
+  int q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+// ATA = false: out (dim_x)  = weight * S C P v          block owns e[] low-res voxels
+// ATA = true : out (dim_yx) = weight * C' S C P v        block owns e[] intermediate voxels
+//              (S already holds the squared factors)
+template <bool ATA>
+__global__ void __launch_bounds__(kRotThreads)
+    rot_forward_kernel(const float *__restrict__ v, float *__restrict__ out, const RotFwd F,
+                       const RotTile T) {
+  extern __shared__ float sm[];
+  const int ax = F.axis;
+  const int tid = threadIdx.x;
+  const int b3[3] = {(int)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x};
+  int o0[3];  // first owned output index per axis
+#pragma unroll
+  for (int a = 0; a < 3; ++a) o0[a] = b3[a] * T.e[a];
+  // low-res rows of this tile along the profile axis
+  int j_min, nj_t;
+  if (ATA) {
+    const int u0 = o0[ax], u1 = min(u0 + T.e[ax], F.nyx[ax]) - 1;
+    j_min = -floordiv_i(-(u0 - F.k0 - F.K + 1), F.r);  // ceil
+    const int j_max = floordiv_i(u1 - F.k0, F.r);
+    nj_t = j_max - j_min + 1;
+  } else {
+    j_min = o0[ax];
+    nj_t = min(T.e[ax], F.nlr[ax] - o0[ax]);
+  }
+  if (nj_t < 1) nj_t = 0;
+  // pulled tile: intermediate indices [ps, ps + pn) per axis
+  int ps[3], pn[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ps[a] = o0[a];
+    pn[a] = min(T.e[a], (ATA ? F.nyx[a] : F.nlr[a]) - o0[a]);
+  }
+  ps[ax] = j_min * F.r + F.k0;
+  pn[ax] = nj_t > 0 ? (nj_t - 1) * F.r + F.K : 0;
+  float *pulled = sm;                                     // [pn0][pn1][pn2], pitches from T.pe
+  float *lres = sm + T.pe[0] * T.pe[1] * T.pe[2];         // low-res rows, same pitches but nj_t
+  const int pp1 = T.pe[2], pp0 = T.pe[1] * T.pe[2];
+  // ---- phase 1: pull ----
+  {
+    const int tot = pn[0] * pn[1] * pn[2];
+    for (int idx = tid; idx < tot; idx += kRotThreads) {
+      const int c2 = idx % pn[2], t = idx / pn[2];
+      const int c1 = t % pn[1], c0 = t / pn[1];
+      const int i = ps[0] + c0, j = ps[1] + c1, k = ps[2] + c2;
+      const int pa = ax == 0 ? i : (ax == 1 ? j : k);
+      float val = 0.f;
+      if (pa >= 0 && pa < F.nyx[ax]) val = rot_pull(v, F, i, j, k);
+      pulled[c0 * pp0 + c1 * pp1 + c2] = val;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: low-res rows  x[j] = s_j sum_t ker[t] yx[j r + k0 + t] ----
+  int ln[3] = {pn[0], pn[1], pn[2]};
+  ln[ax] = nj_t;
+  const int astep = ax == 0 ? pp0 : (ax == 1 ? pp1 : 1);
+  {
+    const int tot = ln[0] * ln[1] * ln[2];
+    for (int idx = tid; idx < tot; idx += kRotThreads) {
+      const int c2 = idx % ln[2], t = idx / ln[2];
+      const int c1 = t % ln[1], c0 = t / ln[1];
+      const int cc[3] = {c0, c1, c2};
+      const int jl = cc[ax];          // tile-local row
+      const int j = j_min + jl;       // global low-res row
+      int base = c0 * pp0 + c1 * pp1 + c2;
+      base += (jl * F.r - jl) * astep;  // replace the axis coordinate jl by jl * r
+      float acc = 0.f;
+      if (j >= 0 && j < F.nj) {
+        for (int tt = 0; tt < F.K; ++tt) acc = fmaf(F.ker[tt], pulled[base + tt * astep], acc);
+        if (F.scl_axis >= 0) {
+          const int g[3] = {ps[0] + c0, ps[1] + c1, ps[2] + c2};
+          const int js = F.scl_axis == ax ? j : g[F.scl_axis];
+          acc *= (js & 1) ? F.s_odd : F.s_even;
+        }
+      }
+      if (ATA) {
+        lres[c0 * pp0 + c1 * pp1 + c2] = acc;
+      } else if (j >= 0 && j < F.nj) {
+        int g[3] = {ps[0] + c0, ps[1] + c1, ps[2] + c2};
+        g[ax] = j;
+        out[((size_t)g[0] * F.nlr[1] + g[1]) * F.nlr[2] + g[2]] = F.weight * acc;
+      }
+    }
+  }
+  if (!ATA) return;
+  __syncthreads();
+  // ---- phase 3: expand  u[p] = weight sum_j ker[p - k0 - j r] x[j] ----
+  {
+    int en[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) en[a] = min(T.e[a], F.nyx[a] - o0[a]);
+    const int tot = en[0] * en[1] * en[2];
+    for (int idx = tid; idx < tot; idx += kRotThreads) {
+      const int c2 = idx % en[2], t = idx / en[2];
+      const int c1 = t % en[1], c0 = t / en[1];
+      int cc[3] = {c0, c1, c2};
+      const int u = o0[ax] + cc[ax] - F.k0;  // position relative to the first tap of row 0
+      int jl_lo = -floordiv_i(-(u - F.K + 1), F.r) - j_min;  // ceil((u-K+1)/r) - j_min
+      int jl_hi = floordiv_i(u, F.r) - j_min;
+      if (jl_lo < 0) jl_lo = 0;
+      if (jl_hi > nj_t - 1) jl_hi = nj_t - 1;
+      cc[ax] = 0;
+      const int base = cc[0] * pp0 + cc[1] * pp1 + cc[2];
+      float acc = 0.f;
+      for (int jl = jl_lo; jl <= jl_hi; ++jl)
+        acc = fmaf(F.ker[u - (j_min + jl) * F.r], lres[base + jl * astep], acc);
+      out[((size_t)(o0[0] + c0) * F.nyx[1] + (o0[1] + c1)) * F.nyx[2] + (o0[2] + c2)] =
+          F.weight * acc;
+    }
+  }
+}
+
+// u = weight * C' S x  (At): thread per intermediate voxel, x read from global (low-res)
+__global__ void __launch_bounds__(256)
+    rot_expand_kernel(const float *__restrict__ x, float *__restrict__ u, const RotFwd F) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int i = blockIdx.z;
+  if (k >= F.nyx[2] || j >= F.nyx[1]) return;
+  int g[3] = {i, j, k};
+  const int ax = F.axis;
+  const int uu = g[ax] - F.k0;
+  int j_lo = -floordiv_i(-(uu - F.K + 1), F.r), j_hi = floordiv_i(uu, F.r);
+  if (j_lo < 0) j_lo = 0;
+  if (j_hi > F.nj - 1) j_hi = F.nj - 1;
+  const size_t st = ax == 0 ? (size_t)F.nlr[1] * F.nlr[2] : (ax == 1 ? (size_t)F.nlr[2] : 1);
+  int gl[3] = {i, j, k};
+  gl[ax] = 0;
+  const float *base = x + ((size_t)gl[0] * F.nlr[1] + gl[1]) * F.nlr[2] + gl[2];
+  float acc = 0.f;
+  for (int jj = j_lo; jj <= j_hi; ++jj) {
+    float val = __ldg(base + (size_t)jj * st);
+    if (F.scl_axis >= 0) {
+      const int js = F.scl_axis == ax ? jj : g[F.scl_axis];
+      val *= (js & 1) ? F.s_odd : F.s_even;
+    }
+    acc = fmaf(F.ker[uu - jj * F.r], val, acc);
+  }
+  u[((size_t)i * F.nyx[1] + j) * F.nyx[2] + k] = F.weight * acc;
+}
+
+__global__ void __launch_bounds__(256)
+    rot_adjoint_kernel(const RotTerm T, float *__restrict__ out, int nx, int ny, int nz,
+                       int accumulate) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (z >= nz || y >= ny) return;
+  const float val = rot_gather(T, x, y, z, nx, ny, nz);
+  const size_t i = ((size_t)x * ny + y) * nz + z;
+  out[i] = accumulate ? out[i] + val : val;
+}
+
+static bool dirac_axis(const ::ur_proj *po, int a) {
+  return po->ksize[a] == 1 && po->ratio[a] == 1;
+}
+
+bool rot_describe(const ::ur_proj *po, int op, float tau, RotFwd *F, RotTerm *T) {
+  const bool sr = po->method == UR_SUPERRES;
+  const int32_t *src = sr ? po->dim_yx : po->dim_x;
+  RotFwd f;
+  memset(&f, 0, sizeof(f));
+  f.axis = -1;
+  float w = 1.f;
+  for (int a = 0; a < 3; ++a) {
+    f.s[a] = po->dim_y[a];
+    f.nyx[a] = src[a];
+    f.nlr[a] = po->dim_x[a];
+    if (sr && !dirac_axis(po, a)) {
+      if (f.axis >= 0) return false;  // several decimated axes: general path
+      f.axis = a;
+    } else if (sr) {
+      w *= po->ker[a][0];
+      if (po->dim_yx[a] != po->dim_x[a]) return false;
+    }
+  }
+  for (int k = 0; k < 12; ++k) f.m[k] = po->mat[k];
+  if (f.axis >= 0) {
+    const int a = f.axis;
+    int k0 = 0, k1 = po->ksize[a];
+    while (k1 - k0 > 1 && po->ker[a][k0] == 0.f) ++k0;
+    while (k1 - k0 > 1 && po->ker[a][k1 - 1] == 0.f) --k1;
+    f.K = k1 - k0;
+    f.k0 = k0;
+    f.r = po->ratio[a];
+    for (int t = 0; t < f.K; ++t) f.ker[t] = po->ker[a][k0 + t];
+  } else {  // no profile: a 1-tap kernel along z
+    f.axis = 2;
+    f.K = 1;
+    f.k0 = 0;
+    f.r = 1;
+    f.ker[0] = 1.f;
+  }
+  f.nj = f.nlr[f.axis];
+  f.scl_axis = -1;
+  f.s_even = f.s_odd = 1.f;
+  if (sr && po->scl != 0.f) {
+    f.scl_axis = po->dim_thick;
+    const float e = op == UR_OP_ATA ? 2.f * po->scl : po->scl;
+    f.s_even = expf(e);
+    f.s_odd = expf(-e);
+  }
+  // A: in-plane 1-tap factors once; At: once; AtA: twice (and tau)
+  f.weight = op == UR_OP_ATA ? tau * (w * w) : (op == UR_OP_AT ? tau * w : w);
+  if (F) *F = f;
+  if (T) {
+    RotTerm t;
+    memset(&t, 0, sizeof(t));
+    const float *mat = po->mat;
+    const double a[3][3] = {{mat[0], mat[1], mat[2]}, {mat[4], mat[5], mat[6]},
+                            {mat[8], mat[9], mat[10]}};
+    const double tr[3] = {mat[3], mat[7], mat[11]};
+    const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) -
+                       a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                       a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (!(fabs(det) > 1e-9)) return false;
+    double iv[3][3];
+    iv[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det;
+    iv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+    iv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det;
+    iv[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+    iv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det;
+    iv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+    iv[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det;
+    iv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+    iv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+    double cand = 1.0;
+    for (int r = 0; r < 3; ++r) {
+      double hh = 0.0, off = 0.0;
+      for (int c = 0; c < 3; ++c) {
+        t.inv[4 * r + c] = (float)iv[r][c];
+        hh += fabs(iv[r][c]);
+        off -= iv[r][c] * tr[c];
+      }
+      t.inv[4 * r + 3] = (float)off;
+      t.h[r] = (float)(hh * 1.0005 + 1e-2);  // float32 slack on coordinates up to ~1e3
+      cand *= 2.0 * t.h[r] + 1.0;
+      t.n[r] = f.nyx[r];
+    }
+    if (cand > 4096.0) return false;
+    for (int k = 0; k < 12; ++k) t.m[k] = mat[k];
+    t.rz = fabsf(mat[10]) >= 0.5f ? 1.f / mat[10] : 0.f;
+    *T = t;
+  }
+  return true;
+}
+
+static void rot_tile(const RotFwd &F, bool ata, RotTile *T) {
+  // owned block: 64 voxels along z (coalesced), a few rows, >= 32 along a non-z profile axis
+  int e[3] = {2, 2, 64};
+  if (F.axis == 2) {
+    e[0] = 4;
+    e[1] = 8;
+    e[2] = ata ? 64 : (64 / F.r > 8 ? 64 / F.r : 8);
+  } else {
+    e[F.axis] = ata ? 32 : (32 / F.r > 2 ? 32 / F.r : 2);
+    e[1 - F.axis] = 2;
+  }
+  for (int a = 0; a < 3; ++a) {
+    T->e[a] = e[a];
+    T->pe[a] = e[a];
+  }
+  int njm;
+  if (ata) {
+    njm = (e[F.axis] + F.K - 2) / F.r + 2;  // rows touching a block of e voxels, any alignment
+  } else {
+    njm = e[F.axis];
+  }
+  T->nj_max = njm;
+  T->pe[F.axis] = (njm - 1) * F.r + F.K;
+  if (F.axis == 2) T->pe[2] |= 1;  // odd z pitch: conflict-free strided reads of phase 2
+}
+
+int rot_forward_launch(int op, const RotFwd &F, const float *v, float *out, cudaStream_t st) {
+  const bool ata = op == UR_OP_ATA;
+  RotTile T;
+  rot_tile(F, ata, &T);
+  const int *on = ata ? F.nyx : F.nlr;
+  dim3 grid(div_up(on[2], T.e[2]), div_up(on[1], T.e[1]), div_up(on[0], T.e[0]));
+  const size_t tile = (size_t)T.pe[0] * T.pe[1] * T.pe[2];
+  const size_t smem = (ata ? 2 * tile : tile) * sizeof(float);
+  UR_REQUIRE(smem <= 96 * 1024, "rot_forward: tile does not fit shared memory (K=%d r=%d)", F.K,
+             F.r);
+  if (ata) {
+    if (smem > 48 * 1024)
+      UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)rot_forward_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    rot_forward_kernel<true><<<grid, kRotThreads, smem, st>>>(v, out, F, T);
+  } else {
+    if (smem > 48 * 1024)
+      UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)rot_forward_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    rot_forward_kernel<false><<<grid, kRotThreads, smem, st>>>(v, out, F, T);
+  }
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+int rot_expand_launch(const RotFwd &F, const float *x, float *u, cudaStream_t st) {
+  dim3 block(64, 4, 1), grid(div_up(F.nyx[2], 64), div_up(F.nyx[1], 4), F.nyx[0]);
+  rot_expand_kernel<<<grid, block, 0, st>>>(x, u, F);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+int rot_adjoint_launch(const RotTerm &T, const int dim_y[3], float *out, int accumulate,
+                       cudaStream_t st) {
+  dim3 block(64, 4, 1), grid(div_up(dim_y[2], 64), div_up(dim_y[1], 4), dim_y[0]);
+  rot_adjoint_kernel<<<grid, block, 0, st>>>(T, out, dim_y[0], dim_y[1], dim_y[2], accumulate);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+}  // namespace ur

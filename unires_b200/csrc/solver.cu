@@ -28,6 +28,9 @@ int lhs_stream_launch(int mode, const LhsArgs &a, int variant, cudaStream_t st);
 int lhs_fast_launch(int mode, const LhsArgs &a, bool dry_run, cudaStream_t st);  // lhs_fast.cu
 
 static int g_lhs_variant = 0;  // ur_tune("lhs_variant")
+extern int g_rot_fused;        // rot.cu; ur_tune("rot_fused"): 0 = rotated operators through the general path
+
+static size_t align_up_sz(size_t v) { return (v + 255) / 256 * 256; }
 
 __device__ __forceinline__ float eval_term(const LatticeTerm &T, const float *__restrict__ v,
                                            const int (&i)[3], size_t lin, const int (&n)[3],
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(256) lhs_direct_kernel(const LhsArgs a) {
       const size_t st[3] = {sx, sy, 1};
       for (int k = 0; k < a.nterm; ++k) data += eval_term(s_term[k], v, idx, i, n, st);
     }
+    for (int k = 0; k < a.nrot; ++k) data += rot_gather(a.rot[k], x, y, z, a.nx, a.ny, a.nz);
     const float val = data + a.rl2 * dtd;
     if (MODE == LHS_PLAIN) {
       a.out[i] = val;
@@ -348,6 +352,8 @@ struct LhsPlan {
   size_t proj_ws;           // max general-path workspace
   int n_chain;              // > 0: the (single) observation is a chain of single-axis terms
   LatticeTerm chain[3];
+  RotFwd rot_fwd[kMaxRot];  // forward kernels of the rotated observations (args.rot[k])
+  size_t rot_bytes[kMaxRot];
   dim3 grid, block;
 };
 
@@ -557,6 +563,13 @@ static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
       UR_REQUIRE(po->dim_y[a] == lhs->dim_y[a], "ur_lhs: observation %d dim_y mismatch", n);
     if (A.nterm < kMaxFused && lattice_term(po, lhs->tau[n], &A.term[A.nterm])) {
       ++A.nterm;
+    } else if (g_rot_fused && !ur_proj_is_lattice(po) && A.nrot < kMaxRot &&
+               rot_describe(po, UR_OP_ATA, lhs->tau[n], &P->rot_fwd[A.nrot], &A.rot[A.nrot])) {
+      // rotated operator: forward kernel into a dim_yx scratch volume, adjoint gathered in the
+      // direct lhs kernel together with D'D and the CG epilogue
+      const RotFwd &F = P->rot_fwd[A.nrot];
+      P->rot_bytes[A.nrot] = align_up_sz((size_t)F.nyx[0] * F.nyx[1] * F.nyx[2] * sizeof(float));
+      ++A.nrot;
     } else if (lhs->n_obs == 1 && g_lhs_variant == 0 &&
                lattice_chain(po, lhs->tau[n], P->chain, &P->n_chain)) {
       // evaluated by chained lean passes in launch_lhs (checked there; general path otherwise)
@@ -602,6 +615,7 @@ static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
   // accumulator volume: general-path observations and / or all but one lattice term
   if (P.n_general || P.args.nterm > 1) s += vol_bytes(lhs) + align_up(P.proj_ws);
   if (P.n_chain) s += vol_bytes(lhs);  // second buffer of the chained passes
+  for (int k = 0; k < P.args.nrot; ++k) s += P.rot_bytes[k];
   return s;
 }
 
@@ -612,6 +626,7 @@ struct LhsWs {
   float *acc2;
   void *proj;
   size_t proj_bytes;
+  float *rot_u[kMaxRot];
 };
 
 static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
@@ -632,7 +647,15 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
     c += w.proj_bytes;
   }
   w.acc2 = nullptr;
-  if (P.n_chain) w.acc2 = (float *)c;
+  if (P.n_chain) {
+    w.acc2 = (float *)c;
+    c += vol_bytes(lhs);
+  }
+  for (int k = 0; k < kMaxRot; ++k) w.rot_u[k] = nullptr;
+  for (int k = 0; k < P.args.nrot; ++k) {
+    w.rot_u[k] = (float *)c;
+    c += P.rot_bytes[k];
+  }
   return w;
 }
 
@@ -757,6 +780,12 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
   }
   A.gr = GridReduce{w.partials, w.counter};
+  for (int k = 0; k < A.nrot; ++k) {  // u_k = tau C' S^2 C P v on the intermediate grid
+    int rc = rot_forward_launch(UR_OP_ATA, P.rot_fwd[k], A.v, w.rot_u[k], st);
+    if (rc) return rc;
+    A.rot[k].u = w.rot_u[k];
+  }
+  if (A.nrot > 0) variant = 1;  // the adjoint gather lives in the direct kernel
   if (A.nterm > 1 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc != nullptr &&
       lean_supports(mode, A, st)) {
     // several lattice observations: term-only passes into the accumulator, then the last term
@@ -873,6 +902,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_lhs_variant = value;
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
+  } else if (!strcmp(name, "rot_fused")) {
+    g_rot_fused = value != 0;
   } else if (!strcmp(name, "cg_fuse")) {
     g_cg_fuse = value != 0;
   } else if (!strcmp(name, "stream_pf")) {
@@ -1042,7 +1073,8 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
   bool padded = false;
   const int nz = lhs->dim_y[2], pitch = pitch4(lhs);
   const size_t rows = (size_t)lhs->dim_y[0] * lhs->dim_y[1];
-  if (nz % 4 != 0 && nz >= 4 && P.n_general == 0 && g_lhs_variant == 0 && opts->variant == 0) {
+  if (nz % 4 != 0 && nz >= 4 && P.n_general == 0 && P.args.nrot == 0 && g_lhs_variant == 0 &&
+      opts->variant == 0) {
     LhsArgs T = P.args;
     T.pitch = pitch;
     T.v = cw.x_pad;
@@ -1100,7 +1132,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
   // a final x += alpha p after the loop (which also runs after a device-side early stop).
   bool fuse = false;
   if (stop != UR_STOP_ENERGY && g_cg_fuse && opts->variant != 1 && g_lhs_variant != 1 && vec &&
-      aligned16(cw.p2) && P.n_general == 0) {
+      aligned16(cw.p2) && P.n_general == 0 && P.args.nrot == 0) {
     LhsArgs A = P.args;
     A.v = cw.p;
     A.out = cw.Ap;
@@ -1118,7 +1150,7 @@ extern "C" int ur_cg_solve(const ur_lhs *lhs, const float *d_b, float *d_x, void
   // p and x each ping-pong between two buffers (neighbouring CTAs still read the old halos).
   bool efuse = false;
   if (stop == UR_STOP_ENERGY && g_cg_fuse && opts->variant == 0 && g_lhs_variant == 0 && vec &&
-      aligned16(cw.p2) && aligned16(cw.x2) && P.n_general == 0) {
+      aligned16(cw.p2) && aligned16(cw.x2) && P.n_general == 0 && P.args.nrot == 0) {
     LhsArgs A = P.args;
     A.v = cw.p;
     A.out = cw.Ap;

@@ -1,6 +1,7 @@
 // Device-side CG bookkeeping shared by the solver kernels.
 #pragma once
 #include "common.cuh"
+#include "rot.cuh"
 
 namespace ur {
 
@@ -59,6 +60,7 @@ __device__ __forceinline__ void record_objective(CgState *st, int n, double o, d
 // lhs kernel arguments (shared by the direct and the streaming kernels)
 // ---------------------------------------------------------------------------
 constexpr int kMaxFused = 4;
+constexpr int kMaxRot = 2;  // rotated observations gathered inside the direct lhs kernel
 
 // One "lattice" observation (identity rotation, integer shift): along `axis`
 //   x[j] = s_j * sum_t ker[t] * v[j*r + t + off],  0 <= j < nj   (v = 0 outside the grid)
@@ -102,6 +104,8 @@ struct LhsArgs {
   const float *acc;
   int nterm;
   LatticeTerm term[kMaxFused];
+  int nrot;  // rotated observations: P' u gathered in-kernel, u from rot_forward_kernel (rot.cuh)
+  RotTerm rot[kMaxRot];
   const float *v;
   float *out;      // PLAIN: A v
   const float *b;  // RESID / ENERGY
