@@ -12,7 +12,11 @@ super-resolution, 256^3 recon grid" (synthetic BrainWeb-like phantom, 181x217x18
 each channel thick-sliced x4 along a different axis).  N>1: one independent subject per GPU
 (weak scaling, no data-path collective).  value = CG iterations of all ranks / max-over-ranks
 device time.  `e2e` is the same step through the public Python API with HOST (pinned) buffers:
-observations and initial estimate uploaded, reconstructed channels downloaded, every step.
+observations uploaded, the initial estimate formed from them on the device, reconstructed
+channels downloaded, every step.  `sharded` (every N): BASELINE.json configs[3], 8 channels of
+384^3 sharded over the ranks -- one full ADMM iteration through `_update_admm_sharded` with its
+NCCL all-reduces (strong scaling).  `energy_rule`: the same y-update in the reference's default
+mode (stop='max_gain' = energy objective, tolerance 1e-3).
 """
 import argparse
 import json
@@ -44,6 +48,9 @@ def parse():
     ap.add_argument('--cpu-sample-iters', type=int, default=10)
     ap.add_argument('--channel-streams', type=int, default=None)
     ap.add_argument('--tune', action='append', default=[], help='knob=value (ur_tune)')
+    ap.add_argument('--no-sharded', action='store_true',
+                    help='skip the channel-sharded ADMM section (configs[3])')
+    ap.add_argument('--sharded-workload', default='thickz2_384x8')
     return ap.parse_args()
 
 
@@ -58,6 +65,7 @@ def peaks():
 WORKLOADS = {
     'sr3_256': 'thick-slice super-resolution',
     'sr3_48': 'thick-slice super-resolution',
+    'sr3_256_rigid': 'thick-slice super-resolution, rigidly mis-aligned scans (rotated operators)',
     'crop3_256': '1 mm observations on a larger 1 mm grid (crop / embed operator)',
     'thickz2_256': 'thick-slice super-resolution (z x2)',
     'thickz2_384': 'thick-slice super-resolution (z x2)',
@@ -73,7 +81,9 @@ def describe(workload):
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed `ncu --set full` capture of this workload (profiles/traffic.json), else None."""
+    COMMITTED `ncu --set full` capture of this workload (profiles/traffic.json), else None.  It
+    is not measured in this run (ncu replays kernels; nothing under a profiler is a bench value):
+    the JSON line says so in roofline.traffic_source."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             return float(json.load(f)[workload]['dram_bytes_per_launch'])
@@ -122,6 +132,61 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(s)}
 
 
+# ----------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned
+    host buffers are allocated (first touch places them there).  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(':')[0]) == 8:
+            bdf = bdf[4:]
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {'numa_node': None, 'bound': False}
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {'numa_node': node, 'bound': bool(allowed), 'cpus': len(allowed)}
+    except Exception as e:  # placement is best effort
+        return {'numa_node': None, 'bound': False, 'why': repr(e)[:80]}
+
+
+def copy_ceiling(dev, h2d_bytes, d2h_bytes, steps, barrier):
+    """its/s a step could reach if the host<->device copies of e2e were the ONLY cost: the same
+    bytes per step, pinned buffers, H2D and D2H on two streams, all ranks at once."""
+    src = torch.empty(max(h2d_bytes, 4) // 4, dtype=torch.float32).pin_memory()
+    dst = torch.empty(max(d2h_bytes, 4) // 4, dtype=torch.float32).pin_memory()
+    a = torch.empty_like(src, device=dev)
+    b = torch.empty_like(dst, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    def once():
+        with torch.cuda.stream(s_up):
+            a.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            dst.copy_(b, non_blocking=True)
+    once()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        once()
+    torch.cuda.current_stream().wait_stream(s_up)
+    torch.cuda.current_stream().wait_stream(s_dn)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
 # ----------------------------------------------------------------------------- workload
 def build_scenario(workload, device):
     from unires_b200 import synth, _project, struct
@@ -133,6 +198,76 @@ def y_update(x, y, z, w, rho, tmp, sett, vx, dim):
     """The y-update of one subject through the product's public functions."""
     from unires_b200 import _update
     return _update._solve_y(x, y, z, w, rho, tmp, sett, dim, vx)
+
+
+def sharded_admm(args, dev, world, rank, barrier):
+    """BASELINE.json configs[3]: 8 channels of 384^3 (z x2 thick slices), channels sharded
+    round-robin over the ranks.  Step = ONE full ADMM iteration through the product's
+    `_update_admm_sharded` (unires/_update.py:105-195): per-channel right-hand side + CG (20 fixed
+    iterations), objective, JTV prox -- with its collectives: SUM all-reduce of the (X,Y,Z) JTV
+    coupling field and of the prior-energy field (226 MB float32 each) + one float64 scalar.
+    Strong scaling: the same 8-channel problem on 1, 2, 4 or 8 GPUs."""
+    import torch.distributed as dist
+    from unires_b200 import synth, _project, struct, _update, parallel
+    cfg = synth.CONFIGS[args.sharded_workload]
+    C = len(cfg['thick'])
+    if world > C:
+        return {'skipped': '%d ranks for %d channels' % (world, C)}
+    mine = parallel.channel_shard(C, world, rank)
+    sc = synth.make_scenario(cfg, _project, struct, device=dev, seed=0, channels=mine,
+                             phantom_device=dev)
+    sett = sc.sett
+    sett.cgs_max_iter, sett.cgs_tol = args.cg_iters, 0.0
+    rho = sc.rho.clone()
+    if world > 1:
+        dist.broadcast(rho, 0)
+    dim = tuple(sc.y[0].dim)
+    n_vox = dim[0] * dim[1] * dim[2]
+    z, w = _update._admm_aux(sc.y, sett)
+    tmp = torch.zeros(dim, device=dev)
+    n_steps = max(2, min(args.steps, 3))
+    obj = torch.zeros(n_steps + 2, 3, dtype=torch.float64, device=dev)
+    for it in range(2):  # warm-up (also moves z, w away from zero)
+        _update._update_admm_sharded(sc.x, sc.y, z, w, rho, tmp, obj, it, sett)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(n_steps):
+        _update._update_admm_sharded(sc.x, sc.y, z, w, rho, tmp, obj, 2 + it, sett)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / n_steps
+    ar_ms = 0.0
+    if world > 1:  # one all-reduce of the coupling field, in isolation
+        field = torch.zeros(dim, device=dev)
+        dist.all_reduce(field)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(field)
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / 5
+    t = torch.tensor([ms, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = t.tolist()
+    finite = bool(torch.isfinite(obj[2:2 + n_steps]).all().item())
+    return {'workload': '%s: %d-channel %s, recon grid %s, channels sharded round-robin over '
+                        '%d rank(s); step = one full ADMM iteration (y-update with %d fixed CG '
+                        'iterations per channel, objective, JTV prox) through _update_admm_sharded'
+                        % (args.sharded_workload, C, describe(args.sharded_workload),
+                           'x'.join(map(str, dim)), world, args.cg_iters),
+            'scaling': 'strong', 'n_gpus': world, 'channels': C, 'channels_per_rank': len(mine),
+            'ms_per_admm_iteration': ms, 'steps': n_steps,
+            'value': C * args.cg_iters / (ms * 1e-3), 'unit': UNIT,
+            'collectives_per_iteration': 0 if world == 1 else
+            '2 x all-reduce(SUM) of %.0f MB float32 + 1 float64 scalar (NCCL)' % (n_vox * 4 / 1e6),
+            'allreduce_ms': ar_ms,
+            'allreduce_busbw_gbs': (2 * (world - 1) / world * n_vox * 4 / (ar_ms * 1e-3) / 1e9)
+            if ar_ms > 0 else None,
+            'objective_finite': finite}
 
 
 def run_ours(args):
@@ -210,15 +345,30 @@ def run_ours(args):
     sett.channel_streams = streams_cfg
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step ----
+    # Per step: the observations of a subject are uploaded from pinned host memory, the initial
+    # estimate is formed FROM THEM on the device (back-projection normalised by the operator's
+    # column sums, what synth.make_scenario does on the host; round 1 uploaded it: 201 MB more
+    # per step), every channel is solved and the reconstruction is downloaded.
+    numa = bind_to_gpu_numa_node(local)
     hx = [[o.dat.cpu().pin_memory() for o in xc] for xc in sc.x]
-    hy0 = [t.cpu().pin_memory() for t in y0]
-    hy = [torch.empty_like(t).pin_memory() for t in hy0]
-    h2d = sum(t.numel() * 4 for xc in hx for t in xc) + sum(t.numel() * 4 for t in hy0)
+    hy = [torch.empty(dim, dtype=torch.float32).pin_memory() for _ in range(C)]
+    h2d = sum(t.numel() * 4 for xc in hx for t in xc)
     d2h = sum(t.numel() * 4 for t in hy)
+    from unires_b200 import _project
+    den = None
+    if sett.do_proj:  # A' 1: a property of the operator, computed once
+        den = [_project._proj_apply('At', torch.ones_like(sc.x[c][0].dat)[None, None],
+                                    sc.x[c][0].po, method=sett.method)[0, 0].clamp_min(1e-3)
+               for c in range(C)]
 
-    # public host-buffer entry point: a double-buffered pipeline over a stream of subjects
-    # (uploads of subject k+1 and the download of subject k-1 overlap the solves of subject k;
-    # every byte of every step still crosses PCIe inside the timed region)
+    def init_y(x, y, c):
+        if den is None:
+            y[c].dat.copy_(x[c][0].dat)
+        else:
+            num = _project._proj_apply('At', x[c][0].dat[None, None], x[c][0].po,
+                                       method=sett.method)[0, 0]
+            torch.div(num, den[c], out=y[c].dat)
+
     def clone_set(x, y):  # same operators (read-only), own observation / estimate volumes
         import copy
         xb = []
@@ -237,15 +387,16 @@ def run_ours(args):
         return xb, yb
 
     set_b = clone_set(sc.x, sc.y)
-    pipe = _update.HostPipeline([(sc.x, sc.y), set_b], z, w, rho, sett)
+    pipe = _update.HostPipeline([(sc.x, sc.y), set_b], z, w, rho, sett, init_y=init_y)
 
     def e2e_step():
-        pipe.submit(hx, hy0, hy)
+        pipe.submit(hx, None, hy)
 
     for _ in range(2):
         e2e_step()
     pipe.drain()
     barrier()
+    l_e0 = _lib.lib.ur_launch_count()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
@@ -254,12 +405,43 @@ def run_ours(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    e2e_launches = _lib.lib.ur_launch_count() - l_e0
     e2e_ok = all(torch.isfinite(t).all().item() for t in hy)
+    ms_copy = copy_ceiling(dev, h2d, d2h, args.steps, barrier)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- the reference's default mode: energy stop rule, tolerance 1e-3 (device-side stop) ----
+    sett.cgs_tol = 1e-3
+    for _ in range(2):
+        reset()
+        y_update(sc.x, sc.y, z, w, rho, tmp, sett, vx, dim)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    infos = []
+    for _ in range(args.steps):
+        reset()
+        infos.append(y_update(sc.x, sc.y, z, w, rho, tmp, sett, vx, dim))
+    g1.record()
+    barrier()
+    ms_energy = g0.elapsed_time(g1)
+    its_energy = sum(i.n_iter for step in infos for i in step)
+    sett.cgs_tol = 0.0
+
+    sharded = None
+    if not args.no_sharded:
+        try:
+            sharded = sharded_admm(args, dev, world, rank, barrier)
+        except Exception as e:  # never take the headline down
+            sharded = {'error': repr(e)[:200]}
+
+    t = torch.tensor([ms, ms_e2e, ms_copy, ms_energy], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_copy, ms_energy = t.tolist()
+    t2 = torch.tensor([float(its_energy)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2)
+    its_energy_all = t2.item()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -287,7 +469,22 @@ def run_ours(args):
         'e2e': {'value': total_its / (ms_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'pipeline': 'HostPipeline: 2 device buffer sets, subject k+1 uploads / k-1 '
-                            'downloads while k solves', 'result_finite': bool(e2e_ok)},
+                            'downloads while k solves; observations uploaded, initial estimate '
+                            'formed from them on the device, reconstruction downloaded',
+                'result_finite': bool(e2e_ok), 'gpu_launches': int(e2e_launches),
+                'host_placement': numa,
+                'copy_ceiling': {'value': world * its_per_step / (ms_copy * 1e-3), 'unit': UNIT,
+                                 'ms_per_step': ms_copy,
+                                 'what': 'the same H2D + D2H bytes per step as plain pinned copies '
+                                         'on two streams, all ranks at once, no kernels: the '
+                                         'host-side ceiling of e2e on this box'}},
+        'energy_rule': {'value': its_energy_all / (ms_energy * 1e-3), 'unit': UNIT,
+                        'ms_per_step': ms_energy / args.steps,
+                        'cg_iterations_per_step': its_energy_all / args.steps / world,
+                        'what': "the same y-update in the reference's default mode: "
+                                "stop='max_gain' (energy objective), tolerance 1e-3, at most 20 "
+                                'iterations; iterations counted from the device-side stop'},
+        'sharded': sharded,
         'gpu_launches': int(launches),
         'host_enqueue_ms_per_step': host_ms / args.steps,
         'clocks': clocks,
@@ -297,6 +494,8 @@ def run_ours(args):
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None,
                      'traffic': ncu_traffic(args.workload),
+                     'traffic_source': 'committed ncu --set full capture (profiles/traffic.json), '
+                                       'not measured in this run',
                      'timing': 'CUDA events around every matvec launch in a second pass over the '
                                'same K steps (channels serialised on one stream)',
                      'algorithmic_bytes_per_launch': mv_bpv * n_vox,
@@ -318,10 +517,8 @@ def oracle_problem(workload, channel=0):
     """Channel `channel` of the workload built ENTIRELY with the CPU oracle (no kernels)."""
     from unires_b200 import synth
     from oracle.adapters import port_ops, port_structs
-    cfg = dict(synth.CONFIGS[workload])
-    cfg['thick'] = [cfg['thick'][channel]]
-    truth = synth.phantom(tuple(cfg['dim_y']), 1, 0)
-    return synth.make_scenario(cfg, port_ops, port_structs, device='cpu', truth=truth)
+    cfg = synth.CONFIGS[workload]
+    return synth.make_scenario(cfg, port_ops, port_structs, device='cpu', channels=[channel])
 
 
 def use_all_host_cores():
@@ -336,8 +533,9 @@ def use_all_host_cores():
     return torch.get_num_threads()
 
 
-def time_oracle_cg(sc, n_iters):
-    """Seconds per CG iteration of the oracle port (channel 0, tolerance 0)."""
+def time_oracle_cg(sc, n_iters, warm=1):
+    """Seconds per CG iteration of the oracle port (first channel of `sc`, tolerance 0), after
+    `warm` untimed iterations."""
     use_all_host_cores()
     from oracle import unires_port as P
     from oracle.nitorch_shim.core import optim as OO
@@ -346,53 +544,59 @@ def time_oracle_cg(sc, n_iters):
     b = sc.x[0][0].tau * P.proj('At', sc.x[0][0].dat, sc.x[0], sc.y[0], n=0, **kw)
     lhs = lambda v: P.proj('AtA', v, sc.x[0], sc.y[0], rho=sc.rho, vx_y=vx, **kw)
     stamps = []
-    OO.cg(A=lhs, b=b, x=sc.y[0].dat.clone(), max_iter=n_iters + 1, tolerance=0, stop='max_gain',
+    OO.cg(A=lhs, b=b, x=sc.y[0].dat.clone(), max_iter=warm + n_iters, tolerance=0, stop='max_gain',
           record=lambda it, xi: stamps.append(time.perf_counter()))
-    return (stamps[-1] - stamps[0]) / n_iters
+    return (stamps[-1] - stamps[warm - 1]) / n_iters
 
 
 def cpu_baseline(sc_gpu, args):
     """Oracle port on the host cores, bounded sample: channel 0, a few CG iterations."""
     from unires_b200 import synth
     from oracle.adapters import port_ops, port_structs
-    cfg = dict(sc_gpu.cfg)
-    cfg['thick'] = [cfg['thick'][0]]
-    truth = [sc_gpu.truth[0].cpu()]
-    sc = synth.make_scenario(cfg, port_ops, port_structs, device='cpu', truth=truth)
+    sc = synth.make_scenario(sc_gpu.cfg, port_ops, port_structs, device='cpu', channels=[0],
+                             truth=[sc_gpu.truth[0].cpu()])
     sec = time_oracle_cg(sc, args.cpu_sample_iters)
     return {'value': 1.0 / sec, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
             'sample': 'oracle/unires_port.py (restated reference, pure-PyTorch primitives) on CPU: '
-                      'channel 0 of %s, %d CG iterations at full size (tolerance 0), %.1f s per '
-                      'iteration' % (args.workload, args.cpu_sample_iters, sec)}
+                      'channel 0 of %s, %d CG iterations at full size (tolerance 0) after 1 '
+                      'untimed one, %.1f s per iteration' % (args.workload, args.cpu_sample_iters,
+                                                             sec)}
 
 
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  nitorch is not
-    installable (no network, not vendored) and /root/reference does not exist on the GPU box,
-    so this times the oracle port (restated reference) on all host cores; each step is a
-    bounded sample (one full-size CG iteration of channel 0)."""
+    installable (no network, not vendored), so this times the oracle port -- the reference's
+    control flow (bitwise equal to its own files, tests/test_oracle_vs_reference.py) over the
+    restated nitorch primitives -- on all host cores, on the SAME workload: a step is a bounded
+    sample of the y-update, ONE full-size CG iteration of EVERY channel; `--warmup` untimed
+    steps, then `--steps` timed ones."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sc = oracle_problem(args.workload, 0)
-    n = max(1, args.steps)
-    sec = time_oracle_cg(sc, n)
-    val = 1.0 / sec
-    dim = tuple(sc.y[0].dim)
+    from unires_b200 import synth
+    C = len(synth.CONFIGS[args.workload]['thick'])
+    n, warm = max(1, args.steps), max(1, args.warmup)
+    sec, dim = 0.0, None
+    for c in range(C):
+        sc = oracle_problem(args.workload, c)
+        dim = tuple(sc.y[0].dim)
+        sec += time_oracle_cg(sc, n, warm=warm)  # seconds per iteration of this channel
+        del sc
+    val = C / sec  # CG iterations per second over a step of C iterations
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
-            'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': n, 'warmup': 1,
+            'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': n, 'warmup': warm,
             'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s: %s, recon grid %s, CG '
-                                   'y-update (tolerance 0); bounded sample: each step is ONE full-size '
-                                   'CG iteration of channel 0 on the host cores'
-                                   % (args.workload, describe(args.workload),
+            'config': {'workload': '%s: %d-channel %s, recon grid %s, CG y-update (tolerance 0); '
+                                   'bounded sample: each step is ONE full-size CG iteration of '
+                                   'every channel on the host cores'
+                                   % (args.workload, C, describe(args.workload),
                                       'x'.join(map(str, dim))),
-                       'channels': 1, 'recon_grid': list(dim), 'cg_iters_per_channel': 1},
+                       'channels': C, 'recon_grid': list(dim), 'cg_iters_per_channel': 1},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(),
                              'kind': 'port',
-                             'sample': '%d full-size CG iterations of channel 0 after 1 untimed '
-                                       'iteration' % n},
+                             'sample': '%d timed steps (one full-size CG iteration of each of the '
+                                       '%d channels) after %d untimed ones' % (n, C, warm)},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)

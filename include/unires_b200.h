@@ -65,11 +65,14 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
  * thread (0 automatic, 1 = 8-row tiles, 2 = 16-row tiles) and extra prefetch
  * slots of the generic streaming kernel; "fast_q" / "fast_rpt" / "fast_depth":
  * work units per CTA, rows per thread and ring prefetch depth (plane pairs)
- * of the lean kernel; "cg_fuse": fold the direction update into the matvec.
+ * of the lean kernel; "cg_fuse": fold the direction update into the matvec;
+ * "rot_fused": 0 routes rotated operators through the unfused pull / conv /
+ * conv' / push chain instead of the in-tile kernels (A/B and tests).
  * Unknown names return UR_ERR_ARG.                                          */
 int ur_tune(const char *name, int value);
 /* Which kernel served the most recent lhs launch of this process:
- * 0 direct, 1 generic TMA streaming kernel, 2 lean specialised TMA kernel.  */
+ * 0 direct, 1 generic TMA streaming kernel, 2 lean specialised TMA kernel,
+ * 3 rotated-operator kernel (forward tile kernel + quad gather adjoint).    */
 int ur_last_lhs_path(void);
 
 /* ---------------------------------------------------------------- finite

@@ -24,7 +24,8 @@ def test_reference_arm_prints_one_json_line():
     assert d['unit'] == 'CG-it/s' and d['higher_is_better'] is True and d['value'] > 0
     assert d['vs_baseline'] is None and d['dtype'] == 'f32' and d['data'] == 'synthetic'
     assert d['n_gpus'] == 1 and d['steps'] == 2
-    assert d['config']['workload'].startswith('sr3_48: thick-slice super-resolution')
+    assert d['config']['workload'].startswith('sr3_48: 3-channel thick-slice super-resolution')
+    assert d['config']['channels'] == 3 and d['warmup'] >= 1
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
     e = d['e2e']

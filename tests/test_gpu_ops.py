@@ -254,3 +254,58 @@ def test_rotated_fused_kernels_equal_general_path(cuda, name):
         _lib.check(_lib.lib.ur_tune(b'rot_fused', 1))
     for a, b in zip(res[1], res[0]):
         assert a.shape == b.shape and U.rel_l2(a, b) < 2e-6
+
+
+@pytest.mark.parametrize('dim_y,scl,shift', [((40, 36, 52), (2, 2, 2), (0, 0, 0)),
+                                             ((33, 30, 44), (2, 3, 1), (1, -2, 0)),
+                                             ((26, 41, 36), (1, 2, 4), (0, 3, -1)),
+                                             ((24, 24, 24), (3, 2, 2), (0, 0, 0))])
+def test_multi_axis_lattice_through_low_res_image(cuda, dim_y, scl, shift):
+    """Lattice operators decimated along several axes (csrc/lattice_nd.cu: nd_down + nd_up, the
+    low-resolution image is the only intermediate) against the oracle's pull / dense conv3d /
+    conv_transpose3d / push (unires/_project.py:147-179), for A, At, AtA and the CG left-hand
+    side with its dot product; also against the chained single-axis passes they replace."""
+    from oracle.adapters import port_ops
+    from unires_b200 import _lib, _project, struct
+    mat_y = torch.eye(4, dtype=torch.float64)
+    tr = torch.eye(4, dtype=torch.float64)
+    tr[:3, 3] = torch.tensor([float(s) for s in shift], dtype=torch.float64)
+    mat_x = mat_y @ tr @ torch.diag(torch.tensor([float(s) for s in scl] + [1.0], dtype=torch.float64))
+    dim_x = tuple(int((d - abs(t)) // s) - 1 for d, s, t in zip(dim_y, scl, shift))
+    po_o = port_ops._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, gap=0.0, scl=0.0)
+    po = _project._proj_info(dim_y, mat_y, dim_x, mat_x, prof_ip=2, prof_tp=0, gap=0.0,
+                             device=cuda, scl=0.0)
+    g = torch.Generator().manual_seed(3)
+    vy = torch.rand(dim_y, generator=g) + 1.0
+    vx = torch.rand(dim_x, generator=g)
+    tau, lam, rho = 0.0016, 0.01, 4.0
+    obs_o = type('O', (), {})()
+    obs_o.po, obs_o.tau = po_o, torch.tensor(tau)
+    rec_o = type('R', (), {})()
+    rec_o.dim, rec_o.lam = dim_y, torch.tensor(lam)
+    want = {op: P.proj_apply(op, v[None, None], po_o)[0, 0]
+            for op, v in (('A', vy), ('At', vx), ('AtA', vy))}
+    want['lhs'] = P.proj('AtA', vy, [obs_o], rec_o, rho=torch.tensor(rho), vx_y=torch.ones(3))
+    obs = struct._input(tau=tau, po=po)
+    rec = struct._output(dim=dim_y, lam=lam)
+    res = {}
+    try:
+        for fused in (1, 0):
+            _lib.check(_lib.lib.ur_tune(b'nd_fused', fused))
+            got = {op: _project._proj_apply(op, v.to(cuda)[None, None], po)[0, 0]
+                   for op, v in (('A', vy), ('At', vx), ('AtA', vy))}
+            lhs = _project.LhsOperator([obs], rec, rho=rho, vx_y=[1.0] * 3)
+            dot = torch.zeros(1, dtype=torch.float64, device=cuda)
+            got['lhs'] = lhs(vy.to(cuda), dot=dot)
+            res[fused] = got
+            for k in want:
+                assert U.rel_l2(got[k], want[k]) < 1e-5, (k, fused)
+            d = torch.sum(vy.double() * want['lhs'].double()).item()
+            assert abs(dot.item() - d) < 1e-5 * abs(d)
+        assert _lib.lib.ur_last_lhs_path() != 4  # fused = 0 ran last
+    finally:
+        _lib.check(_lib.lib.ur_tune(b'nd_fused', 1))
+    lhs = _project.LhsOperator([obs], rec, rho=rho, vx_y=[1.0] * 3)
+    lhs(vy.to(cuda))
+    if dim_y[2] % 4 == 0 and sum(s > 1 for s in scl) >= 2:
+        assert _lib.lib.ur_last_lhs_path() == 4

@@ -36,6 +36,7 @@ def _reset():
     for k in ('lhs_variant', 'stream_mc', 'stream_rpt', 'fast_q', 'fast_rpt'):
         _tune(k, 0)
     _tune('cg_fuse', 1)
+    _tune('nd_fused', 1)
 
 
 def _fast_eligible(factor, scl_on_thick=True):
@@ -382,7 +383,9 @@ def test_multi_view_channel_through_lean_passes(cuda, dim_y, fov):
 ])
 def test_multi_axis_decimation_through_chained_lean_passes(cuda, dim_y, zoom, fov_off):
     """Several decimated axes: A'A = prod_a (B_a' B_a) runs as chained single-axis lean passes
-    instead of the general path; against the oracle (dense 3-D conv / conv_transpose)."""
+    instead of the general path; against the oracle (dense 3-D conv / conv_transpose).  (Since
+    round 2 the default route is the low-resolution image, csrc/lattice_nd.cu -- tested in
+    test_gpu_ops.py; the chain stays as the fallback and is forced here with nd_fused=0.)"""
     from oracle.nitorch_shim.core import optim as OO
     from unires_b200 import _project, optim, struct
     mat_y = torch.eye(4, dtype=torch.float64)
@@ -408,6 +411,7 @@ def test_multi_axis_decimation_through_chained_lean_passes(cuda, dim_y, zoom, fo
     try:
         for variant in (1, 0):
             _reset()
+            _tune('nd_fused', 0)
             _tune('lhs_variant', variant)
             out = op(v.to(cuda))
             path = _last_path()

@@ -248,8 +248,11 @@ class HostPipeline:
     set is reused only after its previous download has completed (event, no host sync).
     Every byte of every subject crosses PCIe; `drain()` waits for the last result."""
 
-    def __init__(self, sets, z, w, rho, sett):
+    def __init__(self, sets, z, w, rho, sett, init_y=None):
+        """init_y(x, y, c): optional device-side initial estimate of channel c from its freshly
+        uploaded observations (then `host_y` of submit() may be None and is not uploaded)."""
         self.sets, self.z, self.w, self.rho, self.sett = sets, z, w, rho, sett
+        self.init_y = init_y
         y0 = sets[0][1]
         self.dim, self.vx = _geometry(y0)
         dev = y0[0].dat.device
@@ -273,13 +276,16 @@ class HostPipeline:
             for c in range(len(x)):
                 for n, obs in enumerate(x[c]):
                     obs.dat.copy_(host_x[c][n], non_blocking=True)
-                y[c].dat.copy_(host_y[c], non_blocking=True)
+                if host_y is not None:
+                    y[c].dat.copy_(host_y[c], non_blocking=True)
                 ready.append(self.h2d.record_event())
         infos = []
         for c in range(len(x)):
             s = streams[c % self.ns]
             s.wait_event(ready[c])
             with torch.cuda.stream(s):
+                if self.init_y is not None:
+                    self.init_y(x, y, c)
                 infos.append(_solve_channel(x[c], y[c], self.z[c], self.w[c], self.rho,
                                             _rhs_buffer(self.dim, self.dev), self.sett, self.dim,
                                             self.vx))

@@ -6,9 +6,11 @@
 // S = even/odd slice scaling.  This file is the general path (any rigid
 // transform); the lattice-aligned fused kernels live in solver.cu.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "rot.cuh"
+#include "lattice_nd.cuh"
 
 namespace ur {
 
@@ -156,6 +158,29 @@ int proj_apply_general(int op, const ur_proj *po, const float *d_in, float *d_ou
       if (rc) return rc;
       T.u = bufs[0];
       return rot_adjoint_launch(T, po->dim_y, d_out, 1, st);
+    }
+  }
+  // lattice-aligned operator decimated along several axes: through the low-resolution image
+  // (lattice_nd.cu) instead of crop / three conv passes / three conv' passes / embed
+  if (lat && g_nd_fused) {
+    NdOp nd;
+    if (nd_describe(po, scale, &nd) && nd_conv_axes(nd) >= 2) {
+      if (op == UR_OP_A) return nd_down_launch(nd, d_in, d_out, 1.f, nullptr, st);
+      LhsArgs T;
+      memset(&T, 0, sizeof(T));
+      T.nx = po->dim_y[0];
+      T.ny = po->dim_y[1];
+      T.nz = po->dim_y[2];
+      T.out = d_out;
+      T.acc = d_out;
+      const float *xl = d_in;
+      if (op == UR_OP_ATA) {
+        rc = nd_down_launch(nd, d_in, bufs[0], 1.f, nullptr, st);
+        if (rc) return rc;
+        xl = bufs[0];
+      }
+      rc = nd_up_launch(LHS_TERM, nd, xl, scale, T, st);
+      if (rc != UR_ERR_UNSUPPORTED) return rc;
     }
   }
   auto pull = [&](const float *src, float *dst) {

@@ -60,111 +60,139 @@ __device__ __forceinline__ int floordiv_i(int a, int b) {
 // ATA = false: out (dim_x)  = weight * S C P v          block owns e[] low-res voxels
 // ATA = true : out (dim_yx) = weight * C' S C P v        block owns e[] intermediate voxels
 //              (S already holds the squared factors)
+// The tile loops below run warps over the (c0, c1) rows and lanes along c2 -- no per-element
+// integer division (the first version spent more instructions on idx / n, idx % n than on the
+// trilinear pull: 258 warp instructions per intermediate voxel, ncu).
 template <bool ATA>
 __global__ void __launch_bounds__(kRotThreads)
     rot_forward_kernel(const float *__restrict__ v, float *__restrict__ out, const RotFwd F,
-                       const RotTile T) {
+                       const RotTile T, const int *done) {
   extern __shared__ float sm[];
+  if (done && *done) return;
   const int ax = F.axis;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kRotThreads / 32;
   const int b3[3] = {(int)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x};
   int o0[3];  // first owned output index per axis
 #pragma unroll
   for (int a = 0; a < 3; ++a) o0[a] = b3[a] * T.e[a];
+  const int o0a = ax == 0 ? o0[0] : (ax == 1 ? o0[1] : o0[2]);
+  const int nyxa = ax == 0 ? F.nyx[0] : (ax == 1 ? F.nyx[1] : F.nyx[2]);
+  const int ea = ax == 0 ? T.e[0] : (ax == 1 ? T.e[1] : T.e[2]);
   // low-res rows of this tile along the profile axis
   int j_min, nj_t;
   if (ATA) {
-    const int u0 = o0[ax], u1 = min(u0 + T.e[ax], F.nyx[ax]) - 1;
+    const int u0 = o0a, u1 = min(u0 + ea, nyxa) - 1;
     j_min = -floordiv_i(-(u0 - F.k0 - F.K + 1), F.r);  // ceil
     const int j_max = floordiv_i(u1 - F.k0, F.r);
     nj_t = j_max - j_min + 1;
   } else {
-    j_min = o0[ax];
-    nj_t = min(T.e[ax], F.nlr[ax] - o0[ax]);
+    j_min = o0a;
+    nj_t = min(ea, F.nj - o0a);
   }
   if (nj_t < 1) nj_t = 0;
   // pulled tile: intermediate indices [ps, ps + pn) per axis
-  int ps[3], pn[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    ps[a] = o0[a];
-    pn[a] = min(T.e[a], (ATA ? F.nyx[a] : F.nlr[a]) - o0[a]);
-  }
-  ps[ax] = j_min * F.r + F.k0;
-  pn[ax] = nj_t > 0 ? (nj_t - 1) * F.r + F.K : 0;
-  float *pulled = sm;                                     // [pn0][pn1][pn2], pitches from T.pe
-  float *lres = sm + T.pe[0] * T.pe[1] * T.pe[2];         // low-res rows, same pitches but nj_t
-  const int pp1 = T.pe[2], pp0 = T.pe[1] * T.pe[2];
-  // ---- phase 1: pull ----
+  int ps0 = o0[0], ps1 = o0[1], ps2 = o0[2];
+  int pn0 = min(T.e[0], (ATA ? F.nyx[0] : F.nlr[0]) - o0[0]);
+  int pn1 = min(T.e[1], (ATA ? F.nyx[1] : F.nlr[1]) - o0[1]);
+  int pn2 = min(T.e[2], (ATA ? F.nyx[2] : F.nlr[2]) - o0[2]);
+  const int en0 = pn0, en1 = pn1, en2 = pn2;  // owned extents (ATA: intermediate voxels)
   {
-    const int tot = pn[0] * pn[1] * pn[2];
-    for (int idx = tid; idx < tot; idx += kRotThreads) {
-      const int c2 = idx % pn[2], t = idx / pn[2];
-      const int c1 = t % pn[1], c0 = t / pn[1];
-      const int i = ps[0] + c0, j = ps[1] + c1, k = ps[2] + c2;
-      const int pa = ax == 0 ? i : (ax == 1 ? j : k);
-      float val = 0.f;
-      if (pa >= 0 && pa < F.nyx[ax]) val = rot_pull(v, F, i, j, k);
-      pulled[c0 * pp0 + c1 * pp1 + c2] = val;
+    const int s_ = j_min * F.r + F.k0, n_ = nj_t > 0 ? (nj_t - 1) * F.r + F.K : 0;
+    if (ax == 0) ps0 = s_, pn0 = n_;
+    else if (ax == 1) ps1 = s_, pn1 = n_;
+    else ps2 = s_, pn2 = n_;
+  }
+  float *pulled = sm;                                  // pitches from T.pe
+  float *lres = sm + T.pe[0] * T.pe[1] * T.pe[2];      // low-res rows, same pitches
+  const int pp1 = T.pe[2], pp0 = T.pe[1] * T.pe[2];
+  const int astep = ax == 0 ? pp0 : (ax == 1 ? pp1 : 1);
+  // ---- phase 1: pull ----
+  if (pn1 > 0) {
+    int c0 = warp / pn1, c1 = warp - c0 * pn1;
+    while (c0 < pn0) {
+      const int i = ps0 + c0, j = ps1 + c1;
+      for (int c2 = lane; c2 < pn2; c2 += 32) {
+        const int k = ps2 + c2;
+        const int pa = ax == 0 ? i : (ax == 1 ? j : k);
+        float val = 0.f;
+        if (pa >= 0 && pa < nyxa) val = rot_pull(v, F, i, j, k);
+        pulled[c0 * pp0 + c1 * pp1 + c2] = val;
+      }
+      c1 += NW;
+      while (c1 >= pn1) {
+        c1 -= pn1;
+        ++c0;
+      }
     }
   }
   __syncthreads();
   // ---- phase 2: low-res rows  x[j] = s_j sum_t ker[t] yx[j r + k0 + t] ----
-  int ln[3] = {pn[0], pn[1], pn[2]};
-  ln[ax] = nj_t;
-  const int astep = ax == 0 ? pp0 : (ax == 1 ? pp1 : 1);
   {
-    const int tot = ln[0] * ln[1] * ln[2];
-    for (int idx = tid; idx < tot; idx += kRotThreads) {
-      const int c2 = idx % ln[2], t = idx / ln[2];
-      const int c1 = t % ln[1], c0 = t / ln[1];
-      const int cc[3] = {c0, c1, c2};
-      const int jl = cc[ax];          // tile-local row
-      const int j = j_min + jl;       // global low-res row
-      int base = c0 * pp0 + c1 * pp1 + c2;
-      base += (jl * F.r - jl) * astep;  // replace the axis coordinate jl by jl * r
-      float acc = 0.f;
-      if (j >= 0 && j < F.nj) {
-        for (int tt = 0; tt < F.K; ++tt) acc = fmaf(F.ker[tt], pulled[base + tt * astep], acc);
-        if (F.scl_axis >= 0) {
-          const int g[3] = {ps[0] + c0, ps[1] + c1, ps[2] + c2};
-          const int js = F.scl_axis == ax ? j : g[F.scl_axis];
-          acc *= (js & 1) ? F.s_odd : F.s_even;
+    const int ln0 = ax == 0 ? nj_t : pn0, ln1 = ax == 1 ? nj_t : pn1, ln2 = ax == 2 ? nj_t : pn2;
+    if (ln1 > 0) {
+      int c0 = warp / ln1, c1 = warp - c0 * ln1;
+      while (c0 < ln0) {
+        for (int c2 = lane; c2 < ln2; c2 += 32) {
+          const int jl = ax == 0 ? c0 : (ax == 1 ? c1 : c2);  // tile-local row
+          const int j = j_min + jl;                            // global low-res row
+          // pulled index: the axis coordinate jl becomes jl * r
+          const int base = c0 * pp0 + c1 * pp1 + c2 + (jl * F.r - jl) * astep;
+          float acc = 0.f;
+          const bool valid = j >= 0 && j < F.nj;
+          if (valid) {
+            for (int tt = 0; tt < F.K; ++tt) acc = fmaf(F.ker[tt], pulled[base + tt * astep], acc);
+            if (F.scl_axis >= 0) {
+              const int g0 = ps0 + c0, g1 = ps1 + c1, g2 = ps2 + c2;
+              const int js = F.scl_axis == ax ? j : (F.scl_axis == 0 ? g0 : (F.scl_axis == 1 ? g1 : g2));
+              acc *= (js & 1) ? F.s_odd : F.s_even;
+            }
+          }
+          if (ATA) {
+            lres[c0 * pp0 + c1 * pp1 + c2] = acc;
+          } else if (valid) {
+            const int g0 = ax == 0 ? j : ps0 + c0, g1 = ax == 1 ? j : ps1 + c1,
+                      g2 = ax == 2 ? j : ps2 + c2;
+            out[((size_t)g0 * F.nlr[1] + g1) * F.nlr[2] + g2] = F.weight * acc;
+          }
         }
-      }
-      if (ATA) {
-        lres[c0 * pp0 + c1 * pp1 + c2] = acc;
-      } else if (j >= 0 && j < F.nj) {
-        int g[3] = {ps[0] + c0, ps[1] + c1, ps[2] + c2};
-        g[ax] = j;
-        out[((size_t)g[0] * F.nlr[1] + g[1]) * F.nlr[2] + g[2]] = F.weight * acc;
+        c1 += NW;
+        while (c1 >= ln1) {
+          c1 -= ln1;
+          ++c0;
+        }
       }
     }
   }
   if (!ATA) return;
   __syncthreads();
   // ---- phase 3: expand  u[p] = weight sum_j ker[p - k0 - j r] x[j] ----
-  {
-    int en[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) en[a] = min(T.e[a], F.nyx[a] - o0[a]);
-    const int tot = en[0] * en[1] * en[2];
-    for (int idx = tid; idx < tot; idx += kRotThreads) {
-      const int c2 = idx % en[2], t = idx / en[2];
-      const int c1 = t % en[1], c0 = t / en[1];
-      int cc[3] = {c0, c1, c2};
-      const int u = o0[ax] + cc[ax] - F.k0;  // position relative to the first tap of row 0
-      int jl_lo = -floordiv_i(-(u - F.K + 1), F.r) - j_min;  // ceil((u-K+1)/r) - j_min
-      int jl_hi = floordiv_i(u, F.r) - j_min;
-      if (jl_lo < 0) jl_lo = 0;
-      if (jl_hi > nj_t - 1) jl_hi = nj_t - 1;
-      cc[ax] = 0;
-      const int base = cc[0] * pp0 + cc[1] * pp1 + cc[2];
-      float acc = 0.f;
-      for (int jl = jl_lo; jl <= jl_hi; ++jl)
-        acc = fmaf(F.ker[u - (j_min + jl) * F.r], lres[base + jl * astep], acc);
-      out[((size_t)(o0[0] + c0) * F.nyx[1] + (o0[1] + c1)) * F.nyx[2] + (o0[2] + c2)] =
-          F.weight * acc;
+  const float inv_r = 1.f / (float)F.r;
+  if (en1 > 0) {
+    int c0 = warp / en1, c1 = warp - c0 * en1;
+    while (c0 < en0) {
+      for (int c2 = lane; c2 < en2; c2 += 32) {
+        const int ca = ax == 0 ? c0 : (ax == 1 ? c1 : c2);
+        const int u = o0a + ca - F.k0;  // position relative to the first tap of row 0
+        // floor(u / r) and ceil((u - K + 1) / r) through float (exact for |u| < 2^22; an integer
+        // division per voxel costs more than the taps)
+        const int fl_u = (int)floorf(((float)u + 0.5f) * inv_r);
+        int jl_hi = fl_u - j_min;
+        int jl_lo = (int)floorf(((float)(u - F.K + F.r) + 0.5f) * inv_r) - j_min;
+        if (jl_lo < 0) jl_lo = 0;
+        if (jl_hi > nj_t - 1) jl_hi = nj_t - 1;
+        const int base = c0 * pp0 + c1 * pp1 + c2 - ca * astep;
+        float acc = 0.f;
+        for (int jl = jl_lo; jl <= jl_hi; ++jl)
+          acc = fmaf(F.ker[u - (j_min + jl) * F.r], lres[base + jl * astep], acc);
+        out[((size_t)(o0[0] + c0) * F.nyx[1] + (o0[1] + c1)) * F.nyx[2] + (o0[2] + c2)] =
+            F.weight * acc;
+      }
+      c1 += NW;
+      while (c1 >= en1) {
+        c1 -= en1;
+        ++c0;
+      }
     }
   }
 }
@@ -208,6 +236,25 @@ __global__ void __launch_bounds__(256)
   const float val = rot_gather(T, x, y, z, nx, ny, nz);
   const size_t i = ((size_t)x * ny + y) * nz + z;
   out[i] = accumulate ? out[i] + val : val;
+}
+
+// one thread per quad of z-consecutive voxels (nz % 4 == 0, 16-byte aligned `out`)
+__global__ void __launch_bounds__(256)
+    rot_adjoint4_kernel(const RotTerm T, float *__restrict__ out, int nx, int ny, int nz,
+                        int accumulate) {
+  const int z = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (z >= nz || y >= ny) return;
+  float g[4];
+  rot_gather4(T, x, y, z, nx, ny, nz, g);
+  float4 *o = reinterpret_cast<float4 *>(out + ((size_t)x * ny + y) * nz + z);
+  float4 q = make_float4(g[0], g[1], g[2], g[3]);
+  if (accumulate) {
+    const float4 p = *o;
+    q.x += p.x, q.y += p.y, q.z += p.z, q.w += p.w;
+  }
+  *o = q;
 }
 
 static bool dirac_axis(const ::ur_proj *po, int a) {
@@ -305,12 +352,22 @@ bool rot_describe(const ::ur_proj *po, int op, float tau, RotFwd *F, RotTerm *T)
 }
 
 static void rot_tile(const RotFwd &F, bool ata, RotTile *T) {
-  // owned block: 64 voxels along z (coalesced), a few rows, >= 32 along a non-z profile axis
+  // owned block: ~64 voxels along z (two lane trips), a few rows; along a non-z profile axis
+  // 32 intermediate voxels (AtA) or their low-res rows (A)
   int e[3] = {2, 2, 64};
+  auto rows_of = [&](int ext) { return (ext + F.K - 2) / F.r + 1; };  // low-res rows touching ext
   if (F.axis == 2) {
     e[0] = 4;
     e[1] = 8;
-    e[2] = ata ? 64 : (64 / F.r > 8 ? 64 / F.r : 8);
+    if (ata) {  // the pulled row should fit two lane trips (64)
+      int ext = 64 / F.r * F.r;
+      while (ext > F.r && (rows_of(ext) - 1) * F.r + F.K > 64) ext -= F.r;
+      e[2] = ext;
+    } else {
+      int nj = 64 / F.r > 1 ? 64 / F.r : 1;
+      while (nj > 1 && (nj - 1) * F.r + F.K > 64) --nj;
+      e[2] = nj;
+    }
   } else {
     e[F.axis] = ata ? 32 : (32 / F.r > 2 ? 32 / F.r : 2);
     e[1 - F.axis] = 2;
@@ -319,18 +376,14 @@ static void rot_tile(const RotFwd &F, bool ata, RotTile *T) {
     T->e[a] = e[a];
     T->pe[a] = e[a];
   }
-  int njm;
-  if (ata) {
-    njm = (e[F.axis] + F.K - 2) / F.r + 2;  // rows touching a block of e voxels, any alignment
-  } else {
-    njm = e[F.axis];
-  }
+  const int njm = ata ? rows_of(e[F.axis]) + 1 : e[F.axis];
   T->nj_max = njm;
   T->pe[F.axis] = (njm - 1) * F.r + F.K;
   if (F.axis == 2) T->pe[2] |= 1;  // odd z pitch: conflict-free strided reads of phase 2
 }
 
-int rot_forward_launch(int op, const RotFwd &F, const float *v, float *out, cudaStream_t st) {
+int rot_forward_launch(int op, const RotFwd &F, const float *v, float *out, cudaStream_t st,
+                       const int *done) {
   const bool ata = op == UR_OP_ATA;
   RotTile T;
   rot_tile(F, ata, &T);
@@ -344,12 +397,12 @@ int rot_forward_launch(int op, const RotFwd &F, const float *v, float *out, cuda
     if (smem > 48 * 1024)
       UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)rot_forward_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    rot_forward_kernel<true><<<grid, kRotThreads, smem, st>>>(v, out, F, T);
+    rot_forward_kernel<true><<<grid, kRotThreads, smem, st>>>(v, out, F, T, done);
   } else {
     if (smem > 48 * 1024)
       UR_CUDA_CHECK(cudaFuncSetAttribute((const void *)rot_forward_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    rot_forward_kernel<false><<<grid, kRotThreads, smem, st>>>(v, out, F, T);
+    rot_forward_kernel<false><<<grid, kRotThreads, smem, st>>>(v, out, F, T, done);
   }
   UR_LAUNCH_CHECK();
   return UR_OK;
@@ -364,8 +417,13 @@ int rot_expand_launch(const RotFwd &F, const float *x, float *u, cudaStream_t st
 
 int rot_adjoint_launch(const RotTerm &T, const int dim_y[3], float *out, int accumulate,
                        cudaStream_t st) {
-  dim3 block(64, 4, 1), grid(div_up(dim_y[2], 64), div_up(dim_y[1], 4), dim_y[0]);
-  rot_adjoint_kernel<<<grid, block, 0, st>>>(T, out, dim_y[0], dim_y[1], dim_y[2], accumulate);
+  if (dim_y[2] % 4 == 0 && ((uintptr_t)out & 15u) == 0) {
+    dim3 block(32, 8, 1), grid(div_up(dim_y[2], 128), div_up(dim_y[1], 8), dim_y[0]);
+    rot_adjoint4_kernel<<<grid, block, 0, st>>>(T, out, dim_y[0], dim_y[1], dim_y[2], accumulate);
+  } else {
+    dim3 block(64, 4, 1), grid(div_up(dim_y[2], 64), div_up(dim_y[1], 4), dim_y[0]);
+    rot_adjoint_kernel<<<grid, block, 0, st>>>(T, out, dim_y[0], dim_y[1], dim_y[2], accumulate);
+  }
   UR_LAUNCH_CHECK();
   return UR_OK;
 }

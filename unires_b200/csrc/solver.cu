@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "solver.cuh"
+#include "lattice_nd.cuh"
 
 namespace ur {
 
@@ -122,6 +123,100 @@ __global__ void __launch_bounds__(256) lhs_direct_kernel(const LhsArgs a) {
       if (a.update_p) {
         const float beta = (float)a.fin.st->beta;
         a.p[i] = __fadd_rn(__fmul_rn(beta, a.p[i]), a.r[i]);
+      }
+    }
+  }
+  double total;
+  if (grid_sum(part, a.gr, s_red, &total) && tid == 0) finalize(a.fin, total);
+}
+
+// Rotated observations only (no lattice terms): one thread per QUAD of z-consecutive voxels.
+// The adjoint gather dominates (instruction-issue bound); per quad it shares the x / y weights
+// of every intermediate voxel between the z neighbours it feeds (rot_gather4), D'D comes from
+// 128-bit loads of the five neighbouring rows.  Same arithmetic and epilogues as
+// lhs_direct_kernel.  Requires nz % 4 == 0 and 16-byte aligned volumes.
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) lhs_rot_kernel(const LhsArgs a) {
+  __shared__ double s_red[kMaxWarps];
+  if (a.done && *a.done) return;
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const int z = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int xc = (a.nx + gridDim.z - 1) / gridDim.z;
+  const int x_begin = blockIdx.z * xc, x_end = min(a.nx, x_begin + xc);
+  const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  double part = 0.0;
+  for (int x = x_begin; x < x_end; ++x) {
+    if (z >= a.nz || y >= a.ny) break;
+    const size_t i = x * sx + y * sy + z;
+    const float *__restrict__ v = a.v;
+    const float4 c4 = *reinterpret_cast<const float4 *>(v + i);
+    const float4 xm4 = x > 0 ? *reinterpret_cast<const float4 *>(v + i - sx) : zero4;
+    const float4 xp4 = x + 1 < a.nx ? *reinterpret_cast<const float4 *>(v + i + sx) : zero4;
+    const float4 ym4 = y > 0 ? *reinterpret_cast<const float4 *>(v + i - sy) : zero4;
+    const float4 yp4 = y + 1 < a.ny ? *reinterpret_cast<const float4 *>(v + i + sy) : zero4;
+    const float zl = z > 0 ? __ldg(v + i - 1) : 0.f;
+    const float zr = z + 4 < a.nz ? __ldg(v + i + 4) : 0.f;
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float xm[4] = {xm4.x, xm4.y, xm4.z, xm4.w}, xp[4] = {xp4.x, xp4.y, xp4.z, xp4.w};
+    const float ym[4] = {ym4.x, ym4.y, ym4.z, ym4.w}, yp[4] = {yp4.x, yp4.y, yp4.z, yp4.w};
+    float data[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) data[k] = a.w_ident * cc[k];
+    if (a.acc) {
+      const float4 q = *reinterpret_cast<const float4 *>(a.acc + i);
+      data[0] += q.x, data[1] += q.y, data[2] += q.z, data[3] += q.w;
+    }
+    for (int n = 0; n < a.nrot; ++n) {
+      float g[4];
+      rot_gather4(a.rot[n], x, y, z, a.nx, a.ny, a.nz, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) data[k] += g[k];
+    }
+    float val[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float c = cc[k];
+      const float lft = k == 0 ? zl : cc[k > 0 ? k - 1 : 0];
+      const float rgt = k == 3 ? zr : cc[k < 3 ? k + 1 : 3];
+      const float t0 = ((x > 0 ? (c - xm[k]) * a.ivx : 0.f) - (xp[k] - c) * a.ivx) * a.ivx;
+      const float t1 = ((y > 0 ? (c - ym[k]) * a.ivy : 0.f) - (yp[k] - c) * a.ivy) * a.ivy;
+      const float t2 = ((z + k > 0 ? (c - lft) * a.ivz : 0.f) - (rgt - c) * a.ivz) * a.ivz;
+      val[k] = data[k] + a.rl2 * ((t0 + t1) + t2);
+    }
+    if (MODE == LHS_PLAIN) {
+      *reinterpret_cast<float4 *>(a.out + i) = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(cc[k], val[k]);
+    } else if (MODE == LHS_RESID) {
+      const float4 b4 = *reinterpret_cast<const float4 *>(a.b + i);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      float rr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rr[k] = __fsub_rn(bb[k], val[k]);
+        part += (double)__fmul_rn(rr[k], rr[k]);
+      }
+      const float4 r4 = make_float4(rr[0], rr[1], rr[2], rr[3]);
+      *reinterpret_cast<float4 *>(a.r + i) = r4;
+      *reinterpret_cast<float4 *>(a.p + i) = r4;
+    } else {
+      const float4 b4 = *reinterpret_cast<const float4 *>(a.b + i);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * bb[k]), cc[k]);
+      if (a.update_p) {
+        const float beta = (float)a.fin.st->beta;
+        const float4 p4 = *reinterpret_cast<const float4 *>(a.p + i);
+        const float4 r4 = *reinterpret_cast<const float4 *>(a.r + i);
+        float4 pn;
+        pn.x = __fadd_rn(__fmul_rn(beta, p4.x), r4.x);
+        pn.y = __fadd_rn(__fmul_rn(beta, p4.y), r4.y);
+        pn.z = __fadd_rn(__fmul_rn(beta, p4.z), r4.z);
+        pn.w = __fadd_rn(__fmul_rn(beta, p4.w), r4.w);
+        *reinterpret_cast<float4 *>(a.p + i) = pn;
       }
     }
   }
@@ -354,6 +449,9 @@ struct LhsPlan {
   LatticeTerm chain[3];
   RotFwd rot_fwd[kMaxRot];  // forward kernels of the rotated observations (args.rot[k])
   size_t rot_bytes[kMaxRot];
+  int nd;                   // the (single) observation runs as nd_down + nd_up (lattice_nd.cu)
+  NdOp nd_op;
+  size_t nd_bytes;          // low-resolution image A v
   dim3 grid, block;
 };
 
@@ -573,6 +671,11 @@ static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
     } else if (lhs->n_obs == 1 && g_lhs_variant == 0 &&
                lattice_chain(po, lhs->tau[n], P->chain, &P->n_chain)) {
       // evaluated by chained lean passes in launch_lhs (checked there; general path otherwise)
+      // -- or, better, through the low-resolution image: nd_down + nd_up (13 B/voxel, not 36)
+      if (g_nd_fused && nd_describe(po, lhs->tau[n], &P->nd_op) && nd_conv_axes(P->nd_op) >= 2) {
+        P->nd = 1;
+        P->nd_bytes = align_up_sz((size_t)po->dim_x[0] * po->dim_x[1] * po->dim_x[2] * sizeof(float));
+      }
       P->general[P->n_general++] = n;
       const size_t w = proj_workspace_bytes(po);
       if (w > P->proj_ws) P->proj_ws = w;
@@ -616,6 +719,7 @@ static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
   if (P.n_general || P.args.nterm > 1) s += vol_bytes(lhs) + align_up(P.proj_ws);
   if (P.n_chain) s += vol_bytes(lhs);  // second buffer of the chained passes
   for (int k = 0; k < P.args.nrot; ++k) s += P.rot_bytes[k];
+  if (P.nd) s += P.nd_bytes;
   return s;
 }
 
@@ -627,6 +731,7 @@ struct LhsWs {
   void *proj;
   size_t proj_bytes;
   float *rot_u[kMaxRot];
+  float *nd_x;
 };
 
 static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
@@ -656,6 +761,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
     w.rot_u[k] = (float *)c;
     c += P.rot_bytes[k];
   }
+  w.nd_x = P.nd ? (float *)c : nullptr;
   return w;
 }
 
@@ -726,6 +832,24 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   cudaEvent_t e0 = is_matvec ? prof_event(0) : nullptr;
   cudaEvent_t e1 = e0 ? prof_event(1) : nullptr;
   if (e0) cudaEventRecord(e0, st);
+  if (P.nd && w.nd_x && g_nd_fused && (variant == 0 ? g_lhs_variant : variant) == 0 &&
+      P.n_general == 1 && A.nterm == 0 && A.nrot == 0 &&
+      (mode == LHS_PLAIN || mode == LHS_RESID || mode == LHS_ENERGY)) {
+    // several decimated axes: the low-resolution image A v is the only intermediate in HBM
+    LhsArgs F = A;
+    F.gr = GridReduce{w.partials, w.counter};
+    int rc = nd_down_launch(P.nd_op, A.v, w.nd_x, 1.f, A.done, st);
+    if (rc == UR_OK) rc = nd_up_launch(mode, P.nd_op, w.nd_x, P.nd_op.tau, F, st);
+    if (rc != UR_ERR_UNSUPPORTED) {
+      g_last_path = 4;
+      if (e1 && rc == UR_OK) {
+        cudaEventRecord(e1, st);
+        ++g_prof.used;
+        g_prof.bytes_per_voxel += 8.0;
+      }
+      return rc;
+    }
+  }
   bool chained = false;
   if (P.n_chain > 0 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc && w.acc2 &&
       mode != LHS_COMBINE && mode != LHS_ECOMBINE) {
@@ -781,7 +905,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   }
   A.gr = GridReduce{w.partials, w.counter};
   for (int k = 0; k < A.nrot; ++k) {  // u_k = tau C' S^2 C P v on the intermediate grid
-    int rc = rot_forward_launch(UR_OP_ATA, P.rot_fwd[k], A.v, w.rot_u[k], st);
+    int rc = rot_forward_launch(UR_OP_ATA, P.rot_fwd[k], A.v, w.rot_u[k], st, A.done);
     if (rc) return rc;
     A.rot[k].u = w.rot_u[k];
   }
@@ -838,6 +962,33 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     return UR_ERR_CUDA;
   }
   g_last_path = 0;
+  if (A.nrot > 0 && A.nterm == 0 && A.nz % 4 == 0 && aligned16(A.v) && aligned16(A.out) &&
+      aligned16(A.b) && aligned16(A.r) && aligned16(A.p) && aligned16(A.acc) &&
+      (mode == LHS_PLAIN || mode == LHS_RESID || mode == LHS_ENERGY)) {
+    // quad-per-thread kernel: (32 quads = 128 z) x 8 rows per block, x ranges sized for ~24
+    // blocks per SM (the gather makes a plane expensive: small ranges balance the tail)
+    const dim3 block(32, 8, 1);
+    const unsigned gx = div_up(A.nz, 128), gy = div_up(A.ny, 8);
+    unsigned xs = ((unsigned)sm_count() * 24 + gx * gy - 1) / (gx * gy);
+    if (xs > (unsigned)A.nx) xs = (unsigned)A.nx;
+    if (xs < 1) xs = 1;
+    while ((size_t)gx * gy * xs > (size_t)sm_count() * 8 + 1024 && xs > 1) --xs;  // partials buffer
+    const dim3 grid(gx, gy, xs);
+    if (mode == LHS_PLAIN)
+      lhs_rot_kernel<LHS_PLAIN><<<grid, block, 0, st>>>(A);
+    else if (mode == LHS_RESID)
+      lhs_rot_kernel<LHS_RESID><<<grid, block, 0, st>>>(A);
+    else
+      lhs_rot_kernel<LHS_ENERGY><<<grid, block, 0, st>>>(A);
+    g_last_path = 3;
+    if (e1) {
+      cudaEventRecord(e1, st);
+      ++g_prof.used;
+      g_prof.bytes_per_voxel += 8.0;
+    }
+    UR_LAUNCH_CHECK();
+    return UR_OK;
+  }
   switch (mode) {
     case LHS_PLAIN:
       lhs_direct_kernel<LHS_PLAIN><<<P.grid, P.block, 0, st>>>(A);
@@ -902,6 +1053,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_lhs_variant = value;
   } else if (!strcmp(name, "stream_mc")) {
     stream_mc_override = value;
+  } else if (!strcmp(name, "nd_fused")) {
+    g_nd_fused = value != 0;
   } else if (!strcmp(name, "rot_fused")) {
     g_rot_fused = value != 0;
   } else if (!strcmp(name, "cg_fuse")) {

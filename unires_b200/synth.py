@@ -68,11 +68,15 @@ def scaled(cfg, dim_y, n_channels=None):
     return c
 
 
-def phantom(dim, n_channels, seed=0):
-    """List of float32 (X,Y,Z) CPU volumes: ellipsoid blobs inside a head-like
-    ellipsoid, zero background shell, intensities ~ BrainWeb (0..~1200)."""
+def phantom(dim, n_channels, seed=0, device='cpu', channels=None):
+    """List of float32 (X,Y,Z) volumes: ellipsoid blobs inside a head-like
+    ellipsoid, zero background shell, intensities ~ BrainWeb (0..~1200).
+
+    The random parameters always come from the CPU generator (same phantom everywhere);
+    `device` only says where the volumes are rasterised; `channels` selects a subset of the
+    `n_channels` channels (multi-GPU: a rank builds only the channels it owns)."""
     g = torch.Generator().manual_seed(seed)
-    ax = [torch.linspace(-1, 1, d) for d in dim]
+    ax = [torch.linspace(-1, 1, d).to(device) for d in dim]
     X, Y, Z = torch.meshgrid(*ax, indexing='ij')
     head = ((X / 0.82) ** 2 + (Y / 0.9) ** 2 + (Z / 0.8) ** 2) < 1
     n_blob = 20
@@ -81,14 +85,14 @@ def phantom(dim, n_channels, seed=0):
     amp = torch.rand(n_channels, n_blob, generator=g) * 600 + 100
     base = torch.rand(n_channels, generator=g) * 300 + 200
     vols = []
-    for c in range(n_channels):
-        v = torch.full(dim, float(base[c]))
+    for c in (range(n_channels) if channels is None else channels):
+        v = torch.full(dim, float(base[c]), device=device)
         v += 60 * (X + 0.5 * Y * Z)  # low-frequency ramp
         for k in range(n_blob):
             e = ((X - cen[k, 0]) / rad[k, 0]) ** 2 + ((Y - cen[k, 1]) / rad[k, 1]) ** 2 \
                 + ((Z - cen[k, 2]) / rad[k, 2]) ** 2
             v = torch.where(e < 1, v * 0 + float(amp[c, k]), v)
-        v = torch.where(head, v.clamp_min(1.0), torch.zeros(()))
+        v = torch.where(head, v.clamp_min(1.0), torch.zeros((), device=device))
         vols.append(v.float().contiguous())
     return vols
 
@@ -135,7 +139,7 @@ def geometry(cfg, c):
 
 
 def make_scenario(cfg, ops, structs, device='cpu', seed=0, sd=25.0, reg_scl=4.0, rigid=None,
-                  scl=0.0, truth=None, settings_kw=None):
+                  scl=0.0, truth=None, settings_kw=None, channels=None, phantom_device='cpu'):
     """Build (x, y, sett, rho, truth) for one ADMM problem.
 
     ops:     module/namespace with _proj_info(...) and _proj_apply(op, dat, po, method=...)
@@ -143,11 +147,18 @@ def make_scenario(cfg, ops, structs, device='cpu', seed=0, sd=25.0, reg_scl=4.0,
     structs: namespace with _input, _output, settings classes/factories
     rigid:   optional list of 4x4 rigid matrices per channel (correctness cases)
     The simulated observation is x_c = A_c g_c + N(0, sd^2) on the non-zero FOV,
-    tau = 1/sd^2, lam = reg_scl * sqrt(1/C) / mean(foreground)."""
+    tau = 1/sd^2, lam = reg_scl * sqrt(1/C) / mean(foreground).
+    channels: build only these channels of the C-channel problem (a rank's shard; lam still uses
+    the full C); phantom_device: where the ground truth is rasterised."""
     C = len(cfg['thick'])
+    sel = list(range(C)) if channels is None else list(channels)
     denoise = bool(cfg.get('denoise'))
     dim_y = tuple(cfg['dim_y'])
-    truth = truth if truth is not None else phantom(dim_y, C, seed)
+    if truth is None:
+        truth = phantom(dim_y, C, seed, device=phantom_device, channels=sel)
+        truth = dict(zip(sel, truth))
+    else:
+        truth = dict(zip(sel, truth)) if len(truth) == len(sel) else dict(enumerate(truth))
     if rigid is None and cfg.get('rigid') is not None:
         rigid = [rigid_matrix(t, r) for t, r in cfg['rigid']]
     g = torch.Generator().manual_seed(seed + 1)
@@ -159,7 +170,7 @@ def make_scenario(cfg, ops, structs, device='cpu', seed=0, sd=25.0, reg_scl=4.0,
     for k, v in (settings_kw or {}).items():
         setattr(sett, k, v)
     x, y = [], []
-    for c in range(C):
+    for c in sel:
         dim_x, mat_x, _, mat_y = geometry(cfg, c)
         gt = truth[c].to(device)
         obs = structs._input()
@@ -199,7 +210,8 @@ def make_scenario(cfg, ops, structs, device='cpu', seed=0, sd=25.0, reg_scl=4.0,
                                   method=sett.method)[0, 0]
             rec.dat = (num / den.clamp_min(1e-3)).float().contiguous()
         y.append(rec)
-    lam_mean = sum(float(r.lam) for r in y) / C
-    tau_mean = sum(float(o[0].tau) for o in x) / C
+    lam_mean = sum(float(r.lam) for r in y) / len(sel)
+    tau_mean = sum(float(o[0].tau) for o in x) / len(sel)
     rho = torch.tensor(math.sqrt(tau_mean) / lam_mean, dtype=torch.float32, device=device)
-    return types.SimpleNamespace(x=x, y=y, sett=sett, rho=rho, truth=truth, cfg=cfg)
+    return types.SimpleNamespace(x=x, y=y, sett=sett, rho=rho, truth=[truth[c] for c in sel],
+                                 cfg=cfg, channels=sel)
