@@ -66,6 +66,8 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
  * slots of the generic streaming kernel; "fast_q" / "fast_rpt" / "fast_depth":
  * work units per CTA, rows per thread and ring prefetch depth (plane pairs)
  * of the lean kernel; "cg_fuse": fold the direction update into the matvec;
+ * "cg_graph": 0 disables the CUDA-graph replay of repeated solves; "nd_fused": 0
+ * sends multi-axis lattice operators through chained single-axis passes;
  * "rot_fused": 0 routes rotated operators through the unfused pull / conv /
  * conv' / push chain instead of the in-tile kernels (A/B and tests).
  * Unknown names return UR_ERR_ARG.                                          */

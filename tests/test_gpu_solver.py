@@ -294,3 +294,37 @@ def test_affine_grad_vs_oracle(cuda):
     want = S.grid_grad(v[None, None], S.affine_grid(mat, shape)[None])[0, 0]
     got = spatial.affine_grad(v.to(cuda), mat, shape)
     assert U.rel_l2(got, want) < 1e-5
+
+
+@pytest.mark.parametrize('name', ['sr3_thick_xyz', 'denoise_1ch', 'sr2_rigid'])
+@pytest.mark.parametrize('stop', ['max_gain', 'residual'])
+def test_cg_graph_replay_is_bitwise_identical(cuda, name, stop):
+    """Repeated solves with the same operator and buffers (what an ADMM run does every outer
+    iteration) are captured into a CUDA graph on the second call and replayed afterwards
+    (ur_tune cg_graph): iterates, trip counts, objective traces and the launch accounting are
+    identical to the directly enqueued solve, including the device-side early stop."""
+    from unires_b200 import _lib, optim
+    _, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    b, _, lhs_g, x0 = _channel_problem(sc, 0, cuda)
+    bg = b.to(cuda)
+    res = {}
+    try:
+        for graph in (0, 1):
+            _lib.check(_lib.lib.ur_tune(b'cg_graph', graph))
+            x = x0.clone()
+            runs = []
+            for rep in range(4):
+                x.copy_(x0)
+                l0 = _lib.lib.ur_launch_count()
+                optim.cg(A=lhs_g, b=bg, x=x, max_iter=20, tolerance=1e-3, stop=stop)
+                info = optim.cg.last
+                runs.append((x.clone(), info.n_iter, list(info.obj),
+                             _lib.lib.ur_launch_count() - l0))
+            res[graph] = runs
+    finally:
+        _lib.check(_lib.lib.ur_tune(b'cg_graph', 1))
+    ref = res[0][0]
+    for graph in (0, 1):
+        for xk, n, obj, nl in res[graph]:
+            assert torch.equal(xk, ref[0]) and n == ref[1] and obj == ref[2] and nl == ref[3]

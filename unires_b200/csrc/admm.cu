@@ -8,6 +8,11 @@
 //   u_cd = w_cd / rho + g_cd
 //   s    = sqrt(sum_c sum_d u_cd^2);  f = max(s - 1/rho, 0) / (s + 1e-7)
 //   z_cd = f * u_cd;  w_cd += rho * (g_cd - z_cd)
+// w_cd / rho is evaluated as w_cd * (1 / rho) with the float32 reciprocal formed once on the
+// host (within 1 ulp of the IEEE quotient, 6e-8 relative against the 1e-4 parity bar): the nine
+// IEEE divisions per voxel were ~20 % of the instructions of a kernel that ncu shows
+// latency / issue bound at 16 warps per SM (round 2), and with a one-FMA u the vector variant
+// no longer has to keep u in registers.
 #include "common.cuh"
 
 namespace ur {
@@ -22,6 +27,7 @@ struct JtvGeom {
   float ivx, ivy, ivz;
   float rho;
   float alpha;
+  float irho;  // 1 / rho (float32)
 };
 
 __device__ __forceinline__ void scaled_grad(const float *__restrict__ y, float lam, size_t i,
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(256)
           gr[d] = __fadd_rn(__fmul_rn(g.alpha, gr[d]),
                             __fmul_rn(__fsub_rn(1.f, g.alpha), zz[((size_t)c * 3 + d) * n + i]));
         float u = gr[d];
-        if (MODE != JTV_PRIOR) u = __fadd_rn(__fdiv_rn(w[((size_t)c * 3 + d) * n + i], g.rho), u);
+        if (MODE != JTV_PRIOR) u = __fadd_rn(__fmul_rn(w[((size_t)c * 3 + d) * n + i], g.irho), u);
         if (CT > 0) {
           gkeep[c][d] = gr[d];
           ukeep[c][d] = u;
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(256)
     s2 = nrm2[i];
   }
   const float s = sqrtf(s2);
-  const float f = __fdiv_rn(fmaxf(__fsub_rn(s, __fdiv_rn(1.f, g.rho)), 0.f), __fadd_rn(s, 1e-7f));
+  const float f = __fdiv_rn(fmaxf(__fsub_rn(s, g.irho), 0.f), __fadd_rn(s, 1e-7f));
   if (jtv) jtv[i] = f;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(256)
         gd = gr[d];
         if (g.alpha != 1.f)
           gd = __fadd_rn(__fmul_rn(g.alpha, gd), __fmul_rn(__fsub_rn(1.f, g.alpha), zz[q]));
-        u = __fadd_rn(__fdiv_rn(wv, g.rho), gd);
+        u = __fadd_rn(__fmul_rn(wv, g.irho), gd);
       }
       const float zv = __fmul_rn(f, u);
       zz[q] = zv;
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256, 2)
   if (z >= g.nz || y >= g.ny) return;
   const size_t sy = g.nz, sx = (size_t)g.ny * g.nz, n = sx * g.nx;
   const size_t i = x * sx + y * sy + z;
-  float gk[CT][3][V], wk[CT][3][V], uk[CT][3][V];
+  float gk[CT][3][V], wk[CT][3][V];
   float s2[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) s2[k] = 0.f;
@@ -202,9 +208,8 @@ __global__ void __launch_bounds__(256, 2)
             gr[d] = __fadd_rn(__fmul_rn(g.alpha, gr[d]),
                               __fmul_rn(__fsub_rn(1.f, g.alpha), zo[d][k]));
           float u = gr[d];
-          if (MODE != JTV_PRIOR) u = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), u);
+          if (MODE != JTV_PRIOR) u = __fadd_rn(__fmul_rn(wk[c][d][k], g.irho), u);
           gk[c][d][k] = gr[d];
-          uk[c][d][k] = u;
           e = d == 0 ? __fmul_rn(u, u) : __fadd_rn(e, __fmul_rn(u, u));
         }
         s2[k] = __fadd_rn(s2[k], e);
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const float s = sqrtf(s2[k]);
-    f[k] = __fdiv_rn(fmaxf(__fsub_rn(s, __fdiv_rn(1.f, g.rho)), 0.f), __fadd_rn(s, 1e-7f));
+    f[k] = __fdiv_rn(fmaxf(__fsub_rn(s, g.irho), 0.f), __fadd_rn(s, 1e-7f));
   }
   if (jtv) stv<V>(jtv + i, f);
 #pragma unroll
@@ -237,8 +242,7 @@ __global__ void __launch_bounds__(256, 2)
       float zv[V], wn[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float uu = uk[c][d][k];
-        if (MODE == JTV_APPLY) uu = __fadd_rn(__fdiv_rn(wk[c][d][k], g.rho), gk[c][d][k]);
+        const float uu = __fadd_rn(__fmul_rn(wk[c][d][k], g.irho), gk[c][d][k]);
         zv[k] = __fmul_rn(f[k], uu);
         wn[k] = __fadd_rn(wk[c][d][k], __fmul_rn(g.rho, __fsub_rn(gk[c][d][k], zv[k])));
       }
@@ -249,6 +253,8 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 
+int jtv_wide = 1;  // ur_tune("jtv_wide"): 128-bit accesses for 3-4 channels too (measured at
+                   // 3x256^3: 64-bit 359 us, 128-bit 333 us = 0.94 of the HBM roofline)
 int jtv_block_rows = 4;  // measured at 3x256^3: 8 rows 502 us, 4 rows 478 us, 2 rows 484 us
 
 static bool ptr16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
@@ -265,7 +271,8 @@ static int fill(ChannelPtrs *ch, const float *const *y, const float *lam, int C)
 }
 
 static JtvGeom geom(const int32_t dim[3], const float vx[3], float rho, float alpha) {
-  return JtvGeom{dim[0], dim[1], dim[2], 1.f / vx[0], 1.f / vx[1], 1.f / vx[2], rho, alpha};
+  return JtvGeom{dim[0], dim[1], dim[2], 1.f / vx[0], 1.f / vx[1], 1.f / vx[2], rho, alpha,
+                 1.f / rho};
 }
 
 template <int MODE>
@@ -282,7 +289,7 @@ static int launch(const float *const *y, float *z, float *w, float *nrm2, float 
   bool vec = g.nz % 4 == 0 && C <= 4 && ptr16(z) && ptr16(w) && ptr16(nrm2) && ptr16(jtv);
   for (int c = 0; c < C; ++c) vec = vec && ptr16(y[c]);
   if (vec) {
-    const bool wide = C <= 2 || MODE == JTV_PRIOR;
+    const bool wide = C <= 2 || MODE == JTV_PRIOR || jtv_wide;
     const int V = wide ? 4 : 2;
     const int by = jtv_block_rows;  // rows per block (tuning knob "jtv_rows": 8 | 4 | 2)
     dim3 vblock(32, by, 1), vgrid(div_up(g.nz, 32 * V), div_up(g.ny, by), g.nx);

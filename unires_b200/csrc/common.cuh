@@ -11,6 +11,7 @@ namespace ur {
 void set_error(const char *fmt, ...);
 int sm_count();
 void count_launch();  // bumps the process-wide kernel launch counter (ur_launch_count)
+unsigned long long launches();
 
 #define UR_CUDA_CHECK(expr)                                                         \
   do {                                                                              \

@@ -36,13 +36,6 @@ struct NdUpTile {
   int nt[3];
 };
 
-__device__ __forceinline__ int nd_floordiv(int a, int b) {
-  int q = a / b;
-  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
-  return q;
-}
-__device__ __forceinline__ int nd_ceildiv(int a, int b) { return -nd_floordiv(-a, b); }
-
 // 4-byte asynchronous global -> shared copy with zero fill (src-size 0 reads nothing): every
 // thread fires all the copies of a box back to back and waits once, instead of one exposed
 // global-load round trip per row (the first version of these kernels ran at 1.8 ms per pass)
@@ -139,89 +132,6 @@ __global__ void __launch_bounds__(kNdThreads)
         dst[l2] = scale * acc;
       }
     ND_ROWS_END(l1n)
-  }
-}
-
-// Everything a quad reads from HBM; loaded one row ahead of its use (software pipeline: the
-// row loop would otherwise expose one global round trip per row).
-struct NdQuadIn {
-  float4 c, xm, xp, ym, yp, acc, b;
-  float zl, zr;
-};
-
-template <int MODE>
-__device__ __forceinline__ void nd_quad_load(const LhsArgs &a, int x, int y, int z, NdQuadIn &q) {
-  const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
-  const size_t i = x * sx + y * sy + z;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  q.acc = a.acc ? *reinterpret_cast<const float4 *>(a.acc + i) : zero4;
-  if (MODE == LHS_TERM) return;
-  const float *__restrict__ v = a.v;
-  q.c = *reinterpret_cast<const float4 *>(v + i);
-  q.xm = x > 0 ? *reinterpret_cast<const float4 *>(v + i - sx) : zero4;
-  q.xp = x + 1 < a.nx ? *reinterpret_cast<const float4 *>(v + i + sx) : zero4;
-  q.ym = y > 0 ? *reinterpret_cast<const float4 *>(v + i - sy) : zero4;
-  q.yp = y + 1 < a.ny ? *reinterpret_cast<const float4 *>(v + i + sy) : zero4;
-  q.zl = z > 0 ? __ldg(v + i - 1) : 0.f;
-  q.zr = z + 4 < a.nz ? __ldg(v + i + 4) : 0.f;
-  if (MODE == LHS_RESID || MODE == LHS_ENERGY) q.b = *reinterpret_cast<const float4 *>(a.b + i);
-}
-
-// the 7-point stencil + CG epilogue of one quad (same arithmetic as lhs_direct_kernel)
-template <int MODE>
-__device__ __forceinline__ void nd_quad_finish(const LhsArgs &a, int x, int y, int z,
-                                               const NdQuadIn &q, float (&data)[4], double &part) {
-  const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
-  const size_t i = x * sx + y * sy + z;
-  data[0] += q.acc.x, data[1] += q.acc.y, data[2] += q.acc.z, data[3] += q.acc.w;
-  if (MODE == LHS_TERM) {
-    *reinterpret_cast<float4 *>(a.out + i) = make_float4(data[0], data[1], data[2], data[3]);
-    return;
-  }
-  const float cc[4] = {q.c.x, q.c.y, q.c.z, q.c.w};
-  const float xm[4] = {q.xm.x, q.xm.y, q.xm.z, q.xm.w}, xp[4] = {q.xp.x, q.xp.y, q.xp.z, q.xp.w};
-  const float ym[4] = {q.ym.x, q.ym.y, q.ym.z, q.ym.w}, yp[4] = {q.yp.x, q.yp.y, q.yp.z, q.yp.w};
-  float val[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float c = cc[k];
-    const float lft = k == 0 ? q.zl : cc[k > 0 ? k - 1 : 0];
-    const float rgt = k == 3 ? q.zr : cc[k < 3 ? k + 1 : 3];
-    const float t0 = ((x > 0 ? (c - xm[k]) * a.ivx : 0.f) - (xp[k] - c) * a.ivx) * a.ivx;
-    const float t1 = ((y > 0 ? (c - ym[k]) * a.ivy : 0.f) - (yp[k] - c) * a.ivy) * a.ivy;
-    const float t2 = ((z + k > 0 ? (c - lft) * a.ivz : 0.f) - (rgt - c) * a.ivz) * a.ivz;
-    val[k] = (a.w_ident * c + data[k]) + a.rl2 * ((t0 + t1) + t2);
-  }
-  if (MODE == LHS_PLAIN) {
-    *reinterpret_cast<float4 *>(a.out + i) = make_float4(val[0], val[1], val[2], val[3]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(cc[k], val[k]);
-  } else if (MODE == LHS_RESID) {
-    const float bb[4] = {q.b.x, q.b.y, q.b.z, q.b.w};
-    float rr[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      rr[k] = __fsub_rn(bb[k], val[k]);
-      part += (double)__fmul_rn(rr[k], rr[k]);
-    }
-    const float4 r4 = make_float4(rr[0], rr[1], rr[2], rr[3]);
-    *reinterpret_cast<float4 *>(a.r + i) = r4;
-    *reinterpret_cast<float4 *>(a.p + i) = r4;
-  } else {  // LHS_ENERGY
-    const float bb[4] = {q.b.x, q.b.y, q.b.z, q.b.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) part += (double)__fmul_rn(__fsub_rn(val[k], 2.f * bb[k]), cc[k]);
-    if (a.update_p) {
-      const float beta = (float)a.fin.st->beta;
-      const float4 p4 = *reinterpret_cast<const float4 *>(a.p + i);
-      const float4 r4 = *reinterpret_cast<const float4 *>(a.r + i);
-      float4 pn;
-      pn.x = __fadd_rn(__fmul_rn(beta, p4.x), r4.x);
-      pn.y = __fadd_rn(__fmul_rn(beta, p4.y), r4.y);
-      pn.z = __fadd_rn(__fmul_rn(beta, p4.z), r4.z);
-      pn.w = __fadd_rn(__fmul_rn(beta, p4.w), r4.w);
-      *reinterpret_cast<float4 *>(a.p + i) = pn;
-    }
   }
 }
 
@@ -416,6 +326,10 @@ static int nd_opt_in(const void *kernel, size_t smem) {
 
 int nd_down_launch(const NdOp &op, const float *v, float *out, float scale, const int *done,
                    cudaStream_t st) {
+  {
+    const int rc = nd_down_spec_launch(op, v, out, scale, done, st);
+    if (rc != UR_ERR_UNSUPPORTED) return rc;
+  }
   NdDownTile T;
   const int want[3] = {4, 8, 32};
   for (int a = 0; a < 3; ++a) {
@@ -451,6 +365,10 @@ int nd_up_launch(int mode, const NdOp &op, const float *xl, float scale, const L
   if (!nd_a16(A.v) || !nd_a16(A.out) || !nd_a16(A.b) || !nd_a16(A.r) || !nd_a16(A.p) ||
       !nd_a16(A.acc))
     return UR_ERR_UNSUPPORTED;
+  {
+    const int rc = nd_up_spec_launch(mode, op, xl, scale, A, st);
+    if (rc != UR_ERR_UNSUPPORTED) return rc;
+  }
   NdUpTile T;
   const int want[3] = {8, 16, 128};  // 32 quads per row: one per lane
   for (int a = 0; a < 3; ++a) {

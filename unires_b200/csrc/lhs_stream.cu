@@ -723,6 +723,41 @@ static bool get_tensor_map(const float *v, int nx, int ny, int nz, int sz, int m
   return true;
 }
 
+// 3-D tensor map over an (n0, n1, n2) float volume (n2 contiguous) with an arbitrary box
+// (b0, b1, b2): the input boxes of the multi-axis lattice kernels (lattice_nd.cu).  Needs
+// n2 % 4 == 0, b2 % 4 == 0, box extents <= 256 and a 16-byte aligned base.
+bool box_tensor_map(const float *v, int n0, int n1, int n2, int b0, int b1, int b2,
+                    CUtensorMap *out) {
+  if (n2 % 4 != 0 || b2 % 4 != 0 || b0 > 256 || b1 > 256 || b2 > 256 || b0 < 1 || b1 < 1 ||
+      b2 < 1 || ((uintptr_t)v & 15u) != 0)
+    return false;
+  // same cache as the plane maps: (sz, rows, pitch) carry the box, march_y = 2 marks the kind
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{v, n0, n1, n2, b2, 2, b1, b0};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)n0};
+  cuuint64_t gstr[2] = {(cuuint64_t)n2 * 4, (cuuint64_t)n2 * n1 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)b2, (cuuint32_t)b1, (cuuint32_t)b0};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)v, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
 bool stream_tensor_map(const float *v, int nx, int ny, int nz, int sz, int march_y, int rows,
                        CUtensorMap *out, int pitch) {
   return get_tensor_map(v, nx, ny, nz, sz, march_y, rows, out, pitch);
