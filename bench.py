@@ -79,6 +79,21 @@ def describe(workload):
     return WORKLOADS.get(workload, 'thick-slice super-resolution')
 
 
+def matvec_kernel_desc(path):
+    """What served the CG matvec (ur_last_lhs_path of the last launch)."""
+    return {
+        2: 'lhs_fast_kernel: CG matvec A p = sum tau AtA p + rho lam^2 DtD p with p = beta p + r, '
+           'x += alpha p and p.Ap fused in (first iteration of a solve: plain matvec)',
+        3: 'rotated operator: rot_forward_kernel (tile pull + slice profile + scaling + transposed '
+           'profile in shared memory) + lhs_rot_kernel (gather adjoint + DtD + p.Ap); the launch '
+           'pair is timed as one matvec; instruction-issue bound, not HBM bound (DESIGN.md 4.3)',
+        4: 'several decimated axes: nd_down_spec_kernel (v -> low-resolution image) + '
+           'nd_up_spec_kernel (expansion + DtD + p.Ap); the launch pair is timed as one matvec',
+        1: 'lhs_stream_kernel (generic TMA streaming kernel)',
+        0: 'lhs_direct_kernel (+ general-path accumulation)',
+    }.get(int(path), 'lhs kernel path %d' % int(path))
+
+
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
     COMMITTED `ncu --set full` capture of this workload (profiles/traffic.json), else None.  It
@@ -204,8 +219,8 @@ def sharded_admm(args, dev, world, rank, barrier):
     """BASELINE.json configs[3]: 8 channels of 384^3 (z x2 thick slices), channels sharded
     round-robin over the ranks.  Step = ONE full ADMM iteration through the product's
     `_update_admm_sharded` (unires/_update.py:105-195): per-channel right-hand side + CG (20 fixed
-    iterations), objective, JTV prox -- with its collectives: SUM all-reduce of the (X,Y,Z) JTV
-    coupling field and of the prior-energy field (226 MB float32 each) + one float64 scalar.
+    iterations), objective, JTV prox -- with its collectives: ONE SUM all-reduce of the prior-energy
+    field and the JTV coupling field (2 x 226 MB float32 in one buffer) + one float64 scalar.
     Strong scaling: the same 8-channel problem on 1, 2, 4 or 8 GPUs."""
     import torch.distributed as dist
     from unires_b200 import synth, _project, struct, _update, parallel
@@ -238,8 +253,8 @@ def sharded_admm(args, dev, world, rank, barrier):
     barrier()
     ms = e0.elapsed_time(e1) / n_steps
     ar_ms = 0.0
-    if world > 1:  # one all-reduce of the coupling field, in isolation
-        field = torch.zeros(dim, device=dev)
+    if world > 1:  # the iteration's (2, X, Y, Z) field all-reduce, in isolation
+        field = torch.zeros((2,) + dim, device=dev)
         dist.all_reduce(field)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,9 +278,10 @@ def sharded_admm(args, dev, world, rank, barrier):
             'ms_per_admm_iteration': ms, 'steps': n_steps,
             'value': C * args.cg_iters / (ms * 1e-3), 'unit': UNIT,
             'collectives_per_iteration': 0 if world == 1 else
-            '2 x all-reduce(SUM) of %.0f MB float32 + 1 float64 scalar (NCCL)' % (n_vox * 4 / 1e6),
+            '1 x all-reduce(SUM) of 2 x %.0f MB float32 (prior-energy field + JTV coupling field in '
+            'one buffer) + 1 float64 scalar (NCCL)' % (n_vox * 4 / 1e6),
             'allreduce_ms': ar_ms,
-            'allreduce_busbw_gbs': (2 * (world - 1) / world * n_vox * 4 / (ar_ms * 1e-3) / 1e9)
+            'allreduce_busbw_gbs': (2 * (world - 1) / world * 2 * n_vox * 4 / (ar_ms * 1e-3) / 1e9)
             if ar_ms > 0 else None,
             'objective_finite': finite}
 
@@ -341,6 +357,7 @@ def run_ours(args):
     tot, cnt, bpv = C_.c_double(0), C_.c_int32(0), C_.c_double(0)
     _lib.check(_lib.lib.ur_profile_matvec_read(C_.byref(tot), C_.byref(cnt), C_.byref(bpv)))
     _lib.lib.ur_profile_matvec(0)
+    mv_path = _lib.lib.ur_last_lhs_path()
     sett.channel_streams = streams_cfg
     clocks = sampler.result()  # sampled over the timed region and the roofline pass (same load)
 
@@ -488,9 +505,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'host_enqueue_ms_per_step': host_ms / args.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'lhs_fast_kernel: CG matvec A p = sum tau AtA p + rho lam^2 '
-                                               'DtD p with p = beta p + r, x += alpha p and p.Ap '
-                                               'fused in (first iteration of a solve: plain matvec)',
+        'roofline': {'bound': 'hbm', 'kernel': matvec_kernel_desc(mv_path),
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None,
                      'traffic': ncu_traffic(args.workload),

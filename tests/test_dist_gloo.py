@@ -73,9 +73,6 @@ def _worker(rank, world, port, out_dir):
             for yc in y:
                 f += torch.sum((yc.lam * S.im_gradient(yc.dat, vx=vx)) ** 2, dim=0)
 
-        parallel.coupled_objective(row, field, data_and_prior,
-                                   lambda f: torch.sum(torch.sqrt(f), dtype=torch.float64))
-
         def norm2(f):
             f.zero_()
             for k, yc in enumerate(y):
@@ -92,7 +89,11 @@ def _worker(rank, world, port, out_dir):
                 z[k] = fac * (w[k] / rho + g)
                 w[k] += rho * (g - z[k])
 
-        parallel.coupled_prox(field, norm2, apply)
+        # the product's sharded iteration: both fields in ONE all-reduce
+        fields = torch.zeros((2,) + tuple(sc.y[0].dim))
+        parallel.coupled_objective_and_prox(
+            row, fields, data_and_prior, norm2,
+            lambda f: torch.sum(torch.sqrt(f), dtype=torch.float64), apply)
         torch.save({'mine': mine, 'y': [yc.dat for yc in y], 'z': z, 'w': w, 'row': row, 'jtv': jtv},
                    os.path.join(out_dir, 'rank%d.pt' % rank))
     finally:

@@ -343,8 +343,9 @@ _update_admm.last_cg = None
 def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     """Channel-sharded ADMM iteration: this rank holds a subset of the channels
     (x, y, z, w are the LOCAL lists / tensors).  Communication per iteration:
-    one SUM all-reduce of the (X,Y,Z) JTV coupling field, one of the prior
-    energy field and one of the scalar data term (only if sett.tolerance > 0).
+    ONE SUM all-reduce of a (2, X, Y, Z) buffer -- the prior-energy field of the objective and
+    the JTV coupling field of the prox, formed back to back -- and one float64 scalar (the data
+    term); with sett.tolerance == 0 only the coupling field travels.
     With a single rank it reduces to `_update_admm`."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -360,7 +361,13 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
     _update_admm.last_cg = _solve_y(x, y, z, w, rho_f, tmp, sett, dim, vx)
     ys = [yc.dat for yc in y]
     lam = _lib.farr([_hs(yc.lam) for yc in y])
-    field = torch.empty(dim, dtype=torch.float32, device=tmp.device)
+    alpha = float(sett.alpha)
+    norm2 = lambda f: check(lib.ur_jtv_norm2(_ptr_array(ys), ptr(z), ptr(w), ptr(f), len(ys), lam,
+                                             i3(dim), f3(vx), rho_f, alpha, 0, stream()))
+    apply = lambda f: check(lib.ur_jtv_apply(_ptr_array(ys), ptr(z), ptr(w), ptr(f), ptr(tmp),
+                                             len(ys), lam, i3(dim), f3(vx), rho_f, alpha, stream()))
+    fields = _lib.workspace(8 * n_vox, tmp.device, 'shard_fields').view(torch.float32)[:2 * n_vox] \
+        .view((2,) + tuple(dim))
     if sett.tolerance > 0:
         row = torch.zeros(3, dtype=torch.float64, device=tmp.device)
 
@@ -368,17 +375,13 @@ def _update_admm_sharded(x, y, z, w, rho, tmp, obj, n_iter, sett, group=None):
             check(lib.ur_sqrt_sum(ptr(f), n_vox, ptr(row[2:3]), stream()))
             return row[2].clone()
 
-        parallel.coupled_objective(
-            row, field, lambda r, f: _nll_terms(x, y, sett, r, prior_field=f), sqrt_sum, group)
+        # prior-energy field and JTV coupling field in ONE all-reduce (2 N floats)
+        parallel.coupled_objective_and_prox(
+            row, fields, lambda r, f: _nll_terms(x, y, sett, r, prior_field=f), norm2, sqrt_sum,
+            apply, group)
         obj[n_iter, :] = row.to(obj.device, obj.dtype)
-    alpha = float(sett.alpha)
-    parallel.coupled_prox(
-        field,
-        lambda f: check(lib.ur_jtv_norm2(_ptr_array(ys), ptr(z), ptr(w), ptr(f), len(ys), lam,
-                                         i3(dim), f3(vx), rho_f, alpha, 0, stream())),
-        lambda f: check(lib.ur_jtv_apply(_ptr_array(ys), ptr(z), ptr(w), ptr(f), ptr(tmp), len(ys),
-                                         lam, i3(dim), f3(vx), rho_f, alpha, stream())),
-        group)
+    else:
+        parallel.coupled_prox(fields[1], norm2, apply, group)
     return y, z, w, tmp, obj
 
 

@@ -38,7 +38,7 @@ struct SpecTaps {
 // ---------------------------------------------------------------- down: v -> scale * A v
 template <int K0, int R0, int K1, int R1, int K2, int R2>
 struct DownCfg {
-  static constexpr int L0 = 4, L1 = 8, L2 = 32;                 // low-res tile
+  static constexpr int L0 = 2, L1 = 8, L2 = 32;  // low-res tile (86 KB of shared memory: 2 CTAs/SM)
   static constexpr int I0 = (L0 - 1) * R0 + K0, I1 = (L1 - 1) * R1 + K1,
                        I2 = (L2 - 1) * R2 + K2;                  // input box
   static constexpr int I2P = (I2 + 3) / 4 * 4;                   // TMA inner extent (16 B)
@@ -50,7 +50,7 @@ struct DownCfg {
 };
 
 template <int K0, int R0, int K1, int R1, int K2, int R2>
-__global__ void __launch_bounds__(kSpecThreads, 1)
+__global__ void __launch_bounds__(kSpecThreads, 2)
     nd_down_spec_kernel(const __grid_constant__ CUtensorMap map_v, float *__restrict__ out,
                         const SpecTaps taps, int off0, int off1, int off2, int nj0, int nj1,
                         int nj2, int nt0, int nt1, int nt2, float scale, const int *done) {
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kSpecThreads, 1)
 // ---------------------------------------------------------------- up
 template <int K0, int R0, int K1, int R1, int K2, int R2>
 struct UpCfg {
-  static constexpr int E0 = 8, E1 = 16, E2 = 128;                 // output tile
+  static constexpr int E0 = 8, E1 = 16, E2 = 128;  // output tile (112 KB of shared memory: 2 CTAs/SM;
+                                                   // 4 x 16 x 128 at 3 CTAs/SM measured slower)
   static constexpr int N0 = (E0 + K0 - 2) / R0 + 2, N1 = (E1 + K1 - 2) / R1 + 2,
                        N2 = (E2 + K2 - 2) / R2 + 2;                // low-res box
   static constexpr int N2P = (N2 + 3) / 4 * 4;
@@ -276,6 +277,26 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's box has landed
     __syncthreads();  // ... for every thread; the previous tile is done with u1 / u2 / buf ^ 1
     if (nxt < ntiles) issue(nxt, buf ^ 1);  // next tile's box, in flight during this tile
+    // L2 prefetch of everything the finish stage of THIS tile reads from HBM (v with its one
+    // voxel halo, acc, b): the stage prefetches registers only one row ahead, which leaves too
+    // few bytes in flight at 16 warps per SM (ncu: long-scoreboard 4.5 warps per issue slot);
+    // these fire-and-forget prefetches run under the x and y passes.
+    {
+      constexpr int PR = (C::E0 + 2) * (C::E1 + 2) * (C::E2 / 32);
+      const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
+      for (int r = tid; r < PR; r += kSpecThreads) {
+        const int seg = r % (C::E2 / 32), row = r / (C::E2 / 32);
+        const int px = o0 - 1 + row / (C::E1 + 2), py = o1 - 1 + row % (C::E1 + 2);
+        const int pz = o2 + 32 * seg;
+        if (px < 0 || px >= a.nx || py < 0 || py >= a.ny || pz >= a.nz) continue;
+        const size_t i = px * sx + py * sy + pz;
+        const bool inner = px >= o0 && px < o0 + C::E0 && py >= o1 && py < o1 + C::E1;
+        if (MODE != LHS_TERM) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.v + i));
+        if (inner && a.acc) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.acc + i));
+        if (inner && (MODE == LHS_RESID || MODE == LHS_ENERGY))
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b + i));
+      }
+    }
     const float *lr = box0 + buf * C::BOXP;  // [N0][N1][N2P], rows outside the low-res grid = 0
     // The box starts at the first row that reaches the tile, so relative to it the first output
     // of the tile has tap index K - 1 or K - 2 on box row 0: only its PARITY is a run-time
@@ -410,7 +431,8 @@ int nd_down_spec_launch(const NdOp &op, const float *v, float *out, float scale,
   const int nt0 = (op.ax[0].nj + C::L0 - 1) / C::L0, nt1 = (op.ax[1].nj + C::L1 - 1) / C::L1,
             nt2 = (op.ax[2].nj + C::L2 - 1) / C::L2;
   const long long ntiles = (long long)nt0 * nt1 * nt2;
-  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  const long long slots = 2ll * sm_count();
+  const int grid = (int)(ntiles < slots ? ntiles : slots);
   kernel<<<grid, kSpecThreads, C::SMEM, st>>>(map, out, spec_taps(op), op.ax[0].off, op.ax[1].off,
                                              op.ax[2].off, op.ax[0].nj, op.ax[1].nj, op.ax[2].nj,
                                              nt0, nt1, nt2, scale, done);

@@ -73,3 +73,23 @@ def coupled_objective(row, field, data_and_prior_local, sqrt_sum, group=None):
     row[2] = sqrt_sum(field)
     row[0] = row[1] + row[2]
     return row
+
+
+def coupled_objective_and_prox(row, fields, data_and_prior_local, norm2_local, sqrt_sum,
+                               apply_local, group=None):
+    """Objective and JTV prox of one ADMM iteration with ONE field all-reduce.
+
+    fields: (2, X, Y, Z).  fields[0] receives this rank's prior-energy field
+    (data_and_prior_local(row, fields[0]) also writes the local data term into row[1]) and
+    fields[1] its sum_c |u_c|^2 (norm2_local(fields[1])); both depend only on the freshly solved
+    y and on z, w, so they are formed back to back and summed across ranks in a single
+    all-reduce of 2 N floats (one launch / ring set-up instead of two, better bus utilisation),
+    followed by the float64 scalar.  Then sqrt_sum(fields[0]) -> row[2] and apply_local(fields[1])."""
+    data_and_prior_local(row, fields[0])
+    norm2_local(fields[1])
+    all_reduce_sum(fields, group)
+    all_reduce_sum(row[1:2], group)
+    row[2] = sqrt_sum(fields[0])
+    row[0] = row[1] + row[2]
+    apply_local(fields[1])
+    return row
