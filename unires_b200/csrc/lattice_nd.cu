@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(kNdThreads, 2)
             for (int n = 0; n < wn[k]; ++n) acc = fmaf(s_kz[wt[k] - n * rz], row[wa[k] + n], acc);
             data[k] = scale * acc;
           }
-          nd_quad_finish<MODE>(a, o0 + c0, o1 + c1, z, cur, data, part);
+          nd_quad_finish<MODE>(a, o0 + c0, o1 + c1, z,
+                               ((size_t)(o0 + c0) * a.ny + (o1 + c1)) * a.nz + z, cur, data, part);
           cur = nxt;
           c0 = n0;
           c1 = n1;

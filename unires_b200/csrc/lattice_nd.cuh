@@ -67,12 +67,27 @@ __device__ __forceinline__ void nd_quad_load(const LhsArgs &a, int x, int y, int
   if (MODE == LHS_RESID || MODE == LHS_ENERGY) q.b = *reinterpret_cast<const float4 *>(a.b + i);
 }
 
+// The operands of a quad other than the x-column of v (which a marching thread keeps in
+// registers): y / z neighbours, accumulator, right-hand side.  `i` = linear index of the quad.
+template <int MODE>
+__device__ __forceinline__ void nd_quad_load_side(const LhsArgs &a, size_t i, int y, int z,
+                                                  NdQuadIn &q) {
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  q.acc = a.acc ? *reinterpret_cast<const float4 *>(a.acc + i) : zero4;
+  if (MODE == LHS_TERM) return;
+  const float *__restrict__ v = a.v;
+  const size_t sy = a.nz;
+  q.ym = y > 0 ? *reinterpret_cast<const float4 *>(v + i - sy) : zero4;
+  q.yp = y + 1 < a.ny ? *reinterpret_cast<const float4 *>(v + i + sy) : zero4;
+  q.zl = z > 0 ? __ldg(v + i - 1) : 0.f;
+  q.zr = z + 4 < a.nz ? __ldg(v + i + 4) : 0.f;
+  if (MODE == LHS_RESID || MODE == LHS_ENERGY) q.b = *reinterpret_cast<const float4 *>(a.b + i);
+}
+
 // the 7-point stencil + CG epilogue of one quad (same arithmetic as lhs_direct_kernel)
 template <int MODE>
-__device__ __forceinline__ void nd_quad_finish(const LhsArgs &a, int x, int y, int z,
+__device__ __forceinline__ void nd_quad_finish(const LhsArgs &a, int x, int y, int z, size_t i,
                                                const NdQuadIn &q, float (&data)[4], double &part) {
-  const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
-  const size_t i = x * sx + y * sy + z;
   data[0] += q.acc.x, data[1] += q.acc.y, data[2] += q.acc.z, data[3] += q.acc.w;
   if (MODE == LHS_TERM) {
     *reinterpret_cast<float4 *>(a.out + i) = make_float4(data[0], data[1], data[2], data[3]);

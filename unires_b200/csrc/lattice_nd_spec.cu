@@ -28,6 +28,19 @@ using fast::mbar_wait;
 using fast::smem_u32;
 using fast::tma_load_3d;
 
+// tile index -> (b0, b1, b2) through float reciprocals (exact for tile < 2^22, see fdiv_small in
+// solver.cu): the integer divisions of the decode were 14 % of nd_down's instructions (ncu)
+struct TileDec {
+  int nt1, nt2;
+  float inv1, inv2;
+};
+__device__ __forceinline__ void tile_decode(const TileDec &d, int tile, int &b0, int &b1, int &b2) {
+  const int tq = (int)floorf(((float)tile + 0.5f) * d.inv2);
+  b2 = tile - tq * d.nt2;
+  b0 = (int)floorf(((float)tq + 0.5f) * d.inv1);
+  b1 = tq - b0 * d.nt1;
+}
+
 constexpr int kSpecThreads = 256;
 constexpr int kSpecWarps = kSpecThreads / 32;
 
@@ -74,13 +87,14 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
   }
   __syncthreads();
   const int ntiles = nt0 * nt1 * nt2;
+  const TileDec dec{nt1, nt2, 1.f / (float)nt1, 1.f / (float)nt2};
   // the descriptor must be addressed in PARAMETER space: take its address here, not through a
   // by-reference lambda capture (which may spill a copy to local memory -> illegal instruction)
   const CUtensorMap *const pmap = &map_v;
   const uint32_t box_u32 = smem_u32(box0);
   auto issue = [=](int tile, int buf) {
-    const int b2 = tile % nt2, tq = tile / nt2;
-    const int b1 = tq % nt1, b0 = tq / nt1;
+    int b0, b1, b2;
+    tile_decode(dec, tile, b0, b1, b2);
     mbar_expect_tx(bar + 8u * buf, (uint32_t)C::BOX * 4u);
     tma_load_3d(box_u32 + (uint32_t)(buf * C::BOXP) * 4u, pmap, bar + 8u * buf,
                 b2 * C::L2 * R2 + off2, b1 * C::L1 * R1 + off1, b0 * C::L0 * R0 + off0);
@@ -134,8 +148,8 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
     __syncthreads();
     // ---- z pass -> global: lane = l2, rows (l0, l1) over the warps, 64-bit LDS ----
     {
-      const int b2 = tile % nt2, tq = tile / nt2;
-      const int b1 = tq % nt1, b0 = tq / nt1;
+      int b0, b1, b2;
+      tile_decode(dec, tile, b0, b1, b2);
       const int j2 = b2 * C::L2 + lane;
       for (int row = warp; row < C::L0 * C::L1; row += kSpecWarps) {
         const int l0 = row / C::L1, l1 = row - l0 * C::L1;
@@ -252,12 +266,13 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
     s_k2[tid] = (t >= 0 && t < K2) ? taps.k2[t] : 0.f;
   }
   const int ntiles = nt0 * nt1 * nt2;
+  const TileDec dec{nt1, nt2, 1.f / (float)nt1, 1.f / (float)nt2};
   // first low-res row whose support can reach output index o:  ceil((o - off - K + 1) / R)
   auto jb_of = [](int o, int off, int K, int R) { return nd_ceildiv(o - off - K + 1, R); };
   const size_t ly = nj2, lx = (size_t)nj1 * nj2;
   auto issue = [&](int tile, int buf) {  // every thread copies its share of the box
-    const int b2 = tile % nt2, tq = tile / nt2;
-    const int b1 = tq % nt1, b0 = tq / nt1;
+    int b0, b1, b2;
+    tile_decode(dec, tile, b0, b1, b2);
     const int g0 = jb_of(b0 * C::E0, off0, K0, R0), g1 = jb_of(b1 * C::E1, off1, K1, R1),
               g2 = jb_of(b2 * C::E2, off2, K2, R2);
     float *dst = box0 + buf * C::BOXP;
@@ -279,8 +294,8 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
   double part = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int nxt = tile + gridDim.x;
-    const int b2 = tile % nt2, tq = tile / nt2;
-    const int b1 = tq % nt1, b0 = tq / nt1;
+    int b0, b1, b2;
+    tile_decode(dec, tile, b0, b1, b2);
     const int o0 = b0 * C::E0, o1 = b1 * C::E1, o2 = b2 * C::E2;
     const int jb0 = jb_of(o0, off0, K0, R0), jb1 = jb_of(o1, off1, K1, R1),
               jb2 = jb_of(o2, off2, K2, R2);
@@ -348,32 +363,46 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
       }
     }
     __syncthreads();
-    // ---- per quad: z pass, stencil, epilogue (one row ahead on the global loads) ----
+    // ---- per quad: z pass, stencil, epilogue.  A warp owns E1 / 8 rows of the tile and MARCHES
+    // along x in each: the x-column of v stays in registers (previous / current / next plane),
+    // the other operands of the next plane are requested before this plane's arithmetic, and
+    // the linear index advances by one plane stride (no per-quad index arithmetic). ----
     {
       constexpr int NR = 4 / 2 + (K2 - 1) / 2;
       const int z = o2 + 4 * lane;
-      const bool z_in = z < a.nz;
-      int e0 = 0, e1 = warp;  // E1 = 16 rows per plane, 8 warps: two rows per plane per warp
-      NdQuadIn cur, nxtq;
-      auto row_in = [&](int r0, int r1) { return o0 + r0 < a.nx && o1 + r1 < a.ny; };
-      if (z_in && row_in(e0, e1)) nd_quad_load<MODE>(a, o0 + e0, o1 + e1, z, cur);
-      while (e0 < C::E0) {
-        int n0 = e0, n1 = e1 + kSpecWarps;
-        if (n1 >= C::E1) {
-          n1 -= C::E1;
-          ++n0;
+      const size_t sy = a.nz, sx = (size_t)a.ny * a.nz;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto ldv = [&](size_t idx) { return *reinterpret_cast<const float4 *>(a.v + idx); };
+      for (int e1 = warp; e1 < C::E1; e1 += kSpecWarps) {
+        const int y = o1 + e1;
+        if (z >= a.nz || y >= a.ny || o0 >= a.nx) continue;
+        size_t i = (size_t)o0 * sx + (size_t)y * sy + z;
+        NdQuadIn q, qn;
+        q.c = q.xm = q.xp = zero4;
+        float4 c_next2 = zero4;
+        if (MODE != LHS_TERM) {
+          q.xm = o0 > 0 ? ldv(i - sx) : zero4;
+          q.c = ldv(i);
+          q.xp = o0 + 1 < a.nx ? ldv(i + sx) : zero4;
         }
-        if (z_in && n0 < C::E0 && row_in(n0, n1)) nd_quad_load<MODE>(a, o0 + n0, o1 + n1, z, nxtq);
-        if (z_in && row_in(e0, e1)) {
+        nd_quad_load_side<MODE>(a, i, y, z, q);
+        const float2 *row = reinterpret_cast<const float2 *>(u2 + e1 * C::N2P) + lane;
+#pragma unroll 1
+        for (int e0 = 0; e0 < C::E0; ++e0, i += sx, row += C::E1 * C::N2P / 2) {
+          const int x = o0 + e0;
+          if (x >= a.nx) break;
+          const bool more = e0 + 1 < C::E0 && x + 1 < a.nx;
+          if (more) {  // operands of the next plane
+            nd_quad_load_side<MODE>(a, i + sx, y, z, qn);
+            c_next2 = (MODE != LHS_TERM && x + 2 < a.nx) ? ldv(i + 2 * sx) : zero4;
+          }
           // the quad at lane l starts 4 l outputs = 2 l low-res rows after the tile's first
-          const float2 *row =
-              reinterpret_cast<const float2 *>(u2 + (e0 * C::E1 + e1) * C::N2P) + lane;
           float v[NR + (NR & 1)], data[4];
 #pragma unroll
-          for (int i = 0; i < NR; i += 2) {
-            const float2 q = row[i / 2];
-            v[i] = q.x;
-            v[i + 1] = q.y;
+          for (int k = 0; k < NR; k += 2) {
+            const float2 t = row[k / 2];
+            v[k] = t.x;
+            v[k + 1] = t.y;
           }
           if (p2)
             expand_r2<K2, 4, 1>(taps.k2, v, data);
@@ -381,11 +410,14 @@ __global__ void __launch_bounds__(kSpecThreads, 2)
             expand_r2<K2, 4, 0>(taps.k2, v, data);
 #pragma unroll
           for (int k = 0; k < 4; ++k) data[k] *= scale;
-          nd_quad_finish<MODE>(a, o0 + e0, o1 + e1, z, cur, data, part);
+          nd_quad_finish<MODE>(a, x, y, z, i, q, data, part);
+          if (more) {
+            qn.xm = q.c;
+            qn.c = q.xp;
+            qn.xp = c_next2;
+            q = qn;
+          }
         }
-        cur = nxtq;
-        e0 = n0;
-        e1 = n1;
       }
     }
     __syncthreads();  // u1 / u2 / the box buffer may be overwritten from here on
