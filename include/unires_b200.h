@@ -74,7 +74,8 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
 int ur_tune(const char *name, int value);
 /* Which kernel served the most recent lhs launch of this process:
  * 0 direct, 1 generic TMA streaming kernel, 2 lean specialised TMA kernel,
- * 3 rotated-operator kernel (forward tile kernel + quad gather adjoint).    */
+ * 3 rotated-operator kernels (forward tile kernel + quad gather adjoint),
+ * 4 multi-axis lattice kernels (nd_down + nd_up through the low-res image). */
 int ur_last_lhs_path(void);
 
 /* ---------------------------------------------------------------- finite
@@ -185,7 +186,10 @@ int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, double *d_do
  * x, identity preconditioner, float64 dot products), run entirely on the
  * device: no host synchronisation between iterations; the stop test
  * |gain| < tolerance is evaluated on the device and later launches of the
- * same solve early-out.                                                    */
+ * same solve early-out.  A solve repeated with the same operator, options,
+ * buffers, stream and knobs (what an ADMM run does every outer iteration) is
+ * stream-captured on its second call and replayed as one CUDA graph afterwards
+ * (ur_tune("cg_graph", 0) disables this); results are bitwise identical.     */
 typedef struct ur_cg_opts {
   int32_t max_iter;  /* sett.cgs_max_iter (unires/struct.py:65), <= UR_CG_MAX_ITER */
   int32_t stop_rule; /* UR_STOP_* */

@@ -309,3 +309,50 @@ def test_multi_axis_lattice_through_low_res_image(cuda, dim_y, scl, shift):
     lhs(vy.to(cuda))
     if dim_y[2] % 4 == 0 and sum(s > 1 for s in scl) >= 2:
         assert _lib.lib.ur_last_lhs_path() == 4
+
+
+@pytest.mark.parametrize('dim_y,combo', [((20, 24, 28), 'rot+rot'), ((20, 24, 28), 'rot+lattice'),
+                                         ((19, 23, 27), 'rot+rot'), ((20, 24, 28), 'rot+rot+rot')])
+def test_lhs_several_observations_with_rotated_operators(cuda, dim_y, combo):
+    """One channel observed by several scans of which some are rigidly mis-aligned
+    (unires/_project.py:80-84 sums tau_n An'An over the repeats): two rotated terms are gathered
+    in the quad kernel, rotated + lattice terms and odd nz in the direct kernel, a third rotated
+    term goes through the (unfused-launch) general path -- all against the oracle, and the CG
+    solve keeps the oracle's trip count."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim, struct, synth
+    mat_y = torch.eye(4, dtype=torch.float64)
+    specs = {'rot': [((1.2, -0.8, 0.5), (0.05, -0.03, 0.08)), ((-0.7, 1.1, -0.4), (-0.06, 0.04, 0.02)),
+                     ((0.4, 0.3, -0.9), (0.02, 0.07, -0.05))]}
+    obs_o, obs_g = [], []
+    k_rot = 0
+    for n, kind in enumerate(combo.split('+')):
+        axis, f = (0, 2) if n % 2 == 0 else (2, 2)
+        scl = [1.0, 1.0, 1.0]
+        scl[axis] = float(f)
+        mat_x = torch.diag(torch.tensor(scl + [1.0], dtype=torch.float64))
+        dim_x = tuple(int(d // s) for d, s in zip(dim_y, scl))
+        rigid = None
+        if kind == 'rot':
+            rigid = synth.rigid_matrix(*specs['rot'][k_rot])
+            k_rot += 1
+        po_o = P.proj_info(dim_y, mat_y, dim_x, mat_x, rigid=rigid, prof_ip=2, prof_tp=0, scl=0.05)
+        po_g = _project._proj_info(dim_y, mat_y, dim_x, mat_x, rigid=rigid, prof_ip=2, prof_tp=0,
+                                   scl=0.05, device=cuda)
+        tau = 0.01 * (1 + n)
+        obs_o.append(P.Observation(torch.zeros(dim_x), mat_x, tau=tau, po=po_o))
+        obs_g.append(struct._input(dat=None, tau=tau, po=po_g))
+    rec_o = P.Recon(torch.zeros(dim_y), mat_y, lam=0.2)
+    rec_g = struct._output(dat=None, dim=dim_y, mat=mat_y, lam=0.2)
+    v = _rand(dim_y, 9) + 1.0
+    vx = torch.ones(3)
+    lhs_o = lambda t: P.proj('AtA', t, obs_o, rec_o, rho=2.0, vx_y=vx)
+    op = _project.LhsOperator(obs_g, rec_g, rho=2.0, vx_y=vx)
+    assert U.rel_l2(op(v.to(cuda)), lhs_o(v)) < 1e-5
+    b = lhs_o(_rand(dim_y, 10) + 0.5)
+    xo = torch.zeros(dim_y)
+    OO.cg(A=lhs_o, b=b, x=xo, max_iter=12, tolerance=1e-3, stop='max_gain')
+    xg = torch.zeros(dim_y, device=cuda)
+    optim.cg(A=op, b=b.to(cuda), x=xg, max_iter=12, tolerance=1e-3, stop='max_gain')
+    assert optim.cg.last.n_iter == OO.cg.last_n_iter
+    assert U.rel_l2(xg, xo) < U.REL_TOL
