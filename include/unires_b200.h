@@ -260,6 +260,14 @@ int ur_jtv_apply(const float *const *d_y, float *d_z, float *d_w,
  * into d_e (X,Y,Z), then ur_sqrt_sum.                                      */
 int ur_nll_data(const float *d_x, const float *d_Ay, size_t n, float tau,
                 double *d_out, int accumulate, ur_stream stream);
+/* The data term of one observation WITHOUT materialising A y when the operator is lattice
+ * aligned with at most one decimated axis (one pass over y; the reference's pull / conv3d /
+ * scaling / boolean-mask compaction of unires/_update.py:411-417 folded into the reduction):
+ * *d_out (+)= 0.5 tau sum_{x != 0} (x - A y)^2.  Any other operator: A y is formed in the
+ * workspace first (ws_bytes >= ur_proj_workspace_bytes(po) + 4 numel(dim_x)).              */
+int ur_nll_data_proj(const ur_proj *po, const float *d_y, const float *d_x, float tau,
+                     double *d_out, int accumulate, void *d_ws, size_t ws_bytes,
+                     ur_stream stream);
 int ur_nll_prior_energy(const float *const *d_y, float *d_e, int n_channels,
                         const float *lam, const int32_t dim[3], const float vx[3],
                         int accumulate, ur_stream stream);

@@ -125,6 +125,7 @@ _SIGNATURES = {
     'ur_jtv_apply': (C.c_int, [C.POINTER(_p), _p, _p, _p, _p, C.c_int, _f3, _i3, _f3, C.c_float,
                                C.c_float, _p]),
     'ur_nll_data': (C.c_int, [_p, _p, _sz, C.c_float, _p, C.c_int, _p]),
+    'ur_nll_data_proj': (C.c_int, [C.POINTER(ur_proj), _p, _p, C.c_float, _p, C.c_int, _p, _sz, _p]),
     'ur_nll_prior_energy': (C.c_int, [C.POINTER(_p), _p, C.c_int, _f3, _i3, _f3, C.c_int, _p]),
     'ur_sqrt_sum': (C.c_int, [_p, _sz, _p, _p]),
     'ur_intensity_range': (C.c_int, [_p, _sz, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float),

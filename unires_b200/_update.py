@@ -82,10 +82,18 @@ def _nll_terms(x, y, sett, out, prior_field=None, accumulate_prior=False):
     for c in range(len(x)):
         for n, obs in enumerate(x[c]):
             dat = require_cuda_f32(obs.dat, 'x.dat')
-            Ay = _proj('A', y[c].dat, x[c], y[c], n=n, method=sett.method, do=sett.do_proj,
-                       bound=sett.bound, interpolation=sett.interpolation)
-            check(lib.ur_nll_data(ptr(dat), ptr(Ay), dat.numel(), _hs(obs.tau),
-                                  ptr(out[1:2]), 1, stream()))
+            if not sett.do_proj:  # A = identity
+                check(lib.ur_nll_data(ptr(dat), ptr(require_cuda_f32(y[c].dat, 'y.dat')),
+                                      dat.numel(), _hs(obs.tau), ptr(out[1:2]), 1, stream()))
+                continue
+            # 0.5 tau sum_{x != 0} (x - A y)^2: one pass over y for lattice operators (A y is
+            # never materialised), A y in the workspace + reduction otherwise
+            s = proj_struct(obs.po, sett.method)
+            nbytes = lib.ur_proj_workspace_bytes(C.byref(s)) + 4 * dat.numel() + 256
+            ws = _lib.workspace(nbytes, dat.device, 'proj')
+            check(lib.ur_nll_data_proj(C.byref(s), ptr(require_cuda_f32(y[c].dat, 'y.dat')),
+                                       ptr(dat), _hs(obs.tau), ptr(out[1:2]), 1, ptr(ws),
+                                       ws.numel(), stream()))
     ys = [require_cuda_f32(yc.dat, 'y.dat') for yc in y]
     lam = _lib.farr([_hs(yc.lam) for yc in y])
     field = prior_field

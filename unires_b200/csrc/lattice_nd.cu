@@ -269,6 +269,121 @@ __global__ void __launch_bounds__(kNdThreads, 2)
 }
 
 // ---------------------------------------------------------------------------
+// Data term of the objective in ONE pass for lattice operators with at most one decimated
+// axis (_compute_nll, unires/_update.py:411-417):  0.5 tau sum_{x != 0} (x - A y)^2.
+// The reference materialises A y (pull, conv3d, scaling) and then compacts it with a boolean
+// mask; here a thread forms (A y)[j] for its low-resolution voxel from the K taps it needs and
+// accumulates the masked squared residual in float64: y is read once, nothing is written.
+// Same per-element arithmetic as the unfused route (conv taps in order, then the in-plane
+// 1-tap factors, then exp(+-scl); __fsub_rn / __fmul_rn on the residual).
+// ---------------------------------------------------------------------------
+struct NllNdArgs {
+  NdOp op;
+  int ca;          // decimated axis, -1 = none
+  float inplane;   // product of the 1-tap factors of the other axes
+  int scl_axis;    // even/odd scaling along this low-res axis, -1 = none
+  float s_even, s_odd;
+  float tau;
+};
+
+__global__ void __launch_bounds__(256)
+    nll_nd_kernel(const float *__restrict__ y, const float *__restrict__ x, const NllNdArgs A,
+                  int accumulate, GridReduce gr, double *out) {
+  __shared__ double s_red[kMaxWarps];
+  const NdOp &op = A.op;
+  const int n0 = op.ax[0].nj, n1 = op.ax[1].nj, n2 = op.ax[2].nj;
+  const size_t sy = op.n[2], sx = (size_t)op.n[1] * op.n[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  double part = 0.0;
+  // warps over the (j0, j1) rows of the low-res grid, lanes along j2
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < (long long)n0 * n1;
+       row += (long long)gridDim.x * wpb) {
+    const int j0 = (int)(row / n1), j1 = (int)(row - (long long)j0 * n1);
+    const int g0 = j0 * op.ax[0].r + op.ax[0].off, g1 = j1 * op.ax[1].r + op.ax[1].off;
+    for (int j2 = lane; j2 < n2; j2 += 32) {
+      const float xv = __ldg(x + ((size_t)j0 * n1 + j1) * n2 + j2);
+      if (xv == 0.f) continue;
+      const int g2 = j2 * op.ax[2].r + op.ax[2].off;
+      int g[3] = {g0, g1, g2};
+      float acc = 0.f;
+      const int K = A.ca >= 0 ? op.ax[A.ca].K : 1;
+      bool inside = true;  // the non-decimated axes: a crop (zero outside the recon grid)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (d != A.ca) inside = inside && g[d] >= 0 && g[d] < op.n[d];
+      if (inside) {
+        const size_t step = A.ca == 0 ? sx : (A.ca == 1 ? sy : 1);
+        const int gc = A.ca >= 0 ? g[A.ca] : 0, nc = A.ca >= 0 ? op.n[A.ca] : 1;
+        const float *base = y + (size_t)(A.ca == 0 ? 0 : g[0]) * sx +
+                            (size_t)(A.ca == 1 ? 0 : g[1]) * sy + (A.ca == 2 ? 0 : g[2]);
+        if (A.ca < 0) {
+          acc = __ldg(base);
+        } else {
+          for (int t = 0; t < K; ++t) {
+            const int q = gc + t;
+            const float v = (q >= 0 && q < nc) ? __ldg(base + (size_t)q * step) : 0.f;
+            acc = fmaf(op.ax[A.ca].ker[t], v, acc);
+          }
+        }
+      }
+      if (A.inplane != 1.f) acc *= A.inplane;
+      if (A.scl_axis >= 0) {
+        const int js = A.scl_axis == 0 ? j0 : (A.scl_axis == 1 ? j1 : j2);
+        acc *= (js & 1) ? A.s_odd : A.s_even;
+      }
+      const float dlt = __fsub_rn(xv, acc);
+      part += (double)__fmul_rn(dlt, dlt);
+    }
+  }
+  double total;
+  if (grid_sum(part, gr, s_red, &total) && threadIdx.x == 0) {
+    total = 0.5 * (double)A.tau * total;
+    *out = accumulate ? *out + total : total;
+  }
+}
+
+int scratch_reduce(GridReduce *gr, cudaStream_t st);  // vecops.cu
+
+// UR_ERR_UNSUPPORTED (nothing launched) unless the operator is lattice aligned with at most
+// one decimated axis
+int nll_nd_launch(const ::ur_proj *po, const float *y, const float *x, float tau, double *out,
+                  int accumulate, cudaStream_t st) {
+  ::ur_proj p0 = *po;
+  p0.scl = 0.f;
+  NllNdArgs A;
+  memset(&A, 0, sizeof(A));
+  if (!nd_describe(&p0, tau, &A.op) || nd_conv_axes(A.op) > 1) return UR_ERR_UNSUPPORTED;
+  A.ca = -1;
+  A.inplane = 1.f;
+  for (int a = 0; a < 3; ++a) {
+    if (A.op.ax[a].K > 1 || A.op.ax[a].r > 1)
+      A.ca = a;
+    else
+      A.inplane *= A.op.ax[a].ker[0];
+  }
+  A.scl_axis = -1;
+  A.s_even = A.s_odd = 1.f;
+  if (po->method == UR_SUPERRES && po->scl != 0.f) {
+    A.scl_axis = po->dim_thick;
+    A.s_even = expf(po->scl);
+    A.s_odd = expf(-po->scl);
+  }
+  A.tau = tau;
+  GridReduce gr;
+  int rc = scratch_reduce(&gr, st);
+  if (rc) return rc;
+  const long long rows = (long long)A.op.ax[0].nj * A.op.ax[1].nj;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  nll_nd_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, x, A, accumulate, gr, out);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 int g_nd_fused = 1;  // ur_tune("nd_fused"): 0 = chained single-axis passes / general path

@@ -28,6 +28,9 @@ int nd_down_launch(const NdOp &op, const float *v, float *out, float scale, cons
 int nd_up_launch(int mode, const NdOp &op, const float *xl, float scale, const LhsArgs &A,
                  cudaStream_t st);
 extern int g_nd_fused;
+// 0.5 tau sum_{x != 0} (x - A y)^2 in one pass (lattice operators, <= 1 decimated axis)
+int nll_nd_launch(const ::ur_proj *po, const float *y, const float *x, float tau, double *out,
+                  int accumulate, cudaStream_t st);
 // compile-time specialised TMA variants (lattice_nd_spec.cu); UR_ERR_UNSUPPORTED when the
 // operator has no instantiation
 int nd_down_spec_launch(const NdOp &op, const float *v, float *out, float scale, const int *done,

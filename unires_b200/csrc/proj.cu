@@ -281,3 +281,24 @@ extern "C" int ur_proj_accumulate(int op, const ur_proj *po, const float *d_in, 
   UR_REQUIRE(d_in && d_out, "ur_proj_accumulate: null data pointer");
   return proj_apply_general(op, po, d_in, d_out, scale, d_ws, ws_bytes, (cudaStream_t)stream);
 }
+
+extern "C" int ur_nll_data_proj(const ur_proj *po, const float *d_y, const float *d_x, float tau,
+                                double *d_out, int accumulate, void *d_ws, size_t ws_bytes,
+                                ur_stream stream) {
+  UR_REQUIRE(d_y && d_x && d_out, "ur_nll_data_proj: null pointer");
+  int rc = validate_proj(po);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ur_proj_is_lattice(po) && g_nd_fused) {
+    rc = nll_nd_launch(po, d_y, d_x, tau, d_out, accumulate, st);
+    if (rc != UR_ERR_UNSUPPORTED) return rc;
+  }
+  // general route: A y into the workspace (after the operator's own scratch), then the reduction
+  const size_t nx = (size_t)po->dim_x[0] * po->dim_x[1] * po->dim_x[2];
+  const size_t pw = proj_workspace_bytes(po);
+  UR_REQUIRE(d_ws && ws_bytes >= pw + nx * sizeof(float), "ur_nll_data_proj: workspace too small");
+  float *Ay = (float *)((char *)d_ws + pw);
+  rc = proj_apply_general(UR_OP_A, po, d_y, Ay, 1.f, d_ws, pw, st);
+  if (rc) return rc;
+  return ur_nll_data(d_x, Ay, nx, tau, d_out, accumulate, stream);
+}
