@@ -256,6 +256,72 @@ def test_rotated_fused_kernels_equal_general_path(cuda, name):
         assert a.shape == b.shape and U.rel_l2(a, b) < 2e-6
 
 
+@pytest.mark.parametrize('name', ['sr2_rigid', 'mid_sr3_rigid'])
+def test_rotated_cell_adjoint_equals_gather(cuda, name):
+    """Adjoint pull of rotated operators through per-cell corner coefficients
+    (rot_adjoint_cell_kernel: scatter into shared-memory cells in colour passes, then a gather
+    per voxel) against the per-voxel candidate gather (ur_tune rot_cell=0), with two and with
+    eight colour passes, for At, AtA and the CG left-hand side; every variant bit-reproducible."""
+    from oracle import gen_golden
+    from unires_b200 import _lib, _project
+    _, recipe = U.load_golden(name)
+    sc = U.build(recipe, *U.port_namespaces())
+    x, y, sett = U.to_device(sc, cuda)
+    vx_y = [float(sc.cfg['vx_y'])] * 3
+    res = {}
+    try:
+        for cell in (1, 8, 0):
+            _lib.check(_lib.lib.ur_tune(b'rot_cell', cell))
+            outs = []
+            for c in range(len(x)):
+                vy, vx = gen_golden.probe_inputs(sc, c)
+                po = x[c][0].po
+                for op, v in (('At', vx), ('AtA', vy)):
+                    a = _project._proj_apply(op, v.to(cuda)[None, None], po)[0, 0].clone()
+                    b = _project._proj_apply(op, v.to(cuda)[None, None], po)[0, 0]
+                    assert torch.equal(a, b)
+                    outs.append(a)
+                lhs = _project.LhsOperator(x[c], y[c], method=sett.method, do=sett.do_proj,
+                                           rho=sc.rho, vx_y=vx_y)
+                a = lhs(vy.to(cuda)).clone()
+                assert torch.equal(a, lhs(vy.to(cuda)))
+                outs.append(a)
+            res[cell] = outs
+    finally:
+        _lib.check(_lib.lib.ur_tune(b'rot_cell', 1))
+    for a, b, c in zip(res[1], res[8], res[0]):
+        assert U.rel_l2(a, c) < 2e-6 and U.rel_l2(b, c) < 2e-6
+
+
+@pytest.mark.parametrize('rot', [(0.0, 0.0, 0.7854), (0.5, -0.4, 0.7), (1e-5, 0.0, -2e-5),
+                                 (0.1, -0.1, 0.1)])
+def test_rotated_cell_adjoint_any_rotation(cuda, rot):
+    """Large, tiny and notebook-sized rotations: whatever path the operator selects (two or
+    eight colours, or the gather when the tile's pre-image is too large) equals the gather, and
+    P' is the exact transpose of P (<P v, u> = <v, P' u> in float64 sums)."""
+    from unires_b200 import _lib, _project, synth
+    cfg = synth.scaled(synth.CONFIGS['sr3_256'], (48, 56, 60))
+    dim_x, mat_x, dim_y, mat_y = synth.geometry(cfg, 2)
+    rigid = synth.rigid_matrix((1.5, -2.0, 0.75), rot)
+    po = _project._proj_info(dim_y, mat_y, dim_x, mat_x, rigid=rigid, prof_ip=2, prof_tp=0,
+                             scl=0.0, device=cuda)
+    g = torch.Generator().manual_seed(5)
+    u = torch.rand(tuple(po.dim_x), generator=g).to(cuda)
+    v = torch.rand(tuple(po.dim_y), generator=g).to(cuda)
+    outs = {}
+    try:
+        for cell in (1, 0):
+            _lib.check(_lib.lib.ur_tune(b'rot_cell', cell))
+            outs[cell] = _project._proj_apply('At', u[None, None], po)[0, 0].clone()
+    finally:
+        _lib.check(_lib.lib.ur_tune(b'rot_cell', 1))
+    assert U.rel_l2(outs[1], outs[0]) < 2e-6
+    Av = _project._proj_apply('A', v[None, None], po)[0, 0]
+    lhs_ = float((Av.double() * u.double()).sum())
+    rhs_ = float((v.double() * outs[1].double()).sum())
+    assert abs(lhs_ - rhs_) <= 1e-4 * abs(lhs_)
+
+
 @pytest.mark.parametrize('dim_y,scl,shift', [((40, 36, 52), (2, 2, 2), (0, 0, 0)),
                                              ((33, 30, 44), (2, 3, 1), (1, -2, 0)),
                                              ((26, 41, 36), (1, 2, 4), (0, 3, -1)),

@@ -20,6 +20,8 @@ int fast_q_units = 0; // units per CTA override (0 automatic)
 int fast_pfd = 0;     // planes prefetched into L2 ahead of the ring
 int fast_lock = 1;    // cut every column into the same segments (neighbours march in step)
 int fast_diag_residue = 1;  // carry the rounding residue of the stencil diagonal (debug knob)
+int fast_to = 0;      // output rows per tile (0 automatic; <= 8 rpt)
+int fast_segs = 0;    // segments per column override (0 automatic)
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
 
@@ -143,30 +145,21 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   if (!kernel) return UR_ERR_UNSUPPORTED;
   const int hz = fast_hz(kind, kp), sz = TZ + 2 * hz;
 
-  const int to = NWARP * rpt;
+  const int to_max = NWARP * rpt;  // rows of the tile in shared memory (compile time)
+  int to = to_max;                  // rows that are output
+  if (fast_to > 0 && fast_to <= to_max) to = fast_to;
   const int L = kind == FK_THICK_M ? kp - 1 : 1;
   const int B = kind == FK_THICK_M ? kp - 1 : 0;
   const int depth = fast_depth < 1 ? 1 : fast_depth;
   S.ns = L + 3 + 2 * depth;
   S.nrs = combine ? S.ns - L - 1 : 0;
   if (S.ns > kMaxSlots) return UR_ERR_UNSUPPORTED;
-  const size_t plane_b = ((size_t)(to + 2) * sz * 4 + 127) / 128 * 128;
+  const size_t plane_b = ((size_t)(to_max + 2) * sz * 4 + 127) / 128 * 128;
   const size_t smem = (size_t)(S.ns + S.nrs) * plane_b + 128;
   if (smem > 200u * 1024u) return UR_ERR_UNSUPPORTED;
 
-  CUtensorMap map_v, map_r, map_x;
-  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, sz, march, to + 2, &map_v, pitch))
-    return UR_ERR_UNSUPPORTED;
-  map_r = map_v;
-  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, sz, march, to + 2, &map_r, pitch))
-    return UR_ERR_UNSUPPORTED;
-  map_x = map_v;
-  if (x_fused && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))
-    return UR_ERR_UNSUPPORTED;
-  if (dry_run) return UR_OK;
-
   int resident = 0;
-  {
+  if (!dry_run) {
     static std::unordered_map<size_t, int> occ_cache;
     static std::mutex occ_mu;
     // the opt-in to > 48 KB of dynamic shared memory and the occupancy are per DEVICE
@@ -193,13 +186,39 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.unit_r = kind == FK_THICK_M ? r : 1;
   S.unit_e2 = kind == FK_THICK_M ? (e > 0 ? e : r) : 1;
   S.units_per_col = 1 + (S.nm > S.unit_e2 ? (S.nm - S.unit_e2 + S.unit_r - 1) / S.unit_r : 0);
-  const unsigned gx = div_up(S.nz, TZ), gy = div_up(S.no, to);
+  const long long slots = (long long)resident * sm_count();
+  const long long q_min = (4 * (B + L + 1) + S.unit_r - 1) / S.unit_r;
+  const long long max_segs = S.units_per_col / q_min > 0 ? S.units_per_col / q_min : 1;
+  const unsigned gx = div_up(S.nz, TZ);
+  // CTAs of the lock-step split with `rows` output rows per tile
+  auto lock_ctas = [&](int rows) {
+    const long long ncol = (long long)gx * div_up(S.no, rows);
+    if (ncol > slots) return 0ll;
+    const long long segs = slots / ncol < max_segs ? slots / ncol : max_segs;
+    return segs * ncol;
+  };
+  // Output rows per tile: a 7-row tile (the eighth warp idles) when that fills more of the
+  // CTA slots -- 256^3: 37 x 2 columns x 6 segments = 444 = 3 x 148 instead of 384 (-2 %)
+  if (!dry_run && rpt == 1 && fast_to == 0 && fast_lock && fast_q_units == 0 && fast_segs == 0 &&
+      lock_ctas(to_max - 1) > lock_ctas(to_max))
+    to = to_max - 1;
+
+  CUtensorMap map_v, map_r, map_x;
+  if (!stream_tensor_map(A.v, A.nx, A.ny, A.nz, sz, march, to + 2, &map_v, pitch))
+    return UR_ERR_UNSUPPORTED;
+  map_r = map_v;
+  if (combine && !stream_tensor_map(A.rres, A.nx, A.ny, A.nz, sz, march, to + 2, &map_r, pitch))
+    return UR_ERR_UNSUPPORTED;
+  map_x = map_v;
+  if (x_fused && !stream_tensor_map(A.xup, A.nx, A.ny, A.nz, TZ, march, to, &map_x, pitch))
+    return UR_ERR_UNSUPPORTED;
+  if (dry_run) return UR_OK;
+
+  const unsigned gy = div_up(S.no, to);
   S.gx = (int)gx;
   S.ncol = (int)(gx * gy);
   const long long total = (long long)S.ncol * S.units_per_col;
-  const long long slots = (long long)resident * sm_count();
   long long q = (total + slots - 1) / slots;
-  const long long q_min = (4 * (B + L + 1) + S.unit_r - 1) / S.unit_r;
   if (q < q_min) q = q_min;
   if (fast_q_units > 0) q = fast_q_units;
   if (q > total) q = total;
@@ -210,13 +229,14 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   S.segs = 0;
   if (fast_lock && fast_q_units == 0 && S.ncol <= slots) {
     long long segs = slots / S.ncol;
-    const long long max_segs = S.units_per_col / q_min > 0 ? S.units_per_col / q_min : 1;
     if (segs > max_segs) segs = max_segs;
-    if (segs * S.ncol * 4 >= slots * 3) {  // keep >= 75 % of the CTA slots busy
+    if (fast_segs > 0) segs = fast_segs < max_segs ? fast_segs : max_segs;
+    if (segs * S.ncol * 4 >= slots * 3 || fast_segs > 0) {  // keep >= 75 % of the CTA slots busy
       S.segs = (int)segs;
       n_cta = (unsigned)(segs * S.ncol);
     }
   }
+  S.to = to;
   S.pfd = fast_pfd < 0 ? 0 : fast_pfd;
 
   S.v = A.v;

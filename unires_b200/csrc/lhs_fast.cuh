@@ -66,6 +66,8 @@ struct FastArgs {
                 // columns then march in step and share their halos through L2); 0: contiguous
                 // ranges of q_units units in (column, unit) order
   int pfd;      // planes prefetched into L2 ahead of the ring's issue front
+  int to;       // rows of a tile that are OUTPUT (<= 8 RPT; the threads of the other rows idle): a
+                // shorter tile makes more columns, so that columns x segments fills the CTA slots
   const float *v;
   float *out;
   const float *b;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   const uint32_t bar_base = smem_u32(s_bar);
   const uint32_t bar_end = bar_base + 8u * (uint32_t)a.ns;
   const uint32_t own_b = (uint32_t)((row0 + 1) * SZ + HZ + 4 * lane) * 4u;
+  const uint32_t box_bytes = (uint32_t)(a.to + 2) * ROWB;  // what one TMA box delivers
 
   if (tid == 0) {
     for (int s = 0; s < a.ns; ++s) mbar_init(bar_base + 8u * s, 1);
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     t += k1 - k0;
     const int m0 = ustart(k0), m1 = ustart(k1);
     const int cz = col % a.gx, co = col / a.gx;
-    const int z0 = cz * TZ, o0 = co * TO;
+    const int z0 = cz * TZ, o0 = co * a.to;
     const int o_first = o0 + row0, z = z0 + 4 * lane;
 
     const int u_begin = m0 - B;
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const int o = o_first + i;
-      act[i] = z < a.nz && o < a.no;
+      act[i] = z < a.nz && o < a.no && row0 + i < a.to;
       const float dz0 = a.d0 - (o == 0 ? a.a_o : 0.f);
       Dq[i] = make_float4(dz0 - (z == 0 ? a.a_z : 0.f), dz0, dz0, dz0);
       const bool o_in = o >= a.lo_o && o < a.hi_o;
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
     auto issue = [&](int limit) {
       while (iq <= last && iq < limit) {
         if (COMBINE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(ip_ba, COMBINE ? 2u * PLANE_BYTES : PLANE_BYTES);
+        mbar_expect_tx(ip_ba, (COMBINE ? 2u : 1u) * box_bytes);
         if (a.march_y) {
           tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, iq, o0 - 1);
           if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, iq, o0 - 1);

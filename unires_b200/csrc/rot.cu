@@ -8,6 +8,8 @@
 namespace ur {
 
 int g_rot_fused = 1;  // ur_tune("rot_fused")
+int g_rot_cell = 1;   // ur_tune("rot_cell"): adjoint through per-cell corner coefficients
+                      // (0 = per-voxel gather, 8 = always eight colour passes: test hook)
 
 constexpr int kRotThreads = 256;
 
@@ -257,6 +259,198 @@ __global__ void __launch_bounds__(256)
   *o = q;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Adjoint pull P'u through per-CELL corner coefficients (deterministic, no atomics).
+//
+// The pull samples v at c(p) = M p + t for every intermediate voxel p; its transpose hands
+// u[p] w_abc(p) to the eight corners (a, b, c) of the recon cell floor(c(p)).  A CTA owns a
+// TX x TY x TZ tile of recon voxels, i.e. the (TX+1)(TY+1)(TZ+1) cells that have a corner in
+// it, and keeps eight coefficients per cell in shared memory:
+//   phase 1 (SCATTER over the intermediate voxels of the tile's pre-image): p is visited once,
+//            c(p), the FOV test and the corner weights with the pull's own float32
+//            expressions; coef[abc][cell] += u[p] w_abc.  Two intermediate voxels can share a
+//            cell only if they differ by a lattice vector whose image fits a unit cell; the
+//            host picks a colouring of the lattice (2 colours: parity of i+j+k; 8: parities of
+//            i, j, k) under which same-coloured voxels never do, and the colours run as
+//            barrier-separated passes -- plain read-modify-write, fixed order, bit-reproducible;
+//   phase 2 (GATHER): a recon voxel sums coefficient (a,b,c) of the cell at voxel - (a,b,c).
+// ~7 warp instructions per recon voxel instead of ~18 for the per-voxel candidate search of
+// rot_gather4 (which visits 18-27 candidates for 8 contributors).
+// Reference: nitorch grid_push as called at unires/_project.py:172,179 (= transpose of :164).
+constexpr int kCellTX = 8, kCellTY = 8, kCellTZ = 28;
+constexpr int kCellMaxRows = 1000;
+constexpr int kCellThreads = 512;
+
+// k range (clipped into [k0, k1]) where lo <= m k + s < hi can hold; widened against rounding
+__device__ __forceinline__ void cell_krange(float m, float s, float lo, float hi, int &k0, int &k1) {
+  if (fabsf(m) < 1e-6f) return;  // no usable bound along k: the candidate test decides
+  const float r = 1.f / m;
+  const float e0 = (lo - s) * r, e1 = (hi - s) * r;
+  const float slack = 2e-2f + 4e-4f * fabsf(r);
+  const float a = fminf(e0, e1) - slack, b = fmaxf(e0, e1) + slack;
+  // compare in float first: the bounds may exceed the int range
+  if (a > (float)k0) k0 = a > (float)k1 ? k1 + 1 : (int)ceilf(a);
+  if (b < (float)k1) k1 = b < (float)k0 ? k0 - 1 : (int)floorf(b);
+}
+
+template <int TX, int TY, int TZ>
+__global__ void __launch_bounds__(kCellThreads, 2)
+    rot_adjoint_cell_kernel(const RotTerm T, float *__restrict__ out, int nx, int ny, int nz,
+                            int accumulate, const int *done) {
+  constexpr int NW = kCellThreads / 32;
+  static_assert(TX == 8 && NW % 8 == 0 && TY % (NW / 8) == 0, "a warp per x row and y slab");
+  static_assert(TZ <= 32, "one lane per z voxel of the tile");
+  constexpr int CX = TX + 1, CY = TY + 1, CZ = TZ + 1;
+  constexpr int NCELL = CX * CY * CZ;
+  constexpr int PL = (NCELL + 3) / 4 * 4;  // floats per coefficient plane
+  extern __shared__ __align__(16) float cell_sm[];
+  float *coef = cell_sm;  // [8][PL]
+  int4 *rows = reinterpret_cast<int4 *>(cell_sm + 8 * PL);  // (i, j, k0, k1) of the live rows
+  __shared__ int s_nrows;
+  if (done && *done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.z * TX, y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
+  // sample positions of the owned cells: [x0 - 1, x0 + TX) x [y0 - 1, y0 + TY) x [z0 - 1, z0 + TZ)
+  const float bl[3] = {(float)(x0 - 1), (float)(y0 - 1), (float)(z0 - 1)};
+  const float bh[3] = {(float)(x0 + TX), (float)(y0 + TY), (float)(z0 + TZ)};
+  int ilo[3], ihi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // bounding box of the pre-image in intermediate indices
+    const float base = T.inv[4 * a + 0] * bl[0] + T.inv[4 * a + 1] * bl[1] +
+                       T.inv[4 * a + 2] * bl[2] + T.inv[4 * a + 3];
+    const float dx = T.inv[4 * a + 0] * (float)(TX + 1), dy = T.inv[4 * a + 1] * (float)(TY + 1),
+                dz = T.inv[4 * a + 2] * (float)(TZ + 1);
+    const float lo = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.06f;
+    const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.06f;
+    ilo[a] = lo > 0.f ? (lo > 1e9f ? 1 << 30 : (int)ceilf(lo)) : 0;
+    ihi[a] = hi < (float)(T.n[a] - 1) ? (hi < -1e9f ? -2 : (int)floorf(hi)) : T.n[a] - 1;
+  }
+  const int ni = ihi[0] - ilo[0] + 1, nj = ihi[1] - ilo[1] + 1;
+  const bool any = ni > 0 && nj > 0 && ihi[2] >= ilo[2];
+  const int nbox = any ? ni * nj : 0;
+  if (nbox > kCellMaxRows) asm volatile("trap;");  // the host checks the operator: never taken
+  if (tid == 0) s_nrows = 0;
+
+  // ---- phase 0: zero the coefficients; list of the rows (i, j) that can hit the tile with
+  // their k range (list order is irrelevant: rows of one pass never share a cell) ----
+  for (int q = tid; q < 8 * PL / 4; q += kCellThreads)
+    reinterpret_cast<float4 *>(coef)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int r = tid; r < nbox; r += kCellThreads) {
+    const int ii = r / nj, i = ilo[0] + ii, j = ilo[1] + (r - ii * nj);
+    const float fi = (float)i, fj = (float)j;
+    const float bx = fmaf(T.m[1], fj, T.m[0] * fi) + T.m[3];
+    const float by = fmaf(T.m[5], fj, T.m[4] * fi) + T.m[7];
+    const float bz = fmaf(T.m[9], fj, T.m[8] * fi) + T.m[11];
+    int k0 = ilo[2], k1 = ihi[2];
+    cell_krange(T.m[2], bx, bl[0], bh[0], k0, k1);
+    cell_krange(T.m[6], by, bl[1], bh[1], k0, k1);
+    cell_krange(T.m[10], bz, bl[2], bh[2], k0, k1);
+    if (k0 <= k1) rows[atomicAdd(&s_nrows, 1)] = make_int4(i, j, k0, k1);
+  }
+  __syncthreads();
+  const int nrows = s_nrows;
+
+  // ---- phase 1: colour passes over the intermediate voxels ----
+  const float fmax_x = (float)(nx - 1) + kRotFovTol, fmax_y = (float)(ny - 1) + kRotFovTol,
+              fmax_z = (float)(nz - 1) + kRotFovTol;
+  const int sub = lane >> 4, l16 = lane & 15;  // a half warp per candidate row
+  const int ncol = T.cell_ncol;
+  const int n12 = T.n[1] * T.n[2];
+  for (int c = 0; c < ncol && nrows > 0; ++c) {
+    for (int rp = 2 * warp + sub; rp < nrows; rp += 2 * NW) {
+      const int4 e = rows[rp];
+      const int i = e.x, j = e.y;
+      int kpar = (c + i + j) & 1;
+      if (ncol == 8) {  // rows with the pass's parities of i and j only
+        if ((((i & 1) << 1) | (j & 1)) != (c >> 1)) continue;
+        kpar = c & 1;
+      }
+      const float fi = (float)i, fj = (float)j;
+      const float bx = fmaf(T.m[1], fj, T.m[0] * fi);
+      const float by = fmaf(T.m[5], fj, T.m[4] * fi);
+      const float bz = fmaf(T.m[9], fj, T.m[8] * fi);
+      const float *urow = T.u + (i * n12 + j * T.n[2]);
+      for (int k = e.z + ((e.z ^ kpar) & 1) + 2 * l16; k <= e.w; k += 32) {
+        const float uv = __ldg(urow + k);  // requested before the coordinates: latency overlaps
+        const float fk = (float)k;
+        const float cx = fmaf(T.m[2], fk, bx) + T.m[3];
+        const float cy = fmaf(T.m[6], fk, by) + T.m[7];
+        const float cz = fmaf(T.m[10], fk, bz) + T.m[11];
+        const bool ok = cx > -kRotFovTol && cx < fmax_x && cy > -kRotFovTol && cy < fmax_y &&
+                        cz > -kRotFovTol && cz < fmax_z;
+        const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+        const int lx = (int)fx - (x0 - 1), ly = (int)fy - (y0 - 1), lz = (int)fz - (z0 - 1);
+        if (ok && (unsigned)lx < (unsigned)CX && (unsigned)ly < (unsigned)CY &&
+            (unsigned)lz < (unsigned)CZ) {
+          const float wx1 = cx - fx, wy1 = cy - fy, wz1 = cz - fz;
+          const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;
+          const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+          float *cp = coef + (lx * CY + ly) * CZ + lz;
+          cp[0 * PL] += uv * (w00 * wz0);
+          cp[1 * PL] += uv * (w00 * wz1);
+          cp[2 * PL] += uv * (w01 * wz0);
+          cp[3 * PL] += uv * (w01 * wz1);
+          cp[4 * PL] += uv * (w10 * wz0);
+          cp[5 * PL] += uv * (w10 * wz1);
+          cp[6 * PL] += uv * (w11 * wz0);
+          cp[7 * PL] += uv * (w11 * wz1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 2: voxel (x, y, z) <- coefficient (a, b, c) of the cell at (x - a, y - b, z - c) ----
+  constexpr int YS = TY / (NW / 8);  // y rows per warp
+  const int xr = warp & 7, ys = (warp >> 3) * YS;
+  const int x = x0 + xr, z = z0 + lane;
+  if (x < nx && lane < TZ && z < nz) {
+    // the voxel's own cell (its corner 0,0,0) at y = y0 + ys
+    const float *cc = coef + ((xr + 1) * CY + ys + 1) * CZ + lane + 1;
+    float *o = out + ((size_t)x * ny + (y0 + ys)) * nz + z;
+#pragma unroll 2
+    for (int yy = 0; yy < YS; ++yy, cc += CZ, o += nz) {
+      if (y0 + ys + yy >= ny) break;
+      float acc = cc[0 * PL];
+      acc += cc[1 * PL - 1];
+      acc += cc[2 * PL - CZ];
+      acc += cc[3 * PL - CZ - 1];
+      acc += cc[4 * PL - CY * CZ];
+      acc += cc[5 * PL - CY * CZ - 1];
+      acc += cc[6 * PL - CY * CZ - CZ];
+      acc += cc[7 * PL - CY * CZ - CZ - 1];
+      *o = accumulate ? *o + acc : acc;
+    }
+  }
+}
+
+// Colour passes under which two intermediate voxels of one colour never fall into the same
+// recon cell: 2 (parity of i + j + k) when no even-sum lattice vector maps into a unit cell, 8
+// (parities of i, j, k) when no all-even vector does, 0 = neither (strongly anisotropic map).
+static int rot_cell_colours(const float *mat) {
+  bool ok2 = true, ok8 = true;
+  for (int a = -4; a <= 4; ++a)
+    for (int b = -4; b <= 4; ++b)
+      for (int c = -4; c <= 4; ++c) {
+        if (!a && !b && !c) continue;
+        double mx = 0.0;
+        for (int r = 0; r < 3; ++r) {
+          const double v = fabs((double)mat[4 * r] * a + (double)mat[4 * r + 1] * b +
+                                (double)mat[4 * r + 2] * c);
+          if (v > mx) mx = v;
+        }
+        const bool fits = mx < 1.0 + 5e-4;  // float32 slack on coordinates up to ~1e3
+        if (!fits) continue;
+        if (((a + b + c) & 1) == 0) ok2 = false;
+        if (!(a & 1) && !(b & 1) && !(c & 1)) ok8 = false;
+      }
+  return ok2 ? 2 : (ok8 ? 8 : 0);
+}
+
+bool rot_cell_enabled(const RotTerm &T) { return g_rot_cell && T.cell_ncol > 0; }
+
 static bool dirac_axis(const ::ur_proj *po, int a) {
   return po->ksize[a] == 1 && po->ratio[a] == 1;
 }
@@ -346,6 +540,18 @@ bool rot_describe(const ::ur_proj *po, int op, float tau, RotFwd *F, RotTerm *T)
     if (cand > 4096.0) return false;
     for (int k = 0; k < 12; ++k) t.m[k] = mat[k];
     t.rz = fabsf(mat[10]) >= 0.5f ? 1.f / mat[10] : 0.f;
+    // cell-coefficient adjoint: a colouring exists and the candidate rows of a tile fit the table
+    {
+      const double ext[3] = {kCellTX + 1.0, kCellTY + 1.0, kCellTZ + 1.0};
+      double rows = 1.0;
+      for (int r = 0; r < 2; ++r) {
+        double e = 2.2;
+        for (int c = 0; c < 3; ++c) e += fabs(iv[r][c]) * ext[c];
+        rows *= e;
+      }
+      const double nvox = (double)f.nyx[0] * f.nyx[1] * f.nyx[2];  // 32-bit offsets in the kernel
+      t.cell_ncol = (rows <= (double)kCellMaxRows && nvox < 2.0e9) ? rot_cell_colours(mat) : 0;
+    }
     *T = t;
   }
   return true;
@@ -416,7 +622,28 @@ int rot_expand_launch(const RotFwd &F, const float *x, float *u, cudaStream_t st
 }
 
 int rot_adjoint_launch(const RotTerm &T, const int dim_y[3], float *out, int accumulate,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int *done) {
+  if (rot_cell_enabled(T)) {
+    constexpr int CELLS = (kCellTX + 1) * (kCellTY + 1) * (kCellTZ + 1);
+    constexpr size_t smem = (size_t)8 * ((CELLS + 3) / 4 * 4) * sizeof(float) +
+                            (size_t)kCellMaxRows * sizeof(int4);
+    static bool attr_set[64] = {false};  // the opt-in to > 48 KB is per device
+    int dev = 0;
+    UR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      UR_CUDA_CHECK(cudaFuncSetAttribute(
+          (const void *)rot_adjoint_cell_kernel<kCellTX, kCellTY, kCellTZ>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[dev] = true;
+    }
+    dim3 grid(div_up(dim_y[2], kCellTZ), div_up(dim_y[1], kCellTY), div_up(dim_y[0], kCellTX));
+    RotTerm Tc = T;
+    if (g_rot_cell == 8) Tc.cell_ncol = 8;  // valid whenever two colours are
+    rot_adjoint_cell_kernel<kCellTX, kCellTY, kCellTZ><<<grid, kCellThreads, smem, st>>>(
+        Tc, out, dim_y[0], dim_y[1], dim_y[2], accumulate, done);
+    UR_LAUNCH_CHECK();
+    return UR_OK;
+  }
   if (dim_y[2] % 4 == 0 && ((uintptr_t)out & 15u) == 0) {
     dim3 block(32, 8, 1), grid(div_up(dim_y[2], 128), div_up(dim_y[1], 8), dim_y[0]);
     rot_adjoint4_kernel<<<grid, block, 0, st>>>(T, out, dim_y[0], dim_y[1], dim_y[2], accumulate);

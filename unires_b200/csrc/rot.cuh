@@ -24,6 +24,7 @@ struct RotTerm {
   float h[3];     // half extents of the candidate box per intermediate axis
   int n[3];       // dim_yx
   float rz;       // 1 / m[10] when the z rows are resolved exactly (|m[10]| >= 0.5), else 0
+  int cell_ncol;  // cell-coefficient adjoint (rot_adjoint_cell_kernel): colour passes, 0 = n/a
   const float *u; // (dim_yx) volume written by rot_forward_kernel
 };
 
@@ -172,9 +173,12 @@ bool rot_describe(const ::ur_proj *po, int op, float tau, RotFwd *F, RotTerm *T)
 // op = UR_OP_A: out = S C P v on dim_x;  UR_OP_ATA: out = tau C' S^2 C P v on dim_yx
 int rot_forward_launch(int op, const RotFwd &F, const float *v, float *out, cudaStream_t st,
                        const int *done = nullptr);
-// stand-alone adjoint: out (dim_y) (+)= P' u  (accumulate = 0 overwrites)
+// stand-alone adjoint: out (dim_y) (+)= P' u  (accumulate = 0 overwrites): the cell-coefficient
+// kernel when the operator allows it (T.cell_ncol > 0 and ur_tune("rot_cell") != 0), else the
+// per-voxel gather
 int rot_adjoint_launch(const RotTerm &T, const int dim_y[3], float *out, int accumulate,
-                       cudaStream_t st);
+                       cudaStream_t st, const int *done = nullptr);
+bool rot_cell_enabled(const RotTerm &T);
 // C' S x -> u on dim_yx for At (x on dim_x), scaled by F.weight
 int rot_expand_launch(const RotFwd &F, const float *x, float *u, cudaStream_t st);
 

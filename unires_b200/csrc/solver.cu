@@ -35,6 +35,7 @@ static int g_lhs_variant = 0;  // ur_tune("lhs_variant")
 static int g_cg_graph = 1;         // ur_tune("cg_graph"): replay repeated solves as CUDA graphs
 static unsigned g_tune_epoch = 0;  // bumped by every ur_tune: cached graphs embed the knobs
 extern int g_rot_fused;        // rot.cu; ur_tune("rot_fused"): 0 = rotated operators through the general path
+extern int g_rot_cell;         // rot.cu; ur_tune("rot_cell"): 0 = adjoint by the per-voxel gather
 
 static size_t align_up_sz(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -890,8 +891,10 @@ static size_t lhs_partials_bytes(const LhsPlan &P) {
 
 static size_t lhs_ws_bytes(const ur_lhs *lhs, const LhsPlan &P) {
   size_t s = 256 + lhs_partials_bytes(P);
-  // accumulator volume: general-path observations and / or all but one lattice term
-  if (P.n_general || P.args.nterm > 1) s += vol_bytes(lhs) + align_up(P.proj_ws);
+  // accumulator volume: general-path observations, all but one lattice term, and / or the
+  // adjoint of rotated observations (cell-coefficient kernel)
+  if (P.n_general || P.args.nterm > 1 || P.args.nrot > 0)
+    s += vol_bytes(lhs) + align_up(P.proj_ws);
   if (P.n_chain) s += vol_bytes(lhs);  // second buffer of the chained passes
   for (int k = 0; k < P.args.nrot; ++k) s += P.rot_bytes[k];
   if (P.nd) s += P.nd_bytes;
@@ -919,7 +922,7 @@ static LhsWs carve_lhs_ws(const ur_lhs *lhs, const LhsPlan &P, void *ws) {
   w.acc = nullptr;
   w.proj = nullptr;
   w.proj_bytes = 0;
-  if (P.n_general || P.args.nterm > 1) {
+  if (P.n_general || P.args.nterm > 1 || P.args.nrot > 0) {
     w.acc = (float *)c;
     c += vol_bytes(lhs);
     w.proj = c;
@@ -948,6 +951,7 @@ extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
 extern int jtv_block_rows, jtv_wide;  // admm.cu
 extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock, fast_diag_residue;  // lhs_fast.cu
+extern int fast_to, fast_segs;  // lhs_fast.cu
 static int g_cg_fuse = 1;
 static int g_r_reverse = 0;   // residual update sweeps the volume end -> start
 static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
@@ -1079,10 +1083,25 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
   }
   A.gr = GridReduce{w.partials, w.counter};
+  bool acc_live = A.acc != nullptr;  // the accumulator already holds terms of A'A v
+  bool rot_cells = A.nrot > 0 && w.acc != nullptr && (A.acc == nullptr || A.acc == w.acc);
   for (int k = 0; k < A.nrot; ++k) {  // u_k = tau C' S^2 C P v on the intermediate grid
     int rc = rot_forward_launch(UR_OP_ATA, P.rot_fwd[k], A.v, w.rot_u[k], st, A.done);
     if (rc) return rc;
     A.rot[k].u = w.rot_u[k];
+    rot_cells = rot_cells && rot_cell_enabled(A.rot[k]);
+  }
+  if (rot_cells) {
+    // adjoint pulls through the cell-coefficient kernel into the accumulator; D'D and the CG
+    // epilogue then run in the lean streaming kernel like any other pre-accumulated term
+    const int dim_y[3] = {A.nx, A.ny, A.nz};
+    for (int k = 0; k < A.nrot; ++k) {
+      int rc = rot_adjoint_launch(A.rot[k], dim_y, w.acc, acc_live ? 1 : 0, st, A.done);
+      if (rc) return rc;
+      acc_live = true;
+    }
+    A.acc = w.acc;
+    A.nrot = 0;
   }
   if (A.nrot > 0) variant = 1;  // the adjoint gather lives in the direct kernel
   if (A.nterm > 1 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc != nullptr &&
@@ -1092,7 +1111,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     for (int t = 0; t + 1 < A.nterm; ++t) {
       LhsArgs T = single_term(A, t, false);
       T.out = w.acc;
-      T.acc = (t > 0 || P.n_general) ? w.acc : nullptr;
+      T.acc = (t > 0 || acc_live) ? w.acc : nullptr;
       T.fin = FinalizeArgs{FIN_NONE, 0, UR_STOP_NONE, 0.0, nullptr, nullptr};
       int rc = lhs_fast_launch(LHS_TERM, T, false, st);
       if (rc) return rc;
@@ -1235,6 +1254,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_nd_fused = value != 0;
   } else if (!strcmp(name, "rot_fused")) {
     g_rot_fused = value != 0;
+  } else if (!strcmp(name, "rot_cell")) {
+    g_rot_cell = value == 8 ? 8 : (value != 0);
   } else if (!strcmp(name, "cg_fuse")) {
     g_cg_fuse = value != 0;
   } else if (!strcmp(name, "stream_pf")) {
@@ -1257,6 +1278,10 @@ extern "C" int ur_tune(const char *name, int value) {
     fast_lock = value != 0;
   } else if (!strcmp(name, "fast_diag_residue")) {  // debug: 0 drops the diagonal's residue term
     fast_diag_residue = value != 0;
+  } else if (!strcmp(name, "fast_to")) {
+    fast_to = value < 0 ? 0 : value;
+  } else if (!strcmp(name, "fast_segs")) {
+    fast_segs = value < 0 ? 0 : value;
   } else if (!strcmp(name, "fast_q")) {
     fast_q_units = value < 0 ? 0 : value;
   } else if (!strcmp(name, "stream_rpt")) {
