@@ -101,14 +101,18 @@ def test_fit_with_rigid_matches_reference_fixture(cuda):
     last = run.fit.last
     assert last['n_iter'] == int(g['n_iter'])
     q = np.array([o.rigid_q.cpu().tolist() for xc in x for o in xc])
-    # With rotated operators the adjoint is an atomic scatter (run-to-run summation order), and
-    # 29 interleaved Gauss-Newton steps with discrete line-search decisions amplify that noise:
-    # measured spread between two GPU runs 0.012 voxels on the smallest translation, so this is
-    # a trajectory-level check (single steps agree to 2e-5: test_update_rigid_vs_golden)
+    # 29 interleaved Gauss-Newton steps with discrete decisions (line search, borderline CG
+    # stops) amplify float32 rounding: the two deterministic adjoint kernels agree to 7e-8 on
+    # every operator of this scenario (scripts/dbg_cell_ops.py), yet their trajectories end
+    # 0.012 voxels apart on the smallest translation (the spread once measured between two runs
+    # of the atomic scatter): per-voxel gather q within 2.5e-4 / image 1.1e-2 of the reference,
+    # per-cell adjoint 1.2e-2 / 5.6e-2, objective within 7e-4 in both
+    # (scripts/dbg_fit_rigid.py).  Hence a trajectory-level check; single steps agree to 2e-5
+    # (test_update_rigid_vs_golden) and single operators to 1e-5 (test_gpu_ops.py).
     assert np.allclose(q, g['q'], atol=0.03), (q, g['q'])
     assert np.allclose(R.cpu().numpy(), g['R'], atol=0.03)
-    assert np.allclose(last['obj'].cpu().numpy(), g['obj'], rtol=2e-2)
-    assert U.rel_l2(dat_y, g['dat_y']) < 3e-2
+    assert np.allclose(last['obj'].cpu().numpy(), g['obj'], rtol=5e-3)
+    assert U.rel_l2(dat_y, g['dat_y']) < 1e-1
 
 
 def test_fit_unified_rigid_needs_a_basis(cuda):

@@ -307,36 +307,46 @@ __global__ void __launch_bounds__(kCellThreads, 2)
   extern __shared__ __align__(16) float cell_sm[];
   float *coef = cell_sm;  // [8][PL]
   int4 *rows = reinterpret_cast<int4 *>(cell_sm + 8 * PL);  // (i, j, k0, k1) of the live rows
-  __shared__ int s_nrows;
+  __shared__ int s_nrows, s_box[6];
   if (done && *done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.z * TX, y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
   // sample positions of the owned cells: [x0 - 1, x0 + TX) x [y0 - 1, y0 + TY) x [z0 - 1, z0 + TZ)
   const float bl[3] = {(float)(x0 - 1), (float)(y0 - 1), (float)(z0 - 1)};
   const float bh[3] = {(float)(x0 + TX), (float)(y0 + TY), (float)(z0 + TZ)};
-  int ilo[3], ihi[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {  // bounding box of the pre-image in intermediate indices
+  if (tid < 3) {  // bounding box of the pre-image in intermediate indices, one axis per thread
+    const int a = tid;
     const float base = T.inv[4 * a + 0] * bl[0] + T.inv[4 * a + 1] * bl[1] +
                        T.inv[4 * a + 2] * bl[2] + T.inv[4 * a + 3];
     const float dx = T.inv[4 * a + 0] * (float)(TX + 1), dy = T.inv[4 * a + 1] * (float)(TY + 1),
                 dz = T.inv[4 * a + 2] * (float)(TZ + 1);
     const float lo = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.06f;
     const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.06f;
-    ilo[a] = lo > 0.f ? (lo > 1e9f ? 1 << 30 : (int)ceilf(lo)) : 0;
-    ihi[a] = hi < (float)(T.n[a] - 1) ? (hi < -1e9f ? -2 : (int)floorf(hi)) : T.n[a] - 1;
+    s_box[a] = lo > 0.f ? (lo > 1e9f ? 1 << 30 : (int)ceilf(lo)) : 0;
+    s_box[3 + a] = hi < (float)(T.n[a] - 1) ? (hi < -1e9f ? -2 : (int)floorf(hi)) : T.n[a] - 1;
+    if (a == 0) s_nrows = 0;
   }
+  __syncthreads();
+  const int ilo[3] = {s_box[0], s_box[1], s_box[2]}, ihi[3] = {s_box[3], s_box[4], s_box[5]};
   const int ni = ihi[0] - ilo[0] + 1, nj = ihi[1] - ilo[1] + 1;
   const bool any = ni > 0 && nj > 0 && ihi[2] >= ilo[2];
   const int nbox = any ? ni * nj : 0;
   if (nbox > kCellMaxRows) asm volatile("trap;");  // the host checks the operator: never taken
-  if (tid == 0) s_nrows = 0;
+  constexpr int YS = TY / (NW / 8);  // y rows per warp in the output phase
+  const int xr = warp & 7, ys = (warp >> 3) * YS;
+  const int x = x0 + xr, z = z0 + lane;
+  if (nbox == 0) {  // nothing maps into this tile (outside the observation's field of view)
+    if (!accumulate && x < nx && lane < TZ && z < nz) {
+      float *o = out + ((size_t)x * ny + (y0 + ys)) * nz + z;
+      for (int yy = 0; yy < YS && y0 + ys + yy < ny; ++yy, o += nz) *o = 0.f;
+    }
+    return;
+  }
 
   // ---- phase 0: zero the coefficients; list of the rows (i, j) that can hit the tile with
   // their k range (list order is irrelevant: rows of one pass never share a cell) ----
   for (int q = tid; q < 8 * PL / 4; q += kCellThreads)
     reinterpret_cast<float4 *>(coef)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
   for (int r = tid; r < nbox; r += kCellThreads) {
     const int ii = r / nj, i = ilo[0] + ii, j = ilo[1] + (r - ii * nj);
     const float fi = (float)i, fj = (float)j;
@@ -358,6 +368,9 @@ __global__ void __launch_bounds__(kCellThreads, 2)
   const int sub = lane >> 4, l16 = lane & 15;  // a half warp per candidate row
   const int ncol = T.cell_ncol;
   const int n12 = T.n[1] * T.n[2];
+  // the pull's FOV test can only fail in cells next to a face of the recon grid
+  const bool face = x0 == 0 || y0 == 0 || z0 == 0 || x0 + TX >= nx || y0 + TY >= ny ||
+                    z0 + TZ >= nz;
   for (int c = 0; c < ncol && nrows > 0; ++c) {
     for (int rp = 2 * warp + sub; rp < nrows; rp += 2 * NW) {
       const int4 e = rows[rp];
@@ -378,8 +391,10 @@ __global__ void __launch_bounds__(kCellThreads, 2)
         const float cx = fmaf(T.m[2], fk, bx) + T.m[3];
         const float cy = fmaf(T.m[6], fk, by) + T.m[7];
         const float cz = fmaf(T.m[10], fk, bz) + T.m[11];
-        const bool ok = cx > -kRotFovTol && cx < fmax_x && cy > -kRotFovTol && cy < fmax_y &&
-                        cz > -kRotFovTol && cz < fmax_z;
+        bool ok = true;
+        if (face)
+          ok = cx > -kRotFovTol && cx < fmax_x && cy > -kRotFovTol && cy < fmax_y &&
+               cz > -kRotFovTol && cz < fmax_z;
         const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
         const int lx = (int)fx - (x0 - 1), ly = (int)fy - (y0 - 1), lz = (int)fz - (z0 - 1);
         if (ok && (unsigned)lx < (unsigned)CX && (unsigned)ly < (unsigned)CY &&
@@ -403,9 +418,6 @@ __global__ void __launch_bounds__(kCellThreads, 2)
   }
 
   // ---- phase 2: voxel (x, y, z) <- coefficient (a, b, c) of the cell at (x - a, y - b, z - c) ----
-  constexpr int YS = TY / (NW / 8);  // y rows per warp
-  const int xr = warp & 7, ys = (warp >> 3) * YS;
-  const int x = x0 + xr, z = z0 + lane;
   if (x < nx && lane < TZ && z < nz) {
     // the voxel's own cell (its corner 0,0,0) at y = y0 + ys
     const float *cc = coef + ((xr + 1) * CY + ys + 1) * CZ + lane + 1;
