@@ -876,9 +876,13 @@ static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
 
 static int pitch4(const ur_lhs *lhs) { return (lhs->dim_y[2] + 3) / 4 * 4; }
 
-// one volume with its z rows padded to a multiple of 4 elements (>= the dense volume)
+// one volume with its z rows padded to a multiple of 4 elements (>= the dense volume), plus a
+// skew so that the volumes of a workspace do not sit at the same offset modulo a large power
+// of two (256^3 and 512^3 volumes are powers of two themselves): ur_tune("vol_skew")
+static size_t g_vol_skew = 0;
 static size_t vol_bytes(const ur_lhs *lhs) {
-  return align_up((size_t)lhs->dim_y[0] * lhs->dim_y[1] * pitch4(lhs) * sizeof(float));
+  return align_up((size_t)lhs->dim_y[0] * lhs->dim_y[1] * pitch4(lhs) * sizeof(float)) +
+         g_vol_skew;
 }
 
 // lhs workspace: [counter 256B | partials | acc volume (general) | proj ws]
@@ -1254,6 +1258,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_nd_fused = value != 0;
   } else if (!strcmp(name, "rot_fused")) {
     g_rot_fused = value != 0;
+  } else if (!strcmp(name, "vol_skew")) {
+    g_vol_skew = value < 0 ? 0 : (size_t)value / 256 * 256;
   } else if (!strcmp(name, "rot_cell")) {
     g_rot_cell = value == 8 ? 8 : (value != 0);
   } else if (!strcmp(name, "cg_fuse")) {
