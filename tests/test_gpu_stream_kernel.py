@@ -222,6 +222,53 @@ def test_cg_fused_direction_update(cuda, case, stop, tol, kern):
     assert U.rel_l2(res[1][0], xo) < U.REL_TOL
 
 
+@pytest.mark.parametrize('to,segs', [(7, 0), (7, 3), (6, 2), (5, 0), (8, 4)])
+@pytest.mark.parametrize('case', [((40, 96, 260), (33, 90, 251), 0, 4, 0.05),
+                                  ((44, 90, 136), None, 1, 2, 0.0),
+                                  ((36, 70, 264), (30, 61, 250), 2, 4, 0.1)])
+def test_lean_kernel_tile_rows_and_segments(cuda, case, to, segs):
+    """Run-time tile shape of the lean kernel: `to` output rows per 8-row tile (the other warps
+    idle; the automatic choice takes 7 rows when that fills more CTA slots, e.g. 444 instead of
+    384 at 256^3) and the number of lock-step segments per column.  Matvec against the direct
+    kernel (bitwise across tile shapes) and the oracle, fused CG iterates against the oracle."""
+    from oracle.nitorch_shim.core import optim as OO
+    from unires_b200 import _project, optim
+    dim_y, fov, axis, factor, scl = case
+    obs_o, rec_o, obs_g, rec_g = _make(dim_y, fov, axis, factor, scl, cuda)
+    g = torch.Generator().manual_seed(17)
+    v = torch.rand(dim_y, generator=g) - 0.4
+    b = torch.rand(dim_y, generator=g) * 0.1
+    x0 = torch.rand(dim_y, generator=g)
+    vx = torch.ones(3)
+    ref = P.proj('AtA', v, [obs_o], rec_o, rho=1.3, vx_y=vx)
+    xo = x0.clone()
+    OO.cg(A=lambda q: P.proj('AtA', q, [obs_o], rec_o, rho=1.3, vx_y=vx), b=b, x=xo, max_iter=8,
+          tolerance=0.0, stop='max_gain')
+    op = _project.LhsOperator([obs_g], rec_g, rho=1.3, vx_y=[1.0, 1.0, 1.0])
+    try:
+        _tune('fast_rpt', 1)
+        base = op(v.to(cuda)).clone()
+        assert _last_path() == 2
+        _tune('fast_to', to)
+        _tune('fast_segs', segs)
+        dot = torch.zeros(1, dtype=torch.float64, device=cuda)
+        out = op(v.to(cuda), dot=dot).clone()
+        assert _last_path() == 2
+        x = x0.clone().to(cuda)
+        optim.cg(A=op, b=b.to(cuda), x=x, max_iter=8, tolerance=0.0, stop='max_gain')
+        n_it = optim.cg.last.n_iter
+    finally:
+        _tune('fast_to', 0)
+        _tune('fast_segs', 0)
+        _reset()
+    assert torch.equal(out, base)  # the arithmetic of a voxel does not depend on the tiling
+    assert U.rel_l2(out, ref) < 1e-5
+    want = torch.sum(v * ref, dtype=torch.float64).item()
+    assert abs(dot.item() - want) < 1e-5 * abs(want)
+    assert n_it == OO.cg.last_n_iter
+    assert U.rel_l2(x, xo) < U.REL_TOL
+
+
 @pytest.mark.parametrize('stop,tol', [('max_gain', 1e-3), ('residual', 1e-3), ('max_gain', 0.0)])
 @pytest.mark.parametrize('case', [
     # dim_y (nz % 4 != 0), fov, thick axis (None = denoising), factor, scl
