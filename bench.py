@@ -87,6 +87,11 @@ def matvec_kernel_desc(path):
         3: 'rotated operator: rot_forward_kernel (tile pull + slice profile + scaling + transposed '
            'profile in shared memory) + lhs_rot_kernel (gather adjoint + DtD + p.Ap); the launch '
            'pair is timed as one matvec; instruction-issue bound, not HBM bound (DESIGN.md 4.3)',
+        5: 'rotated operator: rot_forward_kernel (tile pull + slice profile + scaling + transposed '
+           'profile in shared memory) + rot_adjoint_cell_kernel (adjoint pull through per-cell '
+           'corner coefficients in shared memory, deterministic) + lhs_fast_kernel (DtD + p.Ap with '
+           'the adjoint as accumulator); the three launches are timed as one matvec; '
+           'instruction-issue bound, not HBM bound (DESIGN.md 4.3)',
         4: 'several decimated axes: nd_down_spec_kernel (v -> low-resolution image) + '
            'nd_up_spec_kernel (expansion + DtD + p.Ap); the launch pair is timed as one matvec',
         1: 'lhs_stream_kernel (generic TMA streaming kernel)',

@@ -69,13 +69,21 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
  * "cg_graph": 0 disables the CUDA-graph replay of repeated solves; "nd_fused": 0
  * sends multi-axis lattice operators through chained single-axis passes;
  * "rot_fused": 0 routes rotated operators through the unfused pull / conv /
- * conv' / push chain instead of the in-tile kernels (A/B and tests).
+ * conv' / push chain instead of the in-tile kernels (A/B and tests);
+ * "rot_cell": adjoint pull of rotated operators through per-cell corner
+ * coefficients (1, default), with eight colour passes forced (8, test hook),
+ * or by the per-voxel candidate gather (0); "fast_to" / "fast_segs": output
+ * rows per tile (0 automatic, <= 8 x rows per thread) and lock-step segments
+ * per column (0 automatic) of the lean kernel; "vol_skew": bytes added to
+ * every workspace volume (placement experiment, default 0).
  * Unknown names return UR_ERR_ARG.                                          */
 int ur_tune(const char *name, int value);
 /* Which kernel served the most recent lhs launch of this process:
  * 0 direct, 1 generic TMA streaming kernel, 2 lean specialised TMA kernel,
  * 3 rotated-operator kernels (forward tile kernel + quad gather adjoint),
- * 4 multi-axis lattice kernels (nd_down + nd_up through the low-res image). */
+ * 4 multi-axis lattice kernels (nd_down + nd_up through the low-res image),
+ * 5 rotated-operator kernels (forward tile kernel + cell-coefficient adjoint
+ *   into the accumulator) followed by the lean TMA kernel.                  */
 int ur_last_lhs_path(void);
 
 /* ---------------------------------------------------------------- finite

@@ -958,7 +958,8 @@ extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock, fast_diag_re
 extern int fast_to, fast_segs;  // lhs_fast.cu
 static int g_cg_fuse = 1;
 static int g_r_reverse = 0;   // residual update sweeps the volume end -> start
-static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel  // fold the direction / x updates into the matvec when possible
+static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel, 3 rotated: gather kernel,
+                             // 4 nd_down + nd_up, 5 rotated: cell adjoint + lean kernel  // fold the direction / x updates into the matvec when possible
 
 struct MatvecProfile {
   bool on = false;
@@ -1107,6 +1108,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
     A.acc = w.acc;
     A.nrot = 0;
   }
+  const bool via_cells = rot_cells;
   if (A.nrot > 0) variant = 1;  // the adjoint gather lives in the direct kernel
   if (A.nterm > 1 && (variant == 0 ? g_lhs_variant : variant) == 0 && w.acc != nullptr &&
       lean_supports(mode, A, st)) {
@@ -1130,7 +1132,7 @@ static int launch_lhs(int mode, const ur_lhs *lhs, const LhsPlan &P, const LhsWs
   if (variant != 1 || mode == LHS_COMBINE) {
     int rc = UR_ERR_UNSUPPORTED;
     if (variant != 2 || lean_only) rc = lhs_fast_launch(mode, A, false, st);
-    g_last_path = 2;
+    g_last_path = via_cells ? 5 : 2;  // 5: rotated terms through the cell adjoint + lean pass
     if (rc == UR_ERR_UNSUPPORTED && lean_only) {
       set_error("fused energy-rule sweeps need the lean TMA kernel");
       return UR_ERR_CUDA;
