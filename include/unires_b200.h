@@ -74,8 +74,11 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
  * coefficients (1, default), with eight colour passes forced (8, test hook),
  * or by the per-voxel candidate gather (0); "fast_to" / "fast_segs": output
  * rows per tile (0 automatic, <= 8 x rows per thread) and lock-step segments
- * per column (0 automatic) of the lean kernel; "vol_skew": bytes added to
- * every workspace volume (placement experiment, default 0).
+ * per column (0 automatic) of the lean kernel; "l2_hints": L2 eviction
+ * priorities of the fused CG iteration (bit 0, default on: vectors touched
+ * once per launch are evict_first; bit 1: the residual is evict_last);
+ * "vol_skew": bytes added to every workspace volume (placement experiment,
+ * default 0).
  * Unknown names return UR_ERR_ARG.                                          */
 int ur_tune(const char *name, int value);
 /* Which kernel served the most recent lhs launch of this process:

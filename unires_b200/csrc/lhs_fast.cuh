@@ -66,6 +66,8 @@ struct FastArgs {
                 // columns then march in step and share their halos through L2); 0: contiguous
                 // ranges of q_units units in (column, unit) order
   int pfd;      // planes prefetched into L2 ahead of the ring's issue front
+  int l2_stream, l2_keep;  // L2 eviction priority (L2_*) of the once-per-launch vectors (v, x,
+                           // p_out, out) and of the residual ring's source
   int to;       // rows of a tile that are OUTPUT (<= 8 RPT; the threads of the other rows idle): a
                 // shorter tile makes more columns, so that columns x segments fills the CTA slots
   const float *v;
@@ -132,6 +134,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// the same with an L2 eviction priority (l2_policy, common.cuh)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
 
@@ -210,6 +221,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   }
   __syncthreads();
 
+  const uint64_t pol_s = l2_policy(a.l2_stream), pol_k = l2_policy(a.l2_keep);
   float beta_c = 0.f, alpha_c = 0.f;
   if (COMBINE) {
     beta_c = (float)a.fin.st->beta;
@@ -352,11 +364,11 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
         if (COMBINE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(ip_ba, (COMBINE ? 2u : 1u) * box_bytes);
         if (a.march_y) {
-          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, iq, o0 - 1);
-          if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, iq, o0 - 1);
+          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, iq, o0 - 1, pol_s);
+          if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, iq, o0 - 1, pol_k);
         } else {
-          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, o0 - 1, iq);
-          if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, o0 - 1, iq);
+          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, o0 - 1, iq, pol_s);
+          if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, o0 - 1, iq, pol_k);
         }
         ip_pa += PLANE_B;
         ip_ba += 8u;
@@ -407,8 +419,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
 #pragma unroll
           for (int i = 0; i < RPT; ++i)
             if (act[i])
-              xr[h][i] = *reinterpret_cast<const float4 *>(a.xup + (goff_c + h * a.gs_m +
-                                                                      i * a.gs_o));
+              xr[h][i] = ldg_hint4(a.xup + (goff_c + h * a.gs_m + i * a.gs_o), pol_s);
         }
       }
     }
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
               if (cap_cur) cur[i] = pn;
               if (c_own && act[i]) {
                 const int gi = goff_c + i * a.gs_o;
-                *reinterpret_cast<float4 *>(a.p_out + gi) = pn;
+                stg_hint4(a.p_out + gi, pn, pol_s);
               }
               if (x_fused && c_own && act[i]) {
                 const int gi = goff_c + i * a.gs_o;
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 xn.y = __fadd_rn(xr[h][i].y, __fmul_rn(alpha_c, po.y));
                 xn.z = __fadd_rn(xr[h][i].z, __fmul_rn(alpha_c, po.z));
                 xn.w = __fadd_rn(xr[h][i].w, __fmul_rn(alpha_c, po.w));
-                *reinterpret_cast<float4 *>(a.xup + gi) = xn;
+                stg_hint4(a.xup + gi, xn, pol_s);
               }
             }
             if (h_has) {
@@ -496,8 +507,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
             for (int i = 0; i < RPT; ++i) {
               xr[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (x_fused && q_own && act[i])
-                xr[h][i] = *reinterpret_cast<const float4 *>(a.xup + (goff_c + 2 * a.gs_m +
-                                                                        i * a.gs_o));
+                xr[h][i] = ldg_hint4(a.xup + (goff_c + 2 * a.gs_m + i * a.gs_o), pol_s);
             }
             arr_ra += PLANE_B;
             if (arr_ra == rring_end) arr_ra = rring_base;
@@ -693,8 +703,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
                 *reinterpret_cast<float4 *>(a.out + gi) =
                     make_float4(val[0], val[1], val[2], val[3]);
               } else if (MODE == LHS_PLAIN || MODE == LHS_COMBINE) {
-                *reinterpret_cast<float4 *>(a.out + gi) =
-                    make_float4(val[0], val[1], val[2], val[3]);
+                stg_hint4(a.out + gi, make_float4(val[0], val[1], val[2], val[3]), pol_s);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   part += (double)__fmul_rn(cmpv(cur[i], k), val[k]);

@@ -325,9 +325,12 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
     cg_update_r_kernel(float *__restrict__ r, const float *__restrict__ Ap, size_t n,
                        const double *alpha_ptr, const int *done, GridReduce gr, FinalizeArgs fin,
-                       int reverse) {
+                       int reverse, int l2_hints) {
   __shared__ double s_red[kMaxWarps];
   if (done && *done) return;
+  // A p is read once (evict_first), r is what the next matvec and residual update read again
+  const uint64_t pol_s = l2_policy((l2_hints & 1) ? L2_FIRST : L2_NORMAL);
+  const uint64_t pol_k = l2_policy((l2_hints & 2) ? L2_LAST : L2_NORMAL);
   const float alpha = (float)(*alpha_ptr);
   double part = 0.0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(256)
         const size_t i = i0 + u * stride;
         idx[u] = reverse ? n4 - 1 - i : i;
         if (i < n4) {
-          rv[u] = r4[idx[u]];
-          av[u] = A4[idx[u]];
+          rv[u] = ldg_hint4(r + 4 * idx[u], pol_k);
+          av[u] = ldg_hint4(Ap + 4 * idx[u], pol_s);
         }
       }
 #pragma unroll
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(256)
         q.y = __fsub_rn(q.y, __fmul_rn(alpha, av[u].y));
         q.z = __fsub_rn(q.z, __fmul_rn(alpha, av[u].z));
         q.w = __fsub_rn(q.w, __fmul_rn(alpha, av[u].w));
-        r4[idx[u]] = q;
+        stg_hint4(r + 4 * idx[u], q, pol_k);
         part += (double)__fmul_rn(q.x, q.x) + (double)__fmul_rn(q.y, q.y) +
                 (double)__fmul_rn(q.z, q.z) + (double)__fmul_rn(q.w, q.w);
       }
@@ -955,7 +958,7 @@ extern int stream_rpt;          // lhs_stream.cu
 extern int stream_pf;           // lhs_stream.cu
 extern int jtv_block_rows, jtv_wide;  // admm.cu
 extern int fast_rpt, fast_depth, fast_q_units, fast_pfd, fast_lock, fast_diag_residue;  // lhs_fast.cu
-extern int fast_to, fast_segs;  // lhs_fast.cu
+extern int fast_to, fast_segs, g_l2_hints;  // lhs_fast.cu
 static int g_cg_fuse = 1;
 static int g_r_reverse = 0;   // residual update sweeps the volume end -> start
 static int g_last_path = 0;  // 0 direct, 1 generic streaming kernel, 2 lean kernel, 3 rotated: gather kernel,
@@ -1260,6 +1263,8 @@ extern "C" int ur_tune(const char *name, int value) {
     g_nd_fused = value != 0;
   } else if (!strcmp(name, "rot_fused")) {
     g_rot_fused = value != 0;
+  } else if (!strcmp(name, "l2_hints")) {
+    g_l2_hints = value & 3;
   } else if (!strcmp(name, "vol_skew")) {
     g_vol_skew = value < 0 ? 0 : (size_t)value / 256 * 256;
   } else if (!strcmp(name, "rot_cell")) {
@@ -1559,7 +1564,7 @@ static int cg_enqueue(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_w
     {  // r -= alpha Ap ; beta = rz'/rz
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
       cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
-                                                     g_r_reverse);
+                                                     g_r_reverse, fuse ? g_l2_hints : 0);
       UR_LAUNCH_CHECK();
     }
     {  // x = x_old + alpha p ; obj = 0.5 (A x - 2 b).x ; stop test
@@ -1604,7 +1609,7 @@ static int cg_enqueue(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_w
     if (fuse) {  // r -= alpha Ap ; beta = rz'/rz
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
       cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
-                                                     g_r_reverse);
+                                                     g_r_reverse, fuse ? g_l2_hints : 0);
       UR_LAUNCH_CHECK();
       continue;
     }
@@ -1621,12 +1626,12 @@ static int cg_enqueue(const ur_lhs *lhs, const float *d_b, float *d_x, void *d_w
       FinalizeArgs fin{FIN_BETA, it, stop, tol, cw.st, nullptr};
       if (vec) {
         cg_update_r_kernel<4><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
-                                                     g_r_reverse);
+                                                     g_r_reverse, fuse ? g_l2_hints : 0);
         UR_LAUNCH_CHECK();
         cg_update_xp_kernel<4><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
       } else {
         cg_update_r_kernel<1><<<vblocks, 256, 0, st>>>(cw.r, cw.Ap, n, &cw.st->alpha, done, gr, fin,
-                                                       0);
+                                                       0, 0);
         UR_LAUNCH_CHECK();
         cg_update_xp_kernel<1><<<vblocks, 256, 0, st>>>(d_x, cw.p, cw.r, n, cw.st, it);
       }
