@@ -75,8 +75,9 @@ int ur_profile_matvec_read(double *total_ms, int32_t *count,
  * or by the per-voxel candidate gather (0); "fast_to" / "fast_segs": output
  * rows per tile (0 automatic, <= 8 x rows per thread) and lock-step segments
  * per column (0 automatic) of the lean kernel; "l2_hints": L2 eviction
- * priorities of the fused CG iteration (bit 0, default on: vectors touched
- * once per launch are evict_first; bit 1: the residual is evict_last);
+ * priorities of the fused CG iteration (bit 0: stores and x loads are
+ * evict_first; bit 1: the residual is evict_last; bit 2: the TMA tiles of v
+ * are evict_first; default 0 -- measured a loss with concurrent channels);
  * "vol_skew": bytes added to every workspace volume (placement experiment,
  * default 0).
  * Unknown names return UR_ERR_ARG.                                          */

@@ -22,8 +22,10 @@ int fast_lock = 1;    // cut every column into the same segments (neighbours mar
 int fast_diag_residue = 1;  // carry the rounding residue of the stencil diagonal (debug knob)
 int fast_to = 0;      // output rows per tile (0 automatic; <= 8 rpt)
 int fast_segs = 0;    // segments per column override (0 automatic)
-int g_l2_hints = 1;   // ur_tune("l2_hints"): bit 0 = once-per-launch vectors evict_first (-2.6 % per CG
-                      // iteration at 256^3), bit 1 = the CG residual evict_last (no further gain);
+int g_l2_hints = 0;   // ur_tune("l2_hints"): L2 eviction priorities of the fused CG iteration -- bit 0:
+                      // stores and x loads evict_first, bit 1: residual evict_last, bit 2: TMA tiles of v
+                      // evict_first.  -2.6 % single stream at 256^3, but a LOSS with three channel
+                      // streams and at 384^3 (profiles/r02_l2_eviction_hints.txt): off by default;
                       // solver.cu applies the same to the residual update
 
 static bool a16(const void *p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; }
@@ -243,6 +245,7 @@ int lhs_fast_launch(int mode, const LhsArgs &A, bool dry_run, cudaStream_t st) {
   // only the fused CG iteration has a vector worth keeping (the residual); elsewhere: normal
   S.l2_stream = (combine && (g_l2_hints & 1)) ? L2_FIRST : L2_NORMAL;
   S.l2_keep = (combine && (g_l2_hints & 2)) ? L2_LAST : L2_NORMAL;
+  S.l2_v = (combine && (g_l2_hints & 4)) ? L2_FIRST : L2_NORMAL;
   S.pfd = fast_pfd < 0 ? 0 : fast_pfd;
 
   S.v = A.v;

@@ -66,8 +66,9 @@ struct FastArgs {
                 // columns then march in step and share their halos through L2); 0: contiguous
                 // ranges of q_units units in (column, unit) order
   int pfd;      // planes prefetched into L2 ahead of the ring's issue front
-  int l2_stream, l2_keep;  // L2 eviction priority (L2_*) of the once-per-launch vectors (v, x,
-                           // p_out, out) and of the residual ring's source
+  int l2_stream, l2_keep;  // L2 eviction priority (L2_*) of the vectors without reuse (x loads and
+                           // every store) and of the residual ring's source
+  int l2_v;                // ... and of the TMA tiles of v (their halos are re-read by neighbours)
   int to;       // rows of a tile that are OUTPUT (<= 8 RPT; the threads of the other rows idle): a
                 // shorter tile makes more columns, so that columns x segments fills the CTA slots
   const float *v;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
   __syncthreads();
 
   const uint64_t pol_s = l2_policy(a.l2_stream), pol_k = l2_policy(a.l2_keep);
+  const uint64_t pol_v = l2_policy(a.l2_v);
   float beta_c = 0.f, alpha_c = 0.f;
   if (COMBINE) {
     beta_c = (float)a.fin.st->beta;
@@ -364,10 +366,10 @@ __global__ void __launch_bounds__(NTHR, RPT == 1 ? 3 : 2)
         if (COMBINE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(ip_ba, (COMBINE ? 2u : 1u) * box_bytes);
         if (a.march_y) {
-          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, iq, o0 - 1, pol_s);
+          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, iq, o0 - 1, pol_v);
           if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, iq, o0 - 1, pol_k);
         } else {
-          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, o0 - 1, iq, pol_s);
+          tma_load_3d(ip_pa, &tmap_v, ip_ba, z0 - HZ, o0 - 1, iq, pol_v);
           if (COMBINE) tma_load_3d(ip_ra, &tmap_r, ip_ba, z0 - HZ, o0 - 1, iq, pol_k);
         }
         ip_pa += PLANE_B;

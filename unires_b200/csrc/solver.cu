@@ -1264,7 +1264,7 @@ extern "C" int ur_tune(const char *name, int value) {
   } else if (!strcmp(name, "rot_fused")) {
     g_rot_fused = value != 0;
   } else if (!strcmp(name, "l2_hints")) {
-    g_l2_hints = value & 3;
+    g_l2_hints = value & 7;
   } else if (!strcmp(name, "vol_skew")) {
     g_vol_skew = value < 0 ? 0 : (size_t)value / 256 * 256;
   } else if (!strcmp(name, "rot_cell")) {
