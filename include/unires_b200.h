@@ -164,6 +164,13 @@ typedef struct ur_proj {
  * pull/push degenerate to crop/zero-pad and the fused kernels apply.       */
 int ur_proj_is_lattice(const ur_proj *po);
 size_t ur_proj_workspace_bytes(const ur_proj *po);
+/* Rotated operators, adjoint pull (nitorch grid_push at unires/_project.py:172,
+ * 179) through per-cell corner coefficients: number of colour passes under
+ * which two intermediate voxels of one colour never fall into the same unit
+ * cell of the recon grid for the 3x4 row-major map `mat` (intermediate index
+ * -> recon voxel): 2 = parity of i+j+k, 8 = parities of i, j, k, 0 = neither
+ * (the per-voxel gather is used).  Host-only; no GPU needed.                */
+int ur_rot_cell_colours(const float mat[12]);
 /* _proj_apply (unires/_project.py:99-190): op in {A, At, AtA}.
  * A: in = y-space, out = x-space; At: reverse; AtA: y -> y.  out = result
  * (overwritten).                                                           */

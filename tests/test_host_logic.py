@@ -2,6 +2,7 @@
 profiles, stop-rule parsing, lattice detection, error behaviour on CPU tensors."""
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -95,3 +96,50 @@ def test_settings_defaults_match_reference_fields():
     for f in ('dim_x', 'mat_x', 'vx_x', 'dim_y', 'mat_y', 'vx_y', 'dim_yx', 'mat_yx', 'ratio',
               'smo_ker', 'rigid', 'scl', 'dim_thick', 'D_x', 'D_y'):
         assert hasattr(po, f)
+
+
+def _colour_matrix(rot, scale=(1.0, 1.0, 1.0), shift=(3.3, -1.7, 0.45)):
+    from unires_b200 import synth
+    m = synth.rigid_matrix(shift, rot).numpy()
+    m[:3, :3] = m[:3, :3] @ np.diag(scale)
+    return m[:3, :4].astype(np.float32)
+
+
+@pytest.mark.parametrize('rot,scale,want', [
+    ((0.05, -0.1, 0.1), (1, 1, 1), 2),        # notebook-sized rotation: parity of i + j + k
+    ((1e-5, 0.0, -2e-5), (1, 1, 1), 8),       # near identity: (1, 1, 0) maps within the float32
+                                              # slack of a unit cell, so parities of i, j, k
+    ((0.0, 0.0, 0.7853982), (1, 1, 1), 8),    # 45 degrees about z: (1, 0, 1) maps onto a unit cell
+    ((0.5, -0.4, 0.7), (1, 1, 1), 8),
+    ((0.05, 0.02, 0.0), (0.45, 1, 1), 0),     # strongly anisotropic map: per-voxel gather instead
+])
+def test_rot_cell_colouring_never_shares_a_cell(rot, scale, want):
+    """The cell-coefficient adjoint of rotated operators (csrc/rot.cu) scatters intermediate
+    voxels of ONE colour into shared-memory cells without atomics: ur_rot_cell_colours must only
+    return a colouring under which two voxels of one colour never fall into the same unit cell
+    of the recon grid.  Brute force over a 24^3 block of the intermediate lattice."""
+    import ctypes as C
+    from unires_b200 import _lib
+    mat = _colour_matrix(rot, scale)
+    ncol = _lib.lib.ur_rot_cell_colours(mat.ctypes.data_as(C.POINTER(C.c_float)))
+    assert ncol == want
+    if ncol == 0:
+        return
+    n = 24
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing='ij')
+    p = np.stack([i, j, k], -1).reshape(-1, 3).astype(np.float32)
+    # the kernel's float32 expression: fma(m2, k, fma(m1, j, m0 * i)) + t
+    c = (mat[:, 0] * p[:, :1] + mat[:, 1] * p[:, 1:2]) + mat[:, 2] * p[:, 2:3] + mat[:, 3]
+    cell = np.floor(c).astype(np.int64)
+    pi = p.astype(np.int64)
+    if ncol == 2:
+        colour = (pi.sum(1)) & 1
+    else:
+        colour = ((pi[:, 0] & 1) << 2) | ((pi[:, 1] & 1) << 1) | (pi[:, 2] & 1)
+    key = ((cell[:, 0] + 64) * 4096 + (cell[:, 1] + 64)) * 4096 + (cell[:, 2] + 64)
+    key = key * 8 + colour
+    assert len(np.unique(key)) == len(key), 'two voxels of one colour share a cell'
+    # and the colouring is needed: without it some cells do hold several voxels
+    if rot[2] > 0.7:
+        plain = key // 8
+        assert len(np.unique(plain)) < len(plain)

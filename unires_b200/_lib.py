@@ -104,6 +104,7 @@ _SIGNATURES = {
     'ur_apply_scaling': (C.c_int, [_p, _p, _i3, C.c_float, C.c_int, _p]),
     'ur_proj_is_lattice': (C.c_int, [C.POINTER(ur_proj)]),
     'ur_proj_workspace_bytes': (_sz, [C.POINTER(ur_proj)]),
+    'ur_rot_cell_colours': (C.c_int, [C.POINTER(C.c_float)]),
     'ur_proj_apply': (C.c_int, [C.c_int, C.POINTER(ur_proj), _p, _p, _p, _sz, _p]),
     'ur_proj_accumulate': (C.c_int, [C.c_int, C.POINTER(ur_proj), _p, _p, C.c_float, _p, _sz, _p]),
     'ur_lhs_workspace_bytes': (_sz, [C.POINTER(ur_lhs)]),

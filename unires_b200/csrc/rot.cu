@@ -463,6 +463,7 @@ static int rot_cell_colours(const float *mat) {
 
 bool rot_cell_enabled(const RotTerm &T) { return g_rot_cell && T.cell_ncol > 0; }
 
+
 static bool dirac_axis(const ::ur_proj *po, int a) {
   return po->ksize[a] == 1 && po->ratio[a] == 1;
 }
@@ -668,3 +669,8 @@ int rot_adjoint_launch(const RotTerm &T, const int dim_y[3], float *out, int acc
 }
 
 }  // namespace ur
+
+extern "C" int ur_rot_cell_colours(const float mat[12]) {
+  if (!mat) return 0;
+  return ur::rot_cell_colours(mat);
+}
