@@ -42,6 +42,22 @@ __device__ __forceinline__ float rot_pull(const float *__restrict__ v, const Rot
   const float *b = v + ((long long)ix * sx + (long long)iy * sy + iz);
   const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
   float acc = 0.f;
+  if (vx0 && vx1 && vy0 && vy1 && vz0 && vz1) {
+    // interior sample (almost all of them): eight unconditional loads in flight at once, summed
+    // in the same order as below
+    const float c000 = __ldg(b), c001 = __ldg(b + 1), c010 = __ldg(b + sy),
+                c011 = __ldg(b + sy + 1), c100 = __ldg(b + sx), c101 = __ldg(b + sx + 1),
+                c110 = __ldg(b + sx + sy), c111 = __ldg(b + sx + sy + 1);
+    acc += c000 * (w00 * wz0);
+    acc += c001 * (w00 * wz1);
+    acc += c010 * (w01 * wz0);
+    acc += c011 * (w01 * wz1);
+    acc += c100 * (w10 * wz0);
+    acc += c101 * (w10 * wz1);
+    acc += c110 * (w11 * wz0);
+    acc += c111 * (w11 * wz1);
+    return acc;
+  }
   if (vx0 && vy0 && vz0) acc += __ldg(b) * (w00 * wz0);
   if (vx0 && vy0 && vz1) acc += __ldg(b + 1) * (w00 * wz1);
   if (vx0 && vy1 && vz0) acc += __ldg(b + sy) * (w01 * wz0);
@@ -70,9 +86,11 @@ __global__ void __launch_bounds__(kRotThreads)
     rot_forward_kernel(const float *__restrict__ v, float *__restrict__ out, const RotFwd F,
                        const RotTile T, const int *done) {
   extern __shared__ float sm[];
+  __shared__ float s_ker[UR_MAX_TAPS];  // taps by LDS: the expansion indexes them per lane
   if (done && *done) return;
   const int ax = F.axis;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < UR_MAX_TAPS) s_ker[tid] = tid < F.K ? F.ker[tid] : 0.f;
   constexpr int NW = kRotThreads / 32;
   const int b3[3] = {(int)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x};
   int o0[3];  // first owned output index per axis
@@ -143,7 +161,7 @@ __global__ void __launch_bounds__(kRotThreads)
           float acc = 0.f;
           const bool valid = j >= 0 && j < F.nj;
           if (valid) {
-            for (int tt = 0; tt < F.K; ++tt) acc = fmaf(F.ker[tt], pulled[base + tt * astep], acc);
+            for (int tt = 0; tt < F.K; ++tt) acc = fmaf(s_ker[tt], pulled[base + tt * astep], acc);
             if (F.scl_axis >= 0) {
               const int g0 = ps0 + c0, g1 = ps1 + c1, g2 = ps2 + c2;
               const int js = F.scl_axis == ax ? j : (F.scl_axis == 0 ? g0 : (F.scl_axis == 1 ? g1 : g2));
@@ -186,7 +204,7 @@ __global__ void __launch_bounds__(kRotThreads)
         const int base = c0 * pp0 + c1 * pp1 + c2 - ca * astep;
         float acc = 0.f;
         for (int jl = jl_lo; jl <= jl_hi; ++jl)
-          acc = fmaf(F.ker[u - (j_min + jl) * F.r], lres[base + jl * astep], acc);
+          acc = fmaf(s_ker[u - (j_min + jl) * F.r], lres[base + jl * astep], acc);
         out[((size_t)(o0[0] + c0) * F.nyx[1] + (o0[1] + c1)) * F.nyx[2] + (o0[2] + c2)] =
             F.weight * acc;
       }
