@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-bash scripts/r2_gpu7.sh
+bash scripts/runs/r2_gpu7.sh
