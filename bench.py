@@ -370,7 +370,8 @@ def run_ours(args):
     # Per step: the observations of a subject are uploaded from pinned host memory, the initial
     # estimate is formed FROM THEM on the device (back-projection normalised by the operator's
     # column sums, what synth.make_scenario does on the host; round 1 uploaded it: 201 MB more
-    # per step), every channel is solved and the reconstruction is downloaded.
+    # per step; one pass per channel through ur_backproject when the observations are lattice
+    # aligned), every channel is solved and the reconstruction is downloaded.
     numa = bind_to_gpu_numa_node(local)
     hx = [[o.dat.cpu().pin_memory() for o in xc] for xc in sc.x]
     hy = [torch.empty(dim, dtype=torch.float32).pin_memory() for _ in range(C)]
@@ -383,10 +384,16 @@ def run_ours(args):
                                     sc.x[c][0].po, method=sett.method)[0, 0].clamp_min(1e-3)
                for c in range(C)]
 
+    inv_den, bp_ops = None, None
+    if den is not None:  # one-pass back-projection (ur_backproject) for lattice observations
+        inv_den = [1.0 / d for d in den]
+        bp_ops = [_project.LhsOperator(sc.x[c], sc.y[c], method=sett.method, do=sett.do_proj,
+                                       rho=rho, vx_y=vx) for c in range(C)]
+
     def init_y(x, y, c):
         if den is None:
             y[c].dat.copy_(x[c][0].dat)
-        else:
+        elif not _update._backproject(x[c], y[c].dat, bp_ops[c], inv_den[c]):
             num = _project._proj_apply('At', x[c][0].dat[None, None], x[c][0].po,
                                        method=sett.method)[0, 0]
             torch.div(num, den[c], out=y[c].dat)

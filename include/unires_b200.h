@@ -250,6 +250,15 @@ int ur_admm_rhs(float *d_b, const float *d_w, const float *d_z,
 int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, float *d_b,
                       const float *d_w, const float *d_z, float lam, float rho,
                       ur_stream stream);
+/* Back-projection of the observations of one channel in ONE pass, lattice
+ * aligned observations only (else UR_ERR_UNSUPPORTED, nothing launched):
+ *   out = scale .* sum_n An' x_n      (no tau_n; d_scale may be NULL)
+ * With scale = 1 / (A' 1) this is the normalised back-projection used as the
+ * device-side initial estimate of a freshly uploaded subject (the role of
+ * _init_y_dat, unires/_core.py:371-399, in the host pipeline: the estimate
+ * is formed from the uploaded observations instead of being uploaded).      */
+int ur_backproject(const ur_lhs *lhs, const float *const *d_x, float *d_out,
+                   const float *d_scale, ur_stream stream);
 /* y += a * x (float32) */
 int ur_axpy(float *d_y, const float *d_x, float a, size_t n, ur_stream stream);
 

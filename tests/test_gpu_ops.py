@@ -422,3 +422,34 @@ def test_lhs_several_observations_with_rotated_operators(cuda, dim_y, combo):
     optim.cg(A=op, b=b.to(cuda), x=xg, max_iter=12, tolerance=1e-3, stop='max_gain')
     assert optim.cg.last.n_iter == OO.cg.last_n_iter
     assert U.rel_l2(xg, xo) < U.REL_TOL
+
+
+def test_backproject_one_pass_equals_general_adjoint(cuda):
+    """ur_backproject: out = scale * sum_n An' x_n in one pass for lattice-aligned observations
+    (the device-side initial estimate of the host pipeline) against the operator's own adjoint;
+    rotated observations are declined (nothing launched)."""
+    from unires_b200 import _project, _update, struct, synth
+    cfg = synth.scaled(synth.CONFIGS['sr3_256'], (40, 48, 56))
+    g = torch.Generator().manual_seed(9)
+    for c in range(3):
+        dim_x, mat_x, dim_y, mat_y = synth.geometry(cfg, c)
+        for rigid, scl in ((None, 0.0), (None, 0.07),
+                           (synth.rigid_matrix((1.0, -0.5, 0.25), (0.03, 0.0, -0.02)), 0.0)):
+            po = _project._proj_info(dim_y, mat_y, dim_x, mat_x, rigid=rigid, prof_ip=2,
+                                     prof_tp=0, scl=scl, device=cuda)
+            obs = struct._input(dat=torch.rand(tuple(po.dim_x), generator=g).to(cuda), tau=0.4,
+                                po=po)
+            rec = struct._output(dim=dim_y, mat=mat_y, lam=0.2)
+            lhs = _project.LhsOperator([obs], rec, rho=1.0, vx_y=[1.0, 1.0, 1.0])
+            scale = (torch.rand(dim_y, generator=g) + 0.5).to(cuda)
+            out = torch.full(dim_y, float('nan'), device=cuda)
+            ok = _update._backproject([obs], out, lhs, scale)
+            if rigid is not None:
+                assert not ok
+                continue
+            assert ok
+            want = _project._proj_apply('At', obs.dat[None, None], po)[0, 0] * scale
+            assert U.rel_l2(out, want) < 1e-6
+            plain = torch.empty(dim_y, device=cuda)
+            assert _update._backproject([obs], plain, lhs)
+            assert U.rel_l2(plain * scale, want) < 1e-6

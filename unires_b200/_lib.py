@@ -116,6 +116,7 @@ _SIGNATURES = {
     'ur_cg_update_xr': (C.c_int, [_p, _p, _p, _p, _sz, _p, _p, _p]),
     'ur_cg_update_p': (C.c_int, [_p, _p, _sz, _p, _p]),
     'ur_admm_rhs': (C.c_int, [_p, _p, _p, _i3, _f3, C.c_float, C.c_float, _p]),
+    'ur_backproject': (C.c_int, [C.POINTER(ur_lhs), C.POINTER(_p), _p, _p, _p]),
     'ur_admm_rhs_fused': (C.c_int, [C.POINTER(ur_lhs), C.POINTER(_p), _p, _p, _p, C.c_float,
                                     C.c_float, _p]),
     'ur_axpy': (C.c_int, [_p, _p, C.c_float, _sz, _p]),

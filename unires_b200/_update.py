@@ -145,6 +145,23 @@ def _rhs(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx, lhs=None):
                           _hs(rho), stream()))
 
 
+def _backproject(xc, out, lhs, scale=None):
+    """out = scale * sum_n An' x_n in one pass (`ur_backproject`; lattice-aligned observations).
+
+    With scale = 1 / (A' 1) this is the normalised back-projection `HostPipeline` users form as
+    the initial estimate of a freshly uploaded subject on the device (the role of
+    unires/_core.py:371-399 `_init_y_dat`, without uploading the estimate).  Returns False --
+    nothing launched -- when an observation is not lattice aligned (rotated operators: use
+    `_proj_apply('At')`)."""
+    dats = [require_cuda_f32(obs.dat, 'x.dat') for obs in xc]
+    rc = lib.ur_backproject(C.byref(lhs.c), _ptr_array(dats), ptr(out),
+                            ptr(scale) if scale is not None else None, stream())
+    if rc == _lib.UR_ERR_UNSUPPORTED:
+        return False
+    check(rc)
+    return True
+
+
 def _solve_channel(xc, yc, z_c, w_c, rho, tmp, sett, dim, vx):
     """RHS + device-resident CG of one channel (in place on yc.dat).  Returns its CgInfo."""
     stop = getattr(sett, 'cgs_stop', 'max_gain')

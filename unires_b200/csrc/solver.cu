@@ -813,6 +813,38 @@ __global__ void __launch_bounds__(256)
   *reinterpret_cast<float4 *>(b + i) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// out = scale .* sum_n An' x_n (lattice observations), one pass: the back-projected initial
+// estimate A'x / A'1 of a freshly uploaded subject (scale = 1 / A'1, or NULL for plain A'x)
+__global__ void __launch_bounds__(256)
+    backproject4_kernel(float *__restrict__ out, const float *__restrict__ scale,
+                        const RhsArgs a) {
+  __shared__ AtTerm s_term[kMaxFused];
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  {
+    const int nwords = a.nterm * (int)(sizeof(AtTerm) / 4);
+    const int *src = reinterpret_cast<const int *>(a.term);
+    int *dst = reinterpret_cast<int *>(s_term);
+    for (int k = tid; k < nwords; k += blockDim.x * blockDim.y) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int z = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z;
+  if (z >= a.nz || y >= a.ny) return;
+  const size_t i = ((size_t)x * a.ny + y) * a.nz + z;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (scale) sc = *reinterpret_cast<const float4 *>(scale + i);
+  float vals[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < a.nterm; ++t) {
+    float e[4];
+    eval_at4(s_term[t], x, y, z, e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vals[k] += e[k];
+  }
+  *reinterpret_cast<float4 *>(out + i) =
+      make_float4(vals[0] * sc.x, vals[1] * sc.y, vals[2] * sc.z, vals[3] * sc.w);
+}
+
 static int make_plan(const ur_lhs *lhs, LhsPlan *P) {
   UR_REQUIRE(lhs, "ur_lhs is NULL");
   UR_REQUIRE(lhs->dim_y[0] > 0 && lhs->dim_y[1] > 0 && lhs->dim_y[2] > 0, "ur_lhs: bad dim_y");
@@ -1355,13 +1387,11 @@ extern "C" int ur_lhs_apply(const ur_lhs *lhs, const float *d_v, float *d_out, d
   return launch_lhs(LHS_PLAIN, lhs, P, w, A, 0, st);
 }
 
-extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, float *d_b,
-                                 const float *d_w, const float *d_z, float lam, float rho,
-                                 ur_stream stream) {
-  UR_REQUIRE(lhs && d_x && d_b && d_w && d_z, "ur_admm_rhs_fused: null pointer");
+// sum_n tau_n An' x_n of lattice observations as RhsArgs terms (unit_tau: without the tau_n)
+static int rhs_terms(const ur_lhs *lhs, const float *const *d_x, bool unit_tau, RhsArgs *out) {
   UR_REQUIRE(lhs->n_obs >= 1 && lhs->n_obs <= UR_MAX_OBS, "ur_admm_rhs_fused: bad n_obs");
   if (lhs->n_obs > kMaxFused) return UR_ERR_UNSUPPORTED;
-  RhsArgs A;
+  RhsArgs &A = *out;
   memset(&A, 0, sizeof(A));
   A.nx = lhs->dim_y[0];
   A.ny = lhs->dim_y[1];
@@ -1369,10 +1399,9 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
   A.ivx = 1.f / lhs->vx[0];
   A.ivy = 1.f / lhs->vx[1];
   A.ivz = 1.f / lhs->vx[2];
-  A.lam = lam;
-  A.rho = rho;
   for (int n = 0; n < lhs->n_obs; ++n) {
     UR_REQUIRE(d_x[n] != nullptr, "ur_admm_rhs_fused: observation %d is NULL", n);
+    const float tau_n = unit_tau ? 1.f : lhs->tau[n];
     AtTerm &T = A.term[A.nterm];
     T.x = d_x[n];
     T.a_even = T.a_odd = 1.f;
@@ -1380,7 +1409,7 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
       memset(&T.L, 0, sizeof(T.L));
       T.L.axis = -1;
       T.L.scl_axis = -1;
-      T.L.tau = lhs->tau[n];
+      T.L.tau = tau_n;
       for (int a = 0; a < 3; ++a) {
         T.shift[a] = 0;
         T.dimx[a] = lhs->dim_y[a];
@@ -1389,8 +1418,8 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
       const ur_proj *po = &lhs->obs[n];
       int rc = validate_proj(po);
       if (rc) return rc;
-      if (!lattice_term(po, lhs->tau[n], &T.L)) return UR_ERR_UNSUPPORTED;
-      float wgt = lhs->tau[n];  // At applies each thin-axis coefficient once (AtA: twice)
+      if (!lattice_term(po, tau_n, &T.L)) return UR_ERR_UNSUPPORTED;
+      float wgt = tau_n;  // At applies each thin-axis coefficient once (AtA: twice)
       for (int a = 0; a < 3; ++a) {
         T.shift[a] = (int)lrintf(po->mat[4 * a + 3]);
         T.dimx[a] = po->dim_x[a];
@@ -1404,6 +1433,31 @@ extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, flo
     }
     ++A.nterm;
   }
+  return UR_OK;
+}
+
+extern "C" int ur_backproject(const ur_lhs *lhs, const float *const *d_x, float *d_out,
+                              const float *d_scale, ur_stream stream) {
+  UR_REQUIRE(lhs && d_x && d_out, "ur_backproject: null pointer");
+  RhsArgs A;
+  int rc = rhs_terms(lhs, d_x, true, &A);
+  if (rc) return rc;
+  if (A.nz % 4 != 0 || !aligned16(d_out) || !aligned16(d_scale)) return UR_ERR_UNSUPPORTED;
+  dim3 block(32, 8, 1), grid(div_up(A.nz, 128), div_up(A.ny, 8), A.nx);
+  backproject4_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_out, d_scale, A);
+  UR_LAUNCH_CHECK();
+  return UR_OK;
+}
+
+extern "C" int ur_admm_rhs_fused(const ur_lhs *lhs, const float *const *d_x, float *d_b,
+                                 const float *d_w, const float *d_z, float lam, float rho,
+                                 ur_stream stream) {
+  UR_REQUIRE(lhs && d_x && d_b && d_w && d_z, "ur_admm_rhs_fused: null pointer");
+  RhsArgs A;
+  int rc = rhs_terms(lhs, d_x, false, &A);
+  if (rc) return rc;
+  A.lam = lam;
+  A.rho = rho;
   if (A.nz % 4 == 0 && aligned16(d_b) && aligned16(d_w) && aligned16(d_z)) {
     dim3 block(32, 8, 1), grid(div_up(A.nz, 128), div_up(A.ny, 8), A.nx);
     rhs_fused4_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_b, d_w, d_z, A);
